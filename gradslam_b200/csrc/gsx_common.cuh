@@ -1,0 +1,140 @@
+// Shared device helpers for libgsx (sm_100a).  Compiled with -fmad=false: every product and sum below
+// is rounded separately to fp32, in the association order written, so results are bit-identical to the
+// CPU oracle's canonical arithmetic (oracle/gsx_oracle.py).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <cstdio>
+
+namespace gsx {
+
+void set_error(const char *fmt, ...);
+
+#define GSX_CHECK_ARG(cond, ...)   \
+  do {                             \
+    if (!(cond)) {                 \
+      gsx::set_error(__VA_ARGS__); \
+      return 1;                    \
+    }                              \
+  } while (0)
+
+#define GSX_CHECK_LAUNCH(name)                                                    \
+  do {                                                                            \
+    cudaError_t e_ = cudaGetLastError();                                          \
+    if (e_ != cudaSuccess) {                                                      \
+      gsx::set_error("%s: launch failed: %s", name, cudaGetErrorString(e_));     \
+      return 2;                                                                   \
+    }                                                                             \
+  } while (0)
+
+constexpr int kNumSMs = 148;  // B200
+
+struct Rigid {  // row-major rotation + translation of a 4x4 rigid transform
+  float r[9];
+  float t[3];
+};
+
+__device__ __forceinline__ Rigid load_rigid(const float *__restrict__ T) {
+  Rigid a;
+  a.r[0] = __ldg(T + 0); a.r[1] = __ldg(T + 1); a.r[2] = __ldg(T + 2);  a.t[0] = __ldg(T + 3);
+  a.r[3] = __ldg(T + 4); a.r[4] = __ldg(T + 5); a.r[5] = __ldg(T + 6);  a.t[1] = __ldg(T + 7);
+  a.r[6] = __ldg(T + 8); a.r[7] = __ldg(T + 9); a.r[8] = __ldg(T + 10); a.t[2] = __ldg(T + 11);
+  return a;
+}
+
+__device__ __forceinline__ float dot3(float a0, float a1, float a2, float b0, float b1, float b2) {
+  return (a0 * b0 + a1 * b1) + a2 * b2;
+}
+
+// [R^T, (-R^T) t]   (kornia inverse_transformation as called at gradslam/slam/fusionutils.py:249)
+__device__ __forceinline__ Rigid rigid_inverse(const Rigid &a) {
+  Rigid o;
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+#pragma unroll
+    for (int j = 0; j < 3; ++j) o.r[i * 3 + j] = a.r[j * 3 + i];
+    o.t[i] = dot3(-a.r[0 * 3 + i], -a.r[1 * 3 + i], -a.r[2 * 3 + i], a.t[0], a.t[1], a.t[2]);
+  }
+  return o;
+}
+
+__device__ __forceinline__ float3 rigid_apply(const Rigid &a, float x, float y, float z) {
+  float3 q;
+  q.x = dot3(a.r[0], a.r[1], a.r[2], x, y, z) + a.t[0];
+  q.y = dot3(a.r[3], a.r[4], a.r[5], x, y, z) + a.t[1];
+  q.z = dot3(a.r[6], a.r[7], a.r[8], x, y, z) + a.t[2];
+  return q;
+}
+
+__device__ __forceinline__ float3 rotate(const Rigid &a, float x, float y, float z) {
+  float3 q;
+  q.x = dot3(a.r[0], a.r[1], a.r[2], x, y, z);
+  q.y = dot3(a.r[3], a.r[4], a.r[5], x, y, z);
+  q.z = dot3(a.r[6], a.r[7], a.r[8], x, y, z);
+  return q;
+}
+
+// closed-form inverse intrinsics (gradslam/geometry/projutils.py:405-450): eps added to fx, fy.
+struct KInv {
+  float k00, k02, k11, k12;
+};
+__device__ __forceinline__ KInv load_kinv(const float *__restrict__ K) {
+  const float fx = __ldg(K + 0), fy = __ldg(K + 5), cx = __ldg(K + 2), cy = __ldg(K + 6);
+  KInv k;
+  k.k00 = 1.0f / (fx + 1e-6f);
+  k.k11 = 1.0f / (fy + 1e-6f);
+  k.k02 = (-1.0f * cx) / (fx + 1e-6f);
+  k.k12 = (-1.0f * cy) / (fy + 1e-6f);
+  return k;
+}
+
+// local vertex of pixel (u=w, v=h) with depth d, zeroed where d <= 0 (rgbdimages.py:672-679)
+__device__ __forceinline__ float3 backproject(const KInv &k, float u, float v, float d) {
+  const float vf = d > 0.0f ? 1.0f : 0.0f;
+  float3 p;
+  p.x = ((k.k00 * u + k.k02) * d) * vf;
+  p.y = ((k.k11 * v + k.k12) * d) * vf;
+  p.z = d * vf;
+  return p;
+}
+
+// 128-bit record used for the per-pixel arg-min.  The workspace is zero-initialised and zero means
+// "no candidate", so a key (hi:lo) is stored as its bitwise complement and the arg-min over keys
+// becomes an atomic MAX over the stored 128-bit unsigned integers.
+struct __align__(16) U128 {
+  unsigned long long lo, hi;
+};
+
+__device__ __forceinline__ U128 cas128(U128 *addr, U128 expected, U128 desired) {
+  U128 old;
+  asm volatile(
+      "{\n\t.reg .b128 e, d, o;\n\t"
+      "mov.b128 e, {%2, %3};\n\t"
+      "mov.b128 d, {%4, %5};\n\t"
+      "atom.global.relaxed.gpu.cas.b128 o, [%6], e, d;\n\t"
+      "mov.b128 {%0, %1}, o;\n\t}"
+      : "=l"(old.lo), "=l"(old.hi)
+      : "l"(expected.lo), "l"(expected.hi), "l"(desired.lo), "l"(desired.hi), "l"(addr)
+      : "memory");
+  return old;
+}
+
+__device__ __forceinline__ U128 load128_relaxed(const U128 *addr) {
+  U128 v;
+  asm volatile("ld.relaxed.gpu.global.v2.u64 {%0, %1}, [%2];" : "=l"(v.lo), "=l"(v.hi) : "l"(addr) : "memory");
+  return v;
+}
+
+// arg-min over keys == max over complemented records
+__device__ __forceinline__ void atomic_min_key128(U128 *addr, unsigned long long key_hi, unsigned long long key_lo) {
+  const U128 mine{~key_lo, ~key_hi};
+  U128 cur = load128_relaxed(addr);  // a torn read is harmless: the CAS re-validates
+  while (mine.hi > cur.hi || (mine.hi == cur.hi && mine.lo > cur.lo)) {
+    const U128 old = cas128(addr, cur, mine);
+    if (old.hi == cur.hi && old.lo == cur.lo) break;
+    cur = old;
+  }
+}
+
+}  // namespace gsx

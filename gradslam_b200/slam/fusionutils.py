@@ -1,0 +1,216 @@
+"""PointFusion map update: projective data association + confidence-weighted surfel fusion.
+
+Host-side mirror of gradslam/slam/fusionutils.py (same function names, arguments, return types, errors and
+warnings).  `update_map_fusion` runs as two hand-written sm_100a kernels over an in-place, capacity-backed
+map (csrc/gsx_fusion.cu): no table is materialised, no whole-map clone / cat per frame, no host sync.  The
+table-returning helpers (`find_active_map_points`, `find_similar_map_points`,
+`find_best_unique_correspondences`, `fuse_with_map`) are kept for API parity and run the same arithmetic
+through the table kernels in csrc/gsx_tables.cu.
+"""
+import warnings
+from typing import Union
+
+import torch
+
+from .. import _C
+from ..structures.pointclouds import Pointclouds
+from ..structures.rgbdimages import RGBDImages, _frame_base
+
+__all__ = ["update_map_fusion", "update_map_aggregate"]
+
+
+# --------------------------------------------------------------------------------------------- small helpers
+def get_alpha(points: torch.Tensor, sigma: Union[torch.Tensor, float, int], dim: int = -1, keepdim: bool = False,
+              eps: float = 1e-7) -> torch.Tensor:
+    """Sample confidence alpha = clamp(exp(-|p|^2 / 2 sigma^2), eps, 1.01) (fusionutils.py:16-73).
+    Differentiable torch helper; inside the fused update alpha is evaluated by the merge kernel."""
+    if not torch.is_tensor(points):
+        raise TypeError("Expected input points to be of type torch.Tensor. Got {0} instead.".format(type(points)))
+    if not (torch.is_tensor(sigma) or isinstance(sigma, (float, int))):
+        raise TypeError("Expected input sigma to be of type torch.Tensor or float or int. Got {0} instead.".format(
+            type(sigma)))
+    if not isinstance(eps, float):
+        raise TypeError("Expected input eps to be of type float. Got {0} instead.".format(type(eps)))
+    if points.shape[dim] != 3:
+        raise ValueError("Expected length of dim-th ({0}th) dimension to be 3. Got {1} instead.".format(
+            dim, points.shape[dim]))
+    if torch.is_tensor(sigma) and sigma.ndim != 0:
+        raise ValueError("Expected sigma.ndim to be 0 (scalar). Got {0}.".format(sigma.ndim))
+    sq = torch.sum(points ** 2, dim, keepdim=keepdim)
+    return torch.clamp(torch.exp(-sq / (2 * (sigma ** 2))), min=eps, max=1.01)
+
+
+def _pair_checks(tensor1, tensor2, th, th_name, dim):
+    for name, t in (("tensor1", tensor1), ("tensor2", tensor2)):
+        if not torch.is_tensor(t):
+            raise TypeError("Expected input {} to be of type torch.Tensor. Got {} instead.".format(name, type(t)))
+    if not isinstance(th, (float, int)):
+        raise TypeError("Expected input {} to be of type float or int. Got {} instead.".format(th_name, type(th)))
+    if tensor1.shape != tensor2.shape:
+        raise ValueError("tensor1 and tensor2 should have the same shape, but had shapes {0} and {1} "
+                         "respectively.".format(tensor1.shape, tensor2.shape))
+    if tensor1.shape[dim] != 3:
+        raise ValueError("Expected length of input tensors' dim-th ({0}th) dimension to be 3. Got {1} "
+                         "instead.".format(dim, tensor1.shape[dim]))
+
+
+def are_points_close(tensor1: torch.Tensor, tensor2: torch.Tensor, dist_th: Union[float, int],
+                     dim: int = -1) -> torch.Tensor:
+    """||t1 - t2|| < dist_th along `dim` (fusionutils.py:76-130)."""
+    _pair_checks(tensor1, tensor2, dist_th, "dist_th", dim)
+    return (tensor1 - tensor2).norm(dim=dim) < dist_th
+
+
+def are_normals_similar(tensor1: torch.Tensor, tensor2: torch.Tensor, dot_th: Union[float, int],
+                        dim: int = -1) -> torch.Tensor:
+    """<t1, t2> > dot_th along `dim`; warns if the inputs were not unit length (fusionutils.py:133-195)."""
+    _pair_checks(tensor1, tensor2, dot_th, "dot_th", dim)
+    dots = (tensor1 * tensor2).sum(dim)
+    if dots.numel() > 0 and dots.max() > 1.001:
+        warnings.warn("Max of dot product was {0} > 1. Inputs were not normalized along dim ({1}). Was this "
+                      "intentional?".format(dots.max(), dim), RuntimeWarning)
+    return dots > dot_th
+
+
+# --------------------------------------------------------------------------------------------- workspaces
+class _Workspace:
+    """Per (device, B, H, W) scratch for the fusion kernels: arg-min records + scan state, zeroed once."""
+
+    _cache = {}
+
+    def __init__(self, device, B, H, W):
+        nbytes = _C.lib().gsx_fusion_workspace_bytes(B, H, W)
+        self.buf = torch.zeros(nbytes, dtype=torch.uint8, device=device)
+        self.epoch = 0
+
+    @classmethod
+    def get(cls, device, B, H, W):
+        key = (str(device), B, H, W)
+        ws = cls._cache.get(key)
+        if ws is None:
+            ws = cls(device, B, H, W)
+            cls._cache[key] = ws
+        return ws
+
+    def next_epochs(self, n=1):
+        first = self.epoch + 1
+        self.epoch += n
+        if self.epoch >= (1 << 30) - 1:  # wrap: start over on a clean buffer
+            self.buf.zero_()
+            self.epoch = n
+            first = 1
+        return first
+
+
+def _check_frame(rgbdimages):
+    if not isinstance(rgbdimages, RGBDImages):
+        raise TypeError("Expected rgbdimages to be of type gradslam.RGBDImages. Got {0}.".format(type(rgbdimages)))
+    if rgbdimages.shape[1] != 1:
+        raise ValueError("Expected rgbdimages to have sequence length of 1. Got {0}.".format(rgbdimages.shape[1]))
+
+
+def _launch_merge_append(pointclouds, frames, vmap, nmap, sigma):
+    """K4 on the current workspace state.  vmap/nmap: (B,1,H,W,3) maps to merge/append."""
+    B, _, H, W = frames.shape
+    P = H * W
+    dev = pointclouds.device
+    ws = _Workspace.get(dev, B, H, W)
+    depth, d_bs = _frame_base(frames.depth_image, P)
+    rgb, c_bs = _frame_base(frames.rgb_image, P * 3)
+    K = frames.intrinsics.contiguous()
+    st = pointclouds._store
+    cin = pointclouds._counts_dev[pointclouds._cur]
+    cout = pointclouds._counts_dev[pointclouds._cur ^ 1]
+    with torch.cuda.device(dev):
+        rc = _C.lib().gsx_fusion_merge_append(
+            _C.ptr(st["points"]), _C.ptr(st["normals"]), _C.ptr(st["colors"]), _C.ptr(st["features"]),
+            _C.ptr(cin), _C.ptr(cout), pointclouds.capacity, _C.ptr(depth), d_bs, _C.ptr(rgb), c_bs, _C.ptr(K), 16,
+            _C.ptr(vmap), _C.ptr(nmap), B, H, W, float(sigma), _C.ptr(ws.buf), ws.next_epochs(1),
+            _C.ptr(pointclouds._overflow_flag()), _C.stream_ptr(dev))
+    _C.check(rc, "gsx_fusion_merge_append")
+    pointclouds._mark_device_updated(pointclouds._bound + P)
+
+
+def _prepare_map(pointclouds, frames, with_features):
+    """Makes sure the map has storage for B elements with room for one more frame."""
+    B, _, H, W = frames.shape
+    if not pointclouds.has_points:
+        pointclouds.device = frames.device
+        pointclouds._allocate(B, 2 * H * W, 1 if with_features else 0)
+    elif len(pointclouds) != B:
+        raise ValueError("Expected equal batch sizes for pointclouds and rgbdimages. Got {0} and {1} "
+                         "respectively.".format(len(pointclouds), B))
+    if pointclouds._bound + H * W > pointclouds.capacity:
+        pointclouds._host_counts()  # one sync tightens the bound before we decide to grow
+    pointclouds.reserve(pointclouds._bound + H * W)
+
+
+def _append_valid_pixels(pointclouds, frames, global_coordinates=True, sigma=0.6):
+    """Stable append of every valid pixel (K4 with no matches): update_map_aggregate / pointclouds_from_rgbdimages."""
+    _check_frame(frames)
+    frames = frames.to_channels_last()
+    _C.require_cuda(frames.depth_image, "depth_image")
+    had_points = pointclouds.has_points
+    with_features = pointclouds.has_features if had_points else False
+    _prepare_map(pointclouds, frames, with_features)
+    vmap = frames.global_vertex_map if global_coordinates else frames.vertex_map
+    nmap = frames.global_normal_map if global_coordinates else frames.normal_map
+    _launch_merge_append(pointclouds, frames, vmap, nmap, sigma)
+    return pointclouds
+
+
+def _fused_update(pointclouds, frames, dist_th, dot_th, sigma):
+    """K2/K3 then K4, in place."""
+    frames = frames.to_channels_last()
+    _C.require_cuda(frames.depth_image, "depth_image")
+    if frames.poses is None:
+        raise ValueError("rgbdimages must have poses for map fusion")
+    if pointclouds.has_points:
+        for what in ("normals", "colors", "features"):
+            if not getattr(pointclouds, "has_" + what):
+                raise ValueError("Pointclouds must have {} for map fusion, but did not.".format(what))
+        if pointclouds.num_features != 1:
+            raise ValueError("Pointclouds features must be a single confidence count per point for map fusion.")
+    B, _, H, W = frames.shape
+    P = H * W
+    _prepare_map(pointclouds, frames, True)
+    dev = pointclouds.device
+    vmap, nmap = frames.global_vertex_map, frames.global_normal_map
+    if pointclouds._bound > 0:
+        ws = _Workspace.get(dev, B, H, W)
+        st = pointclouds._store
+        poses, p_bs = frames.poses.contiguous(), 16
+        K = frames.intrinsics.contiguous()
+        with torch.cuda.device(dev):
+            rc = _C.lib().gsx_fusion_project_select(
+                _C.ptr(st["points"]), _C.ptr(st["normals"]), _C.ptr(st["features"]),
+                _C.ptr(pointclouds._counts_dev[pointclouds._cur]), pointclouds.capacity, pointclouds._bound,
+                _C.ptr(poses), p_bs, _C.ptr(K), 16, _C.ptr(vmap), _C.ptr(nmap), B, H, W, float(dist_th),
+                float(dot_th), _C.ptr(ws.buf), _C.stream_ptr(dev))
+        _C.check(rc, "gsx_fusion_project_select")
+    _launch_merge_append(pointclouds, frames, vmap, nmap, sigma)
+    return pointclouds
+
+
+# --------------------------------------------------------------------------------------------- public ops
+def update_map_aggregate(pointclouds: Pointclouds, rgbdimages: RGBDImages, inplace: bool = False) -> Pointclouds:
+    """Appends every valid live-frame pixel to the maps (fusionutils.py:725-758)."""
+    if not isinstance(pointclouds, Pointclouds):
+        raise TypeError("Expected pointclouds to be of type gradslam.Pointclouds. Got {0}.".format(type(pointclouds)))
+    if not isinstance(rgbdimages, RGBDImages):
+        raise TypeError("Expected rgbdimages to be of type gradslam.RGBDImages. Got {0}.".format(type(rgbdimages)))
+    if not inplace:
+        pointclouds = pointclouds.clone()
+    return _append_valid_pixels(pointclouds, rgbdimages, True)
+
+
+def update_map_fusion(pointclouds: Pointclouds, rgbdimages: RGBDImages, dist_th: Union[float, int],
+                      dot_th: Union[float, int], sigma: Union[torch.Tensor, float, int],
+                      inplace: bool = False) -> Pointclouds:
+    """PointFusion update of the maps with one live frame (fusionutils.py:761-789)."""
+    if not isinstance(pointclouds, Pointclouds):
+        raise TypeError("Expected pointclouds to be of type gradslam.Pointclouds. Got {0}.".format(type(pointclouds)))
+    _check_frame(rgbdimages)
+    if not inplace:
+        pointclouds = pointclouds.clone()
+    return _fused_update(pointclouds, rgbdimages, dist_th, dot_th, sigma)

@@ -1,0 +1,508 @@
+"""Pointclouds: batch of variable-length surfel maps (points, normals, colors, features/confidence).
+
+Host-side mirror of gradslam.Pointclouds (gradslam/structures/pointclouds.py:13-1467): same constructor,
+list / padded views, arithmetic helpers, `append_points`, `transform`, `pinhole_projection`, `clone`,
+`detach`, `to`, indexing.  The representation is different by design: instead of the
+reference's list <-> padded duality, rebuilt with `torch.cat` on every append, the map lives in ONE
+capacity-backed SoA store
+
+    points / normals / colors  (B, capacity, 3)      features  (B, capacity, C)      counts int32 (2, B)
+
+that the fusion kernels update IN PLACE.  Rows >= counts[b] are always zero, so `*_padded` is the
+zero-copy view `store[:, :max(counts)]` and `*_list[b]` is `store[b, :counts[b]]`.  The per-element sizes
+live on the device (the kernels bump them); the host copy is refreshed lazily, only when a caller asks
+for a shape-dependent view.
+"""
+from typing import List, Optional, Union
+
+import torch
+
+__all__ = ["Pointclouds"]
+
+_ATTRS = ("points", "normals", "colors", "features")
+
+
+class Pointclouds(object):
+    def __init__(self, points=None, normals=None, colors=None, features=None,
+                 device: Union[torch.device, str, None] = None):
+        super().__init__()
+        if not (points is None or isinstance(points, list) or torch.is_tensor(points)):
+            raise TypeError("Expected points to be of type list or tensor or None; got %r" % type(points))
+        for name, val in (("normals", normals), ("colors", colors), ("features", features)):
+            if not (val is None or isinstance(val, type(points))):
+                raise TypeError("Expected %s to be of same type as points (%r); got %r" % (name, type(points), type(val)))
+        if points is not None and len(points) == 0:
+            raise ValueError("len(points) (= 0) should be > 0")
+
+        self._store = {k: None for k in _ATTRS}  # capacity-backed tensors
+        self._counts_dev = None  # int32 (2, B): ping-pong; row self._cur is current
+        self._cur = 0
+        self._counts_host = None  # list[int] or None when stale
+        self._bound = 0  # host-side upper bound of max(counts) (valid even when _counts_host is stale)
+        self._overflow = None  # int32 device flag set by kernels if capacity was exceeded
+        self._B = 0
+        self._list_cache = {}
+
+        if isinstance(points, list):
+            shapes = [p.shape for p in points]
+            if any(p.ndim != 2 for p in points):
+                raise ValueError("ndim of all tensors in points list should be 2")
+            if any(s[-1] != 3 for s in shapes):
+                raise ValueError("last dim of all tensors in points should have shape 3 (X, Y, Z)")
+            self.device = torch.empty(0, device=device).device if device is not None else points[0].device
+            counts = [int(s[0]) for s in shapes]
+            if not (normals is None or [n.shape for n in normals] == shapes):
+                raise ValueError("normals tensors should have same shape as points tensors, but didn't")
+            if not (colors is None or [c.shape for c in colors] == shapes):
+                raise ValueError("colors tensors should have same shape as points tensors, but didn't")
+            if not (features is None or all(f.ndim == 2 for f in features)):
+                raise ValueError("ndim of all tensors in features list should be 2")
+            if not (features is None or [len(f) for f in features] == counts):
+                raise ValueError("number of features per pointcloud has to be equal to number of points")
+            if not (features is None or len(set(f.shape[-1] for f in features)) == 1):
+                raise ValueError("number of features per pointcloud has to be the same")
+            self._B = len(points)
+            cap = max(counts)
+            for key, lst in zip(_ATTRS, (points, normals, colors, features)):
+                if lst is None:
+                    continue
+                C = lst[0].shape[-1]
+                st = torch.zeros((self._B, cap, C), dtype=lst[0].dtype, device=self.device)
+                for b, x in enumerate(lst):
+                    if x.shape[0] > 0:
+                        st[b, : x.shape[0]] = x.to(self.device)
+                self._store[key] = st
+            self._set_counts(counts)
+        elif torch.is_tensor(points):
+            self.device = torch.empty(0, device=device).device if device is not None else points.device
+            if points.ndim != 3:
+                raise ValueError("points should have ndim=3, but had ndim={}".format(points.ndim))
+            if points.shape[-1] != 3:
+                raise ValueError("last dim of points should have shape 3 (X, Y, Z) but had shape %r" % (points.shape[-1]))
+            if points.shape[0] == 0:
+                raise ValueError("Batch size of 0 not supported yet. Got input points shape {}.".format(points.shape))
+            if not (normals is None or normals.shape == points.shape):
+                raise ValueError("normals tensor should have same shape as points tensor, but didn't: %r != %r"
+                                 % (normals.shape, points.shape))
+            if not (colors is None or colors.shape == points.shape):
+                raise ValueError("colors tensor should have same shape as points tensor, but didn't: %r != %r"
+                                 % (colors.shape, points.shape))
+            if not (features is None or features.ndim == 3):
+                raise ValueError("features should have ndim=3, but had ndim={}".format(features.ndim))
+            if not (features is None or features.shape[:-1] == points.shape[:-1]):
+                raise ValueError("first 2 dims of features tensor and points tensor should have same shape, but "
+                                 "didn't: %r != %r" % (features.shape[:-1], points.shape[:-1]))
+            self._B = points.shape[0]
+            for key, t in zip(_ATTRS, (points, normals, colors, features)):
+                self._store[key] = None if t is None else t.to(self.device)
+            self._set_counts([points.shape[1]] * self._B)
+        else:
+            self.device = torch.empty(0, device=device).device if device is not None else torch.device("cpu")
+
+    # ------------------------------------------------------------------ size bookkeeping
+    def _set_counts(self, counts: List[int]):
+        self._counts_host = [int(c) for c in counts]
+        self._bound = max(self._counts_host) if self._counts_host else 0
+        t = torch.tensor([self._counts_host, self._counts_host], dtype=torch.int32, device=self.device)
+        self._counts_dev = t
+        self._cur = 0
+        self._list_cache = {}
+
+    def _host_counts(self) -> List[int]:
+        """Per-element sizes on the host; synchronises with the device only if kernels changed them."""
+        if self._counts_host is None:
+            self._counts_host = [int(c) for c in self._counts_dev[self._cur].tolist()]
+            self._bound = max(self._counts_host)
+            if self._overflow is not None and int(self._overflow.item()) != 0:
+                raise RuntimeError("gradslam_b200: surfel map capacity exceeded; points were dropped")
+        return self._counts_host
+
+    @property
+    def capacity(self) -> int:
+        return 0 if self._store["points"] is None else int(self._store["points"].shape[1])
+
+    def _mark_device_updated(self, new_bound: int):
+        """Called by the fusion ops after kernels wrote counts into the other ping-pong row."""
+        self._cur ^= 1
+        self._counts_host = None
+        self._bound = min(int(new_bound), self.capacity)
+        self._list_cache = {}
+
+    def _allocate(self, B: int, capacity: int, features_dim: int = 1, dtype=torch.float32):
+        """Turns an EMPTY object into B empty maps with the given capacity (used by the fusion ops)."""
+        assert not self.has_points
+        self._B = int(B)
+        for key, C in (("points", 3), ("normals", 3), ("colors", 3), ("features", features_dim)):
+            if C > 0:
+                self._store[key] = torch.zeros((self._B, int(capacity), C), dtype=dtype, device=self.device)
+        self._set_counts([0] * self._B)
+
+    def _overflow_flag(self):
+        if self._overflow is None:
+            self._overflow = torch.zeros(1, dtype=torch.int32, device=self.device)
+        return self._overflow
+
+    def reserve(self, capacity: int):
+        """Grows every attribute store to at least `capacity` rows (amortised doubling, zero-filled)."""
+        cap = self.capacity
+        if capacity <= cap:
+            return
+        new_cap = max(int(capacity), 2 * cap)
+        for key in _ATTRS:
+            st = self._store[key]
+            if st is None:
+                continue
+            grown = torch.zeros((st.shape[0], new_cap, st.shape[2]), dtype=st.dtype, device=st.device)
+            if cap > 0:
+                grown[:, :cap] = st
+            self._store[key] = grown
+        self._list_cache = {}
+
+    # ------------------------------------------------------------------ protocol
+    def __len__(self):
+        return self._B
+
+    @property
+    def has_points(self):
+        return self._store["points"] is not None
+
+    @property
+    def has_normals(self):
+        return self._store["normals"] is not None
+
+    @property
+    def has_colors(self):
+        return self._store["colors"] is not None
+
+    @property
+    def has_features(self):
+        return self._store["features"] is not None
+
+    @property
+    def num_features(self):
+        return 0 if not self.has_features else self._store["features"].shape[-1]
+
+    @property
+    def num_points_per_pointcloud(self):
+        if not self.has_points:
+            return torch.tensor([0], device=self.device)
+        return self._counts_dev[self._cur].to(torch.int64)
+
+    @property
+    def equisized(self):
+        if not self.has_points:
+            return None
+        return len(set(self._host_counts())) == 1
+
+    @property
+    def _N(self):
+        return max(self._host_counts()) if self.has_points else 0
+
+    def _padded(self, key):
+        st = self._store[key]
+        return None if st is None else st[:, : self._N]
+
+    def _list(self, key):
+        st = self._store[key]
+        if st is None:
+            return None
+        if key not in self._list_cache:
+            self._list_cache[key] = [st[b, :c] for b, c in enumerate(self._host_counts())]
+        return self._list_cache[key]
+
+    points_padded = property(lambda self: self._padded("points"))
+    normals_padded = property(lambda self: self._padded("normals"))
+    colors_padded = property(lambda self: self._padded("colors"))
+    features_padded = property(lambda self: self._padded("features"))
+    points_list = property(lambda self: self._list("points"))
+    normals_list = property(lambda self: self._list("normals"))
+    colors_list = property(lambda self: self._list("colors"))
+    features_list = property(lambda self: self._list("features"))
+
+    @property
+    def nonpad_mask(self):
+        if not self.has_points:
+            return None
+        c = self._counts_dev[self._cur].to(torch.int64).view(-1, 1)
+        return torch.arange(self._N, device=self.device).view(1, -1) < c
+
+    # ------------------------------------------------------------------ setters (shape-preserving, as pointclouds.py:811-946)
+    def _assert_set_padded(self, value, first_2_dims_only=False):
+        if not torch.is_tensor(value):
+            raise TypeError("value must be torch.Tensor. Got {}".format(type(value)))
+        if not self.has_points:
+            raise ValueError("cannot set padded representation for an empty pointclouds object")
+        if self.device != torch.empty(0, device=value.device).device:
+            raise ValueError("value must have the same device as pointclouds object: {} vs {}".format(
+                value.device, self.device))
+        if value.ndim != 3:
+            raise ValueError("value.ndim should be 3. Got {}".format(value.ndim))
+        exp = (self._B, self._N) if first_2_dims_only else (self._B, self._N, 3)
+        got = tuple(value.shape[:2]) if first_2_dims_only else tuple(value.shape)
+        if got != exp:
+            raise ValueError("Expected value to have shape {}. Got {}".format(exp, tuple(value.shape)))
+
+    def _set_padded(self, key, value, first_2=False):
+        self._assert_set_padded(value, first_2)
+        st = self._store[key]
+        if st is None or st.shape[-1] != value.shape[-1] or st.dtype != value.dtype:
+            new = torch.zeros((self._B, max(self.capacity, self._N), value.shape[-1]), dtype=value.dtype,
+                              device=self.device)
+            self._store[key] = new
+            st = new
+        else:
+            # out-of-place for autograd friendliness: never mutate a tensor a caller may still hold
+            st = st.clone()
+            self._store[key] = st
+        st[:, : self._N] = value
+        self._list_cache = {}
+
+    def _assert_set_list(self, value, first_dim_only=False):
+        if not isinstance(value, list):
+            raise TypeError("value must be list of tensors. Got {}".format(type(value)))
+        if not self.has_points:
+            raise ValueError("cannot set list representation for an empty pointclouds object")
+        if len(value) != self._B:
+            raise ValueError("Expected value to have len {}. Got {}".format(self._B, len(value)))
+        for b, (v, c) in enumerate(zip(value, self._host_counts())):
+            if not torch.is_tensor(v):
+                raise TypeError("value must be list of tensors")
+            if v.ndim != 2 or v.shape[0] != c or (not first_dim_only and v.shape[1] != 3):
+                raise ValueError("Shape of tensor {} in value does not match pointcloud {}".format(b, b))
+
+    def _set_list(self, key, value, first_dim_only=False):
+        self._assert_set_list(value, first_dim_only)
+        C = value[0].shape[-1]
+        new = torch.zeros((self._B, max(self.capacity, self._N), C), dtype=value[0].dtype, device=self.device)
+        for b, v in enumerate(value):
+            new[b, : v.shape[0]] = v.to(self.device)
+        self._store[key] = new
+        self._list_cache = {}
+
+    points_padded = points_padded.setter(lambda self, v: self._set_padded("points", v))
+    normals_padded = normals_padded.setter(lambda self, v: self._set_padded("normals", v))
+    colors_padded = colors_padded.setter(lambda self, v: self._set_padded("colors", v))
+    features_padded = features_padded.setter(lambda self, v: self._set_padded("features", v, True))
+    points_list = points_list.setter(lambda self, v: self._set_list("points", v))
+    normals_list = normals_list.setter(lambda self, v: self._set_list("normals", v))
+    colors_list = colors_list.setter(lambda self, v: self._set_list("colors", v))
+    features_list = features_list.setter(lambda self, v: self._set_list("features", v, True))
+
+    # ------------------------------------------------------------------ indexing
+    def __getitem__(self, index):
+        if not self.has_points:
+            raise IndexError("Cannot index empty pointclouds object")
+        if isinstance(index, int):
+            idx = [index]
+        elif isinstance(index, slice):
+            idx = list(range(self._B))[index]
+        elif isinstance(index, list):
+            idx = index
+        elif isinstance(index, torch.Tensor):
+            if index.dim() != 1 or index.dtype.is_floating_point:
+                raise IndexError(index)
+            idx = index.nonzero().flatten().tolist() if index.dtype == torch.bool else index.tolist()
+        else:
+            raise IndexError(index)
+        pick = lambda lst: None if lst is None else [lst[i] for i in idx]
+        return Pointclouds(points=pick(self.points_list), normals=pick(self.normals_list),
+                           colors=pick(self.colors_list), features=pick(self.features_list))
+
+    # ------------------------------------------------------------------ arithmetic helpers (pointclouds.py:303-614)
+    def __add__(self, other):
+        try:
+            return self.clone().offset_(other)
+        except TypeError:
+            raise NotImplementedError("Pointclouds + {} currently not implemented.".format(type(other)))
+
+    def __sub__(self, other):
+        try:
+            return self.clone().offset_(other * -1)
+        except TypeError:
+            raise NotImplementedError("Pointclouds - {} currently not implemented.".format(type(other)))
+
+    def __mul__(self, other):
+        try:
+            return self.clone().scale_(other)
+        except TypeError:
+            raise NotImplementedError("Pointclouds * {} currently not implemented.".format(type(other)))
+
+    def __truediv__(self, other):
+        try:
+            return self.__mul__(1.0 / other)
+        except TypeError:
+            raise NotImplementedError("Pointclouds / {} currently not implemented.".format(type(other)))
+
+    def __matmul__(self, other):
+        if not torch.is_tensor(other):
+            raise NotImplementedError("Pointclouds @ {} currently not implemented.".format(type(other)))
+        if not ((other.ndim == 2 or other.ndim == 3) and (other.shape[-2:] == (3, 3) or other.shape[-2:] == (4, 4))):
+            raise ValueError(
+                "Unsupported shape for Pointclouds @ operand: {}\nUse tensor of shape (3, 3) or (B, 3, 3) for "
+                "rotations, or (4, 4) or (B, 4, 4) for transformations".format(other.shape))
+        if other.shape[-2:] == (3, 3):
+            return self.clone().rotate_(other, pre_multiplication=False)
+        return self.clone().transform_(other, pre_multiplication=False)
+
+    def rotate(self, rmat, *, pre_multiplication=True):
+        return self.clone().rotate_(rmat, pre_multiplication=pre_multiplication)
+
+    def transform(self, transform, *, pre_multiplication=True):
+        return self.clone().transform_(transform, pre_multiplication=pre_multiplication)
+
+    def pinhole_projection(self, intrinsics):
+        return self.clone().pinhole_projection_(intrinsics)
+
+    def _write_padded(self, key, value):
+        st = self._store[key].clone()
+        st[:, : self._N] = value
+        self._store[key] = st
+        self._list_cache = {}
+
+    def offset_(self, offset):
+        if not (torch.is_tensor(offset) or isinstance(offset, (float, int))):
+            raise TypeError("Operand should be tensor, float or int but was %r instead" % type(offset))
+        if not self.has_points:
+            return self
+        mask = self.nonpad_mask.to(self.points_padded.dtype).unsqueeze(-1)
+        self._write_padded("points", self.points_padded + offset * mask)
+        return self
+
+    def scale_(self, scale):
+        if not (torch.is_tensor(scale) or isinstance(scale, (float, int))):
+            raise TypeError("Operand should be tensor, float or int but was %r instead" % type(scale))
+        if not self.has_points:
+            return self
+        mask = self.nonpad_mask.to(self.points_padded.dtype).unsqueeze(-1)
+        self._write_padded("points", self.points_padded * scale * mask)
+        return self
+
+    def rotate_(self, rmat, *, pre_multiplication=True):
+        if not torch.is_tensor(rmat):
+            raise TypeError("Rotation matrix should be tensor, but was %r instead" % type(rmat))
+        if not ((rmat.ndim == 2 or rmat.ndim == 3) and rmat.shape[-2:] == (3, 3)):
+            raise ValueError("Rotation matrix should be of shape (3, 3) or (B, 3, 3), but was {} instead.".format(
+                rmat.shape))
+        if rmat.ndim == 3 and rmat.shape[0] != self._B:
+            raise ValueError("Rotation matrix batch size ({}) != Pointclouds batch size ({})".format(
+                rmat.shape[0], self._B))
+        if not self.has_points:
+            return self
+        if pre_multiplication:
+            rmat = rmat.transpose(-1, -2)
+        eq = "bij,jk->bik" if rmat.ndim == 2 else "bij,bjk->bik"
+        self._write_padded("points", torch.einsum(eq, self.points_padded, rmat))
+        if self.has_normals:
+            self._write_padded("normals", torch.einsum(eq, self.normals_padded, rmat))
+        return self
+
+    def transform_(self, transform, *, pre_multiplication=True):
+        if not torch.is_tensor(transform):
+            raise TypeError("transform should be tensor, but was %r instead" % type(transform))
+        if not ((transform.ndim == 2 or transform.ndim == 3) and transform.shape[-2:] == (4, 4)):
+            raise ValueError("transform should be of shape (4, 4) or (B, 4, 4), but was {} instead.".format(
+                transform.shape))
+        if transform.ndim == 3 and transform.shape[0] != self._B:
+            raise ValueError("transform batch size ({}) != Pointclouds batch size ({})".format(
+                transform.shape[0], self._B))
+        if not self.has_points:
+            return self
+        rmat = transform[..., :3, :3]
+        tvec = transform[..., :3, 3]
+        while tvec.ndim < 3:
+            tvec = tvec.unsqueeze(-2)
+        return self.rotate_(rmat, pre_multiplication=pre_multiplication).offset_(tvec)
+
+    def pinhole_projection_(self, intrinsics):
+        if not torch.is_tensor(intrinsics):
+            raise TypeError("intrinsics should be tensor, but was {} instead".format(type(intrinsics)))
+        if not ((intrinsics.ndim == 2 or intrinsics.ndim == 3) and intrinsics.shape[-2:] == (4, 4)):
+            raise ValueError("intrinsics should be of shape (4, 4) or (B, 4, 4), but was {} instead.".format(
+                intrinsics.shape))
+        if not self.has_points:
+            return self
+        from ..geometry import projutils
+
+        uv = projutils.project_points(self.points_padded, intrinsics)
+        mask = self.nonpad_mask.to(uv.dtype).unsqueeze(-1)
+        self._write_padded("points", projutils.homogenize_points(uv) * mask)
+        return self
+
+    # ------------------------------------------------------------------ copies / device moves
+    def _like(self, fn):
+        other = Pointclouds(device=self.device)
+        if not self.has_points:
+            return other
+        other._B = self._B
+        for key in _ATTRS:
+            st = self._store[key]
+            other._store[key] = None if st is None else fn(st)
+        other.device = other._store["points"].device
+        other._counts_dev = self._counts_dev.clone().to(other.device)
+        other._cur = self._cur
+        other._counts_host = None if self._counts_host is None else list(self._counts_host)
+        other._bound = self._bound
+        other._overflow = None if self._overflow is None else self._overflow.clone().to(other.device)
+        return other
+
+    def clone(self):
+        return self._like(lambda t: t.clone())
+
+    def detach(self):
+        return self._like(lambda t: t.detach().clone())
+
+    def to(self, device, copy: bool = False):
+        device = torch.empty(0, device=device).device
+        if not copy and self.device == device:
+            return self
+        other = self._like(lambda t: t.to(device, copy=True))
+        other.device = device
+        return other
+
+    def cpu(self):
+        return self.to(torch.device("cpu"))
+
+    def cuda(self):
+        return self.to(torch.device("cuda"))
+
+    # ------------------------------------------------------------------ growth
+    def append_points(self, pointclouds: "Pointclouds"):
+        """Appends another batch of clouds element-wise, in place (pointclouds.py:1117-1237)."""
+        if not isinstance(pointclouds, type(self)):
+            raise TypeError("Append object must be of type gradslam.Pointclouds, but was of type {}.".format(
+                type(pointclouds)))
+        if not (pointclouds.device == self.device):
+            raise ValueError("Device of pointclouds to append and to be appended must match: ({0} != {1})".format(
+                pointclouds.device, self.device))
+        if not pointclouds.has_points:
+            return self
+        if not self.has_points:
+            src = pointclouds.clone()
+            self._store, self._B = src._store, src._B
+            self._counts_dev, self._cur = src._counts_dev, src._cur
+            self._counts_host, self._bound, self._overflow = src._counts_host, src._bound, src._overflow
+            self._list_cache = {}
+            return self
+        if len(pointclouds) != len(self):
+            raise ValueError("Batch size of pointclouds to append and to be appended must match: ({0} != {1})".format(
+                len(pointclouds), len(self)))
+        for what in ("normals", "colors", "features"):
+            mine, theirs = getattr(self, "has_" + what), getattr(pointclouds, "has_" + what)
+            if mine != theirs:
+                raise ValueError("pointclouds to append and to be appended must either both have or not have {}: "
+                                 "({} != {})".format(what, theirs, mine))
+        if self.has_features and self.num_features != pointclouds.num_features:
+            raise ValueError("pointclouds to append and to be appended must have the same number of features: "
+                             "({0} != {1})".format(pointclouds.num_features, self.num_features))
+        mine, theirs = self._host_counts(), pointclouds._host_counts()
+        total = [a + b for a, b in zip(mine, theirs)]
+        self.reserve(max(total))
+        for key in _ATTRS:
+            dst, src = self._store[key], pointclouds._store[key]
+            if dst is None:
+                continue
+            for b in range(self._B):
+                if theirs[b] > 0:
+                    dst[b, mine[b]: total[b]] = src[b, : theirs[b]]
+        self._set_counts(total)
+        return self

@@ -1,0 +1,103 @@
+/* gsx.h — C ABI of libgsx.so, the B200 (sm_100a) engine behind gradslam's PointFusion / ICPSLAM hot path.
+ *
+ * gradslam (reference @44470ee) is pure Python on PyTorch tensor ops: it has no FFI/plugin layer of its
+ * own.  The boundary a maintainer would bind is therefore the set of tensor-op chains listed below; each
+ * entry point names the reference function(s) (file:line under /root/reference) whose arithmetic it
+ * replaces.  INTEGRATION.md shows the ctypes stub a gradslam maintainer would add at each site.
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes; no torch / C++ types.  All pointers are DEVICE pointers
+ *     (float32 data, int32/int64 tables) owned by the caller and borrowed for the duration of the call.
+ *   - `stream` is a cudaStream_t passed as void*; every call only ENQUEUES work on it (no device
+ *     synchronisation) unless the doc says it returns a host-visible count.
+ *   - return 0 on success, non-zero on invalid argument / launch failure; gsx_last_error() returns a
+ *     thread-local message for the last failure.
+ *   - images are channels-last: depth (B,L,H,W,1), rgb/vertex/normal (B,L,H,W,3).  Per-frame calls take
+ *     a base pointer for the frame plus the element stride (`*_bstride`, in floats) between batch elements,
+ *     so frame s of a (B,L,H,W,C) tensor is addressed without a copy.
+ *   - the surfel map is SoA with a fixed capacity: points/normals/colors (B,cap,3), ccounts (B,cap,1),
+ *     counts int32 (B,).  Rows >= counts[b] are never read.
+ *   - arithmetic is IEEE fp32 with NO fused multiply-add and a fixed association order (see DESIGN.md
+ *     "canonical arithmetic"), so every decision (threshold, pixel rounding, arg-min key) is bit-exact
+ *     against the CPU oracle.
+ */
+#ifndef GSX_H_
+#define GSX_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GSX_VERSION 100 /* 0.1.0 */
+
+int gsx_version(void);
+const char *gsx_last_error(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * K1  depth -> vertex / normal maps (+ posed "global" maps)
+ * replaces RGBDImages._compute_vertex_map / _compute_normal_map / _compute_global_vertex_map /
+ *          _compute_global_normal_map   gradslam/structures/rgbdimages.py:643-762
+ *          and projutils.inverse_intrinsics   gradslam/geometry/projutils.py:405-450
+ * depth (B,L,H,W) with element stride depth_bstride between b and H*W between l;
+ * intrinsics: B matrices 4x4 row-major, stride K_bstride; poses: B*L matrices, strides pose_bstride
+ * (between b) and 16 (between l), or NULL (global maps = local maps).  Any output may be NULL.
+ * Outputs are dense (B,L,H,W,3). */
+int gsx_backproject_normals_fwd(const float *depth, int64_t depth_bstride, const float *intrinsics,
+                                int64_t K_bstride, const float *poses, int64_t pose_bstride, int B, int L,
+                                int H, int W, float *vertex, float *normal, float *gvertex, float *gnormal,
+                                void *stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Fused PointFusion map update (K2+K3 and K4), one live frame for all B elements.
+ * replaces update_map_fusion = find_active_map_points + find_similar_map_points +
+ *          find_best_unique_correspondences + fuse_with_map (+ Pointclouds.append_points)
+ *          gradslam/slam/fusionutils.py:198-287, 290-411, 414-546, 580-722, 761-789;
+ *          gradslam/structures/pointclouds.py:526-614, 1117-1237
+ *
+ * Workspace: gsx_fusion_workspace_bytes(B,H,W) bytes, zero-filled ONCE by the caller before first use
+ * (cudaMemset 0); the kernels leave it clean for the next frame.  `epoch` must increase by one with
+ * every gsx_fusion_merge_append call on the same workspace, starting at 1.                        */
+int64_t gsx_fusion_workspace_bytes(int B, int H, int W);
+
+/* K2+K3: project every map point into the live camera, keep points that are in the frustum, close to
+ * the frame vertex they land on and with a similar normal, and reduce per pixel to the best candidate
+ * (largest confidence count, then smallest ray distance, then smallest index) with a 128-bit atomic
+ * min.  max_count = host upper bound on counts[b] (sizes the grid). */
+int gsx_fusion_project_select(const float *map_points, const float *map_normals, const float *map_ccounts,
+                              const int32_t *counts, int64_t capacity, int64_t max_count, const float *poses,
+                              int64_t pose_bstride, const float *intrinsics, int64_t K_bstride,
+                              const float *gvertex, const float *gnormal, int B, int H, int W, float dist_th,
+                              float dot_th, void *workspace, void *stream);
+
+/* K4: per pixel, merge the selected map point with the frame sample (confidence-weighted mean) or, for
+ * valid pixels without a match, append a new surfel in row-major pixel order (stable single-pass scan).
+ * counts_in -> counts_out (may not alias).  map_ccounts may be NULL for maps without confidence counts
+ * (ICPSLAM aggregation, gradslam/slam/fusionutils.py:725-758): then nothing is merged and every valid
+ * pixel is appended.  overflow_flag (int32, device) is set to 1 if capacity was
+ * exceeded (the surplus points are dropped). */
+int gsx_fusion_merge_append(float *map_points, float *map_normals, float *map_colors, float *map_ccounts,
+                            const int32_t *counts_in, int32_t *counts_out, int64_t capacity,
+                            const float *depth, int64_t depth_bstride, const float *rgb, int64_t rgb_bstride,
+                            const float *intrinsics, int64_t K_bstride, const float *gvertex,
+                            const float *gnormal, int B, int H, int W, double sigma, void *workspace,
+                            uint32_t epoch, int32_t *overflow_flag, void *stream);
+
+/* Whole-sequence driver with ground-truth poses: for s in [0,L): K1 -> K2/K3 -> K4, no host sync.
+ * replaces ICPSLAM.forward with odom='gt' + PointFusion._map   gradslam/slam/icpslam.py:99-138,
+ *          gradslam/slam/pointfusion.py:107-112
+ * depth (B,L,H,W), rgb (B,L,H,W,3) dense; poses (B,L,4,4) dense; intrinsics (B,4,4) dense.
+ * counts: int32 (2,B) ping-pong buffer; counts[0] holds the current sizes on entry; on return the
+ * current sizes are in counts[L & 1].  scratch_maps: 2*B*H*W*3 floats (gvertex, gnormal of one frame).
+ * epoch0 = first epoch to use (the call consumes L epochs). */
+int gsx_pointfusion_sequence_gt(float *map_points, float *map_normals, float *map_colors, float *map_ccounts,
+                                int32_t *counts, int64_t capacity, int64_t max_count0, const float *depth,
+                                const float *rgb, const float *intrinsics, const float *poses, int B, int L,
+                                int H, int W, float dist_th, float dot_th, double sigma, float *scratch_maps,
+                                void *workspace, uint32_t epoch0, int32_t *overflow_flag, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GSX_H_ */

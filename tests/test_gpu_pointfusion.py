@@ -1,0 +1,108 @@
+"""GPU parity: CUDA hot path (through the C ABI) vs the CPU oracle on identical seeded inputs."""
+import pytest
+import torch
+
+import gsx_oracle as oracle
+from gradslam_b200.synthetic import make_sequence
+
+pytestmark = pytest.mark.gpu
+
+
+def _dev():
+    return torch.device("cuda:0")
+
+
+def _frames(gs, rgb, depth, K, poses, dev):
+    return gs.RGBDImages(rgb.to(dev), depth.to(dev), K.to(dev), None if poses is None else poses.to(dev))
+
+
+@pytest.mark.parametrize("shape", [(2, 3, 48, 64), (1, 2, 120, 160), (3, 1, 33, 47)])
+def test_frame_maps_bit_exact(shape):
+    """K1 against oracle.frame_maps: all four maps identical to the last bit (canonical arithmetic)."""
+    import gradslam_b200 as gs
+
+    B, L, H, W = shape
+    rgb, depth, K, poses = make_sequence(B, L, H, W, seed=3)
+    fr = _frames(gs, rgb, depth, K, poses, _dev())
+    ref = oracle.frame_maps(depth, K, poses)
+    for name, got in (("vertex", fr.vertex_map), ("normal", fr.normal_map), ("gvertex", fr.global_vertex_map),
+                      ("gnormal", fr.global_normal_map)):
+        assert torch.equal(got.cpu(), ref[name]), name
+    # without poses the global maps are the local maps
+    fr2 = _frames(gs, rgb, depth, K, None, _dev())
+    assert torch.equal(fr2.global_vertex_map.cpu(), ref["vertex"])
+    assert torch.equal(fr2.global_normal_map.cpu(), ref["normal"])
+
+
+def _compare_maps(pc, ref_map, exact_structure=True):
+    got = [int(c) for c in pc.num_points_per_pointcloud.tolist()]
+    assert got == ref_map.counts()
+    for b in range(len(got)):
+        # positions / normals / colours of never-merged points are bit-exact; merged ones differ only through
+        # expf (CUDA) vs exp (CPU) in the confidence weight: <= a few ulp.  Tolerance: 1e-6 abs/rel.
+        torch.testing.assert_close(pc.points_list[b].cpu(), ref_map.points[b], rtol=1e-6, atol=1e-6)
+        torch.testing.assert_close(pc.normals_list[b].cpu(), ref_map.normals[b], rtol=1e-6, atol=1e-6)
+        torch.testing.assert_close(pc.colors_list[b].cpu(), ref_map.colors[b], rtol=1e-6, atol=1e-6)
+        torch.testing.assert_close(pc.features_list[b].cpu(), ref_map.ccounts[b], rtol=1e-6, atol=1e-7)
+
+
+@pytest.mark.parametrize("shape", [(2, 4, 48, 64), (1, 5, 120, 160), (3, 3, 64, 64)])
+def test_pointfusion_gt_sequence_matches_oracle(shape):
+    import gradslam_b200 as gs
+
+    B, L, H, W = shape
+    rgb, depth, K, poses = make_sequence(B, L, H, W, seed=0)
+    slam = gs.PointFusion(odom="gt", device=_dev())
+    pc, out_poses = slam(_frames(gs, rgb, depth, K, poses, _dev()))
+    ref = oracle.run_slam(rgb, depth, K, poses, odom="gt")
+    _compare_maps(pc, ref.map)
+    assert torch.equal(out_poses.cpu(), poses)
+
+
+def test_step_api_equals_sequence_call():
+    """slam.step() frame by frame (per-frame C calls) == slam(frames) (single C call)."""
+    import gradslam_b200 as gs
+
+    B, L, H, W = 2, 4, 48, 64
+    rgb, depth, K, poses = make_sequence(B, L, H, W, seed=5)
+    dev = _dev()
+    slam = gs.PointFusion(odom="gt", device=dev)
+    frames = _frames(gs, rgb, depth, K, poses, dev)
+    pc_seq, _ = slam(frames)
+    pc = gs.Pointclouds(device=dev)
+    for s in range(L):
+        pc, _ = slam.step(pc, frames[:, s], None, inplace=True)
+    assert pc.num_points_per_pointcloud.tolist() == pc_seq.num_points_per_pointcloud.tolist()
+    for b in range(B):
+        assert torch.equal(pc.points_list[b], pc_seq.points_list[b])
+        assert torch.equal(pc.features_list[b], pc_seq.features_list[b])
+        assert torch.equal(pc.colors_list[b], pc_seq.colors_list[b])
+    # not-inplace step leaves the input map untouched
+    before = [p.clone() for p in pc.points_list]
+    pc2, _ = slam.step(pc, frames[:, 0], None, inplace=False)
+    for b in range(B):
+        assert torch.equal(pc.points_list[b], before[b])
+    assert pc2 is not pc
+
+
+def test_ragged_and_empty_inputs():
+    """All-invalid depth for one element (its map stays empty), tiny images, single frame."""
+    import gradslam_b200 as gs
+
+    B, L, H, W = 2, 3, 16, 24
+    rgb, depth, K, poses = make_sequence(B, L, H, W, seed=7)
+    depth[1] = 0.0  # element 1 never sees a valid depth
+    slam = gs.PointFusion(odom="gt", device=_dev())
+    pc, _ = slam(_frames(gs, rgb, depth, K, poses, _dev()))
+    ref = oracle.run_slam(rgb, depth, K, poses, odom="gt")
+    assert ref.map.counts()[1] == 0
+    _compare_maps(pc, ref.map)
+
+
+def test_cpu_tensors_are_refused():
+    import gradslam_b200 as gs
+
+    rgb, depth, K, poses = make_sequence(1, 1, 16, 16, seed=0)
+    fr = gs.RGBDImages(rgb, depth, K, poses)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        fr.vertex_map
