@@ -10,7 +10,8 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "_lib", "libgsx.so")
+# GSX_LIB_PATH selects another build of the same ABI (kernel tuning variants); never a fallback.
+LIB_PATH = os.environ.get("GSX_LIB_PATH") or os.path.join(_HERE, "_lib", "libgsx.so")
 
 c_f32p = ctypes.c_void_p
 c_i32p = ctypes.c_void_p
@@ -28,6 +29,7 @@ SIGNATURES = {
     "gsx_backproject_normals_fwd": (
         c_int, [c_vp, c_i64, c_vp, c_i64, c_vp, c_i64, c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "gsx_fusion_workspace_bytes": (c_i64, [c_int, c_int, c_int]),
+    "gsx_fusion_workspace_stats_offset": (c_i64, [c_int, c_int, c_int]),
     "gsx_fusion_project_select": (
         c_int, [c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_vp, c_i64, c_vp, c_i64, c_vp, c_vp, c_int, c_int, c_int,
                 c_float, c_float, c_vp, c_vp]),
@@ -35,8 +37,8 @@ SIGNATURES = {
         c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_vp, c_i64, c_vp, c_i64, c_vp, c_i64, c_vp, c_vp, c_int,
                 c_int, c_int, c_double, c_vp, c_u32, c_vp, c_vp]),
     "gsx_pointfusion_sequence_gt": (
-        c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int,
-                c_float, c_float, c_double, c_vp, c_vp, c_u32, c_vp, c_vp]),
+        c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_int,
+                c_int, c_float, c_float, c_double, c_vp, c_vp, c_u32, c_vp, c_vp]),
 }
 
 _lib = None

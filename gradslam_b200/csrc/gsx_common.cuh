@@ -129,7 +129,7 @@ __device__ __forceinline__ U128 load128_relaxed(const U128 *addr) {
 // arg-min over keys == max over complemented records
 __device__ __forceinline__ void atomic_min_key128(U128 *addr, unsigned long long key_hi, unsigned long long key_lo) {
   const U128 mine{~key_lo, ~key_hi};
-  U128 cur = load128_relaxed(addr);  // a torn read is harmless: the CAS re-validates
+  U128 cur{0ull, 0ull};  // optimistic: most pixels see a single candidate, so expect "empty" first
   while (mine.hi > cur.hi || (mine.hi == cur.hi && mine.lo > cur.lo)) {
     const U128 old = cas128(addr, cur, mine);
     if (old.hi == cur.hi && old.lo == cur.lo) break;

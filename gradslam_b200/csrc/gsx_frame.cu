@@ -1,5 +1,6 @@
-// K1: depth -> local/global vertex and normal maps.  One thread per pixel, outputs staged through shared
-// memory so every map is written with coalesced 16-byte stores.
+// K1: depth -> local/global vertex and normal maps.  One thread per pixel; per-image constants (inverse
+// intrinsics, pose) are computed once per CTA into shared memory; outputs are staged through shared memory
+// so every map is written with coalesced 16-byte stores.
 // Reference op chain: gradslam/structures/rgbdimages.py:643-762 (see include/gsx.h).
 #include "gsx_common.cuh"
 #include "../../include/gsx.h"
@@ -20,75 +21,76 @@ struct FrameArgs {
 };
 
 __device__ __forceinline__ float3 vertex_at(const float *__restrict__ dimg, const KInv &k, int h, int w, int W) {
-  const float d = __ldg(dimg + (int64_t)h * W + w);
+  const float d = __ldg(dimg + h * W + w);
   return backproject(k, (float)w, (float)h, d);
-}
-
-// computes the four per-pixel vectors of pixel (h,w) of image `dimg`
-__device__ __forceinline__ void pixel_maps(const float *__restrict__ dimg, const KInv &k, const Rigid *pose, int h,
-                                           int w, int H, int W, float3 &v, float3 &n, float3 &gv, float3 &gn) {
-  const float d = __ldg(dimg + (int64_t)h * W + w);
-  const float vf = d > 0.0f ? 1.0f : 0.0f;
-  v = backproject(k, (float)w, (float)h, d);
-  // forward differences; the last column / row re-uses its neighbour's difference (rgbdimages.py:724-731)
-  const int wa = (w < W - 1) ? w : w - 1;
-  const int ha = (h < H - 1) ? h : h - 1;
-  const float3 a0 = (wa == w) ? v : vertex_at(dimg, k, h, wa, W);
-  const float3 a1 = vertex_at(dimg, k, h, wa + 1, W);
-  const float3 b0 = (ha == h) ? v : vertex_at(dimg, k, ha, w, W);
-  const float3 b1 = vertex_at(dimg, k, ha + 1, w, W);
-  const float dhx = a1.x - a0.x, dhy = a1.y - a0.y, dhz = a1.z - a0.z;
-  const float dvx = b1.x - b0.x, dvy = b1.y - b0.y, dvz = b1.z - b0.z;
-  const float cx = dhy * dvz - dhz * dvy;
-  const float cy = dhz * dvx - dhx * dvz;
-  const float cz = dhx * dvy - dhy * dvx;
-  const float nrm = sqrtf((cx * cx + cy * cy) + cz * cz);
-  const float den = (nrm == 0.0f) ? 1.0f : nrm;
-  n.x = (cx / den) * vf;
-  n.y = (cy / den) * vf;
-  n.z = (cz / den) * vf;
-  if (pose) {
-    gv = rigid_apply(*pose, v.x, v.y, v.z);
-    gv.x *= vf; gv.y *= vf; gv.z *= vf;
-    gn = rotate(*pose, n.x, n.y, n.z);
-  } else {
-    gv = v;
-    gn = n;
-  }
 }
 
 __global__ void __launch_bounds__(kTile) k_backproject_normals(FrameArgs a) {
   __shared__ __align__(16) float stage[4][kTile * 3];
-  const int64_t P = (int64_t)a.H * a.W;
-  const int64_t total = (int64_t)a.B * a.L * P;
-  const int64_t tile0 = (int64_t)blockIdx.x * kTile;
-  const int64_t i = tile0 + threadIdx.x;
-  if (i < total) {
-    const int64_t img = i / P;  // b*L + l
-    const int pix = (int)(i - img * P);
-    const int b = (int)(img / a.L), l = (int)(img - (int64_t)b * a.L);
-    const int h = pix / a.W, w = pix - h * a.W;
+  __shared__ KInv s_k;
+  __shared__ Rigid s_pose;
+  const int img = blockIdx.y;  // b*L + l
+  const int b = img / a.L, l = img - b * a.L;
+  const int P = a.H * a.W;
+  if (threadIdx.x == 0) s_k = load_kinv(a.K + b * a.K_bstride);
+  if (threadIdx.x == 32 && a.poses) s_pose = load_rigid(a.poses + b * a.pose_bstride + (int64_t)l * 16);
+  __syncthreads();
+  const KInv k = s_k;
+  const int tile0 = blockIdx.x * kTile;
+  const int pix = tile0 + threadIdx.x;
+  const bool want_local = a.out[0] || a.out[1], want_global = a.out[2] || a.out[3];
+  if (pix < P) {
     const float *dimg = a.depth + b * a.depth_bstride + (int64_t)l * P;
-    const KInv k = load_kinv(a.K + b * a.K_bstride);
-    Rigid pose;
-    if (a.poses) pose = load_rigid(a.poses + b * a.pose_bstride + (int64_t)l * 16);
-    float3 v, n, gv, gn;
-    pixel_maps(dimg, k, a.poses ? &pose : nullptr, h, w, a.H, a.W, v, n, gv, gn);
+    const int h = pix / a.W, w = pix - h * a.W;
+    const float d = __ldg(dimg + pix);
+    const float vf = d > 0.0f ? 1.0f : 0.0f;
+    const float3 v = backproject(k, (float)w, (float)h, d);
+    // forward differences; the last column / row re-uses its neighbour's difference (rgbdimages.py:724-731)
+    const int wa = (w < a.W - 1) ? w : w - 1;
+    const int ha = (h < a.H - 1) ? h : h - 1;
+    const float3 a0 = (wa == w) ? v : vertex_at(dimg, k, h, wa, a.W);
+    const float3 a1 = vertex_at(dimg, k, h, wa + 1, a.W);
+    const float3 b0 = (ha == h) ? v : vertex_at(dimg, k, ha, w, a.W);
+    const float3 b1 = vertex_at(dimg, k, ha + 1, w, a.W);
+    const float dhx = a1.x - a0.x, dhy = a1.y - a0.y, dhz = a1.z - a0.z;
+    const float dvx = b1.x - b0.x, dvy = b1.y - b0.y, dvz = b1.z - b0.z;
+    const float cx = dhy * dvz - dhz * dvy;
+    const float cy = dhz * dvx - dhx * dvz;
+    const float cz = dhx * dvy - dhy * dvx;
+    const float nrm = sqrtf((cx * cx + cy * cy) + cz * cz);
+    const float den = (nrm == 0.0f) ? 1.0f : nrm;
+    float3 n;
+    n.x = (cx / den) * vf;
+    n.y = (cy / den) * vf;
+    n.z = (cz / den) * vf;
     const int t3 = threadIdx.x * 3;
-    stage[0][t3] = v.x;  stage[0][t3 + 1] = v.y;  stage[0][t3 + 2] = v.z;
-    stage[1][t3] = n.x;  stage[1][t3 + 1] = n.y;  stage[1][t3 + 2] = n.z;
-    stage[2][t3] = gv.x; stage[2][t3 + 1] = gv.y; stage[2][t3 + 2] = gv.z;
-    stage[3][t3] = gn.x; stage[3][t3 + 1] = gn.y; stage[3][t3 + 2] = gn.z;
+    if (want_local) {
+      stage[0][t3] = v.x; stage[0][t3 + 1] = v.y; stage[0][t3 + 2] = v.z;
+      stage[1][t3] = n.x; stage[1][t3 + 1] = n.y; stage[1][t3 + 2] = n.z;
+    }
+    if (want_global) {
+      float3 gv = v, gn = n;
+      if (a.poses) {
+        gv = rigid_apply(s_pose, v.x, v.y, v.z);
+        gv.x *= vf; gv.y *= vf; gv.z *= vf;
+        gn = rotate(s_pose, n.x, n.y, n.z);
+      }
+      stage[2][t3] = gv.x; stage[2][t3 + 1] = gv.y; stage[2][t3 + 2] = gv.z;
+      stage[3][t3] = gn.x; stage[3][t3 + 1] = gn.y; stage[3][t3 + 2] = gn.z;
+    }
   }
   __syncthreads();
-  const int64_t remaining = total - tile0;
-  const int nfloat = (int)((remaining < kTile ? remaining : kTile) * 3);
+  const int remaining = P - tile0;
+  const int nfloat = (remaining < kTile ? remaining : kTile) * 3;
+  const int64_t obase = ((int64_t)img * P + tile0) * 3;
+  // every image starts 16-byte aligned only if P*3 floats is a multiple of 4
+  const bool vec_ok = (nfloat == kTile * 3) && ((obase & 3) == 0);
 #pragma unroll
   for (int m = 0; m < 4; ++m) {
     float *out = a.out[m];
     if (!out) continue;
-    float *dst = out + tile0 * 3;
-    if (nfloat == kTile * 3) {
+    float *dst = out + obase;
+    if (vec_ok) {
       if (threadIdx.x < kTile * 3 / 4)
         reinterpret_cast<float4 *>(dst)[threadIdx.x] = reinterpret_cast<const float4 *>(stage[m])[threadIdx.x];
     } else {
@@ -98,10 +100,10 @@ __global__ void __launch_bounds__(kTile) k_backproject_normals(FrameArgs a) {
 }
 
 int launch_backproject(const FrameArgs &a, cudaStream_t stream) {
-  const int64_t total = (int64_t)a.B * a.L * a.H * a.W;
-  if (total == 0) return 0;
-  const int64_t blocks = (total + kTile - 1) / kTile;
-  k_backproject_normals<<<(unsigned)blocks, kTile, 0, stream>>>(a);
+  const int64_t P = (int64_t)a.H * a.W;
+  if ((int64_t)a.B * a.L * P == 0) return 0;
+  const int64_t bx = (P + kTile - 1) / kTile;
+  k_backproject_normals<<<dim3((unsigned)bx, (unsigned)(a.B * a.L)), kTile, 0, stream>>>(a);
   GSX_CHECK_LAUNCH("gsx_backproject_normals_fwd");
   return 0;
 }
@@ -114,6 +116,7 @@ extern "C" int gsx_backproject_normals_fwd(const float *depth, int64_t depth_bst
                                            float *gnormal, void *stream) {
   GSX_CHECK_ARG(depth && intrinsics, "gsx_backproject_normals_fwd: null depth/intrinsics");
   GSX_CHECK_ARG(B >= 0 && L >= 0 && H >= 2 && W >= 2, "gsx_backproject_normals_fwd: need H,W >= 2 (got %d x %d)", H, W);
+  GSX_CHECK_ARG((int64_t)B * L <= 65535 && (int64_t)H * W < (1ll << 30), "gsx_backproject_normals_fwd: extents too large");
   float *outs[4] = {vertex, normal, gvertex, gnormal};
   for (float *o : outs)
     GSX_CHECK_ARG(((uintptr_t)o & 15) == 0, "gsx_backproject_normals_fwd: outputs must be 16-byte aligned");

@@ -12,15 +12,21 @@
 namespace gsx {
 
 constexpr int kBlock = 256;
+#ifndef GSX_KPIX
+#define GSX_KPIX 4
+#endif
+constexpr int kTilePix = kBlock * GSX_KPIX;  // pixels per merge tile (must equal kMergeTile)
 
 // ---- workspace layout -----------------------------------------------------------------------------------
 //   [0, B*P*16)                       U128 best[B][P]     complemented arg-min records (0 = empty)
-//   then  uint64 tile_state[B][T]     (epoch<<34 | flag<<32 | value), T = ceil(P / kBlock)
+//   then  uint64 tile_state[B][T]     (epoch<<34 | flag<<32 | value), T = ceil(P / kTilePix)
 //   then  uint32 ticket[B]            dynamic tile ids (monotonic; tile = ticket - (epoch-1)*T)
+//   then  uint64 stats[B][2]          running totals: {active map points (in frustum), merged points}
 struct Workspace {
   U128 *best;
   unsigned long long *tile_state;
   unsigned int *ticket;
+  unsigned long long *stats;
   int tiles;
 };
 
@@ -29,20 +35,29 @@ __host__ __device__ inline int64_t align_up(int64_t x, int64_t a) { return (x + 
 inline Workspace carve(void *ws, int B, int H, int W) {
   const int64_t P = (int64_t)H * W;
   Workspace w;
-  w.tiles = (int)((P + kBlock - 1) / kBlock);
+  w.tiles = (int)((P + kTilePix - 1) / kTilePix);
   char *p = (char *)ws;
   w.best = (U128 *)p;
   p += align_up(B * P * 16, 256);
   w.tile_state = (unsigned long long *)p;
   p += align_up((int64_t)B * w.tiles * 8, 256);
   w.ticket = (unsigned int *)p;
+  p += align_up((int64_t)B * 4, 256);
+  w.stats = (unsigned long long *)p;
   return w;
+}
+
+inline int64_t stats_offset(int B, int H, int W) {
+  const int64_t P = (int64_t)H * W;
+  const int64_t tiles = (P + kTilePix - 1) / kTilePix;
+  return align_up(B * P * 16, 256) + align_up(B * tiles * 8, 256) + align_up((int64_t)B * 4, 256);
 }
 
 inline int64_t workspace_bytes(int B, int H, int W) {
   const int64_t P = (int64_t)H * W;
-  const int64_t tiles = (P + kBlock - 1) / kBlock;
-  return align_up(B * P * 16, 256) + align_up(B * tiles * 8, 256) + align_up((int64_t)B * 4, 256);
+  const int64_t tiles = (P + kTilePix - 1) / kTilePix;
+  return align_up(B * P * 16, 256) + align_up(B * tiles * 8, 256) + align_up((int64_t)B * 4, 256) +
+         align_up((int64_t)B * 16, 256);
 }
 
 // ---- K2 + K3 ------------------------------------------------------------------------------------------
@@ -58,64 +73,122 @@ struct ProjectArgs {
   int B, H, W;
   float dist_th, dot_th, u_hi, v_hi;  // u_hi = float(W - 0.999), v_hi = float(H - 0.999)
   U128 *best;
+  unsigned long long *stats;
 };
 
+#ifndef GSX_KPTS
+#define GSX_KPTS 4
+#endif
+constexpr int kPts = GSX_KPTS;  // map points per thread (independent chains -> 4x memory-level parallelism)
+
 __global__ void __launch_bounds__(kBlock) k_project_select(ProjectArgs a) {
+  __shared__ Rigid s_tinv;
+  __shared__ float s_k[12];
   const int b = blockIdx.y;
   const int count = a.counts[b];
-  const int64_t stride = (int64_t)gridDim.x * kBlock;
-  int64_t n = (int64_t)blockIdx.x * kBlock + threadIdx.x;
-  if (n >= count) return;
-  const Rigid Tinv = rigid_inverse(load_rigid(a.poses + b * a.pose_bstride));
-  const float *K = a.K + b * a.K_bstride;
+  const int chunk = kBlock * kPts;
+  if ((int64_t)blockIdx.x * chunk >= count) return;
+  if (threadIdx.x == 0) s_tinv = rigid_inverse(load_rigid(a.poses + b * a.pose_bstride));
+  if (threadIdx.x >= 32 && threadIdx.x < 44) s_k[threadIdx.x - 32] = __ldg(a.K + b * a.K_bstride + (threadIdx.x - 32));
+  __syncthreads();
+  const Rigid Tinv = s_tinv;
   float k[12];
 #pragma unroll
-  for (int i = 0; i < 12; ++i) k[i] = __ldg(K + i);
-  const int64_t P = (int64_t)a.H * a.W;
+  for (int i = 0; i < 12; ++i) k[i] = s_k[i];
+  const int P = a.H * a.W;
   const float *pts = a.pts + (int64_t)b * a.cap * 3;
   const float *nrm = a.nrm + (int64_t)b * a.cap * 3;
   const float *cc = a.cc + (int64_t)b * a.cap;
   const float *gv = a.gv + (int64_t)b * P * 3;
   const float *gn = a.gn + (int64_t)b * P * 3;
   U128 *best = a.best + (int64_t)b * P;
-  for (; n < count; n += stride) {
-    const float px = __ldg(pts + n * 3), py = __ldg(pts + n * 3 + 1), pz = __ldg(pts + n * 3 + 2);
-    // world -> camera (pointclouds.py:526-573), then pinhole projection with the 4x4 K on the homogeneous
-    // point (projutils.py:92-238): z == 0 divides by 1.
-    const float3 q = rigid_apply(Tinv, px, py, pz);
-    const float hx = ((k[0] * q.x + k[1] * q.y) + k[2] * q.z) + k[3];
-    const float hy = ((k[4] * q.x + k[5] * q.y) + k[6] * q.z) + k[7];
-    const float hz = ((k[8] * q.x + k[9] * q.y) + k[10] * q.z) + k[11];
-    const float den = (hz != 0.0f) ? hz : 1.0f;
-    const float u = hx / den, v = hy / den;
-    // fusionutils.py:259-266
-    const bool in_frame = (u > -1e-3f) && (u < a.u_hi) && (v > -1e-3f) && (v < a.v_hi) && (q.z > 0.0f);
-    if (!in_frame) continue;
-    // round-half-even like torch.round, then clamp (fusionutils.py:267-274)
-    int w = (int)rintf(u), h = (int)rintf(v);
-    w = min(max(w, 0), a.W - 1);
-    h = min(max(h, 0), a.H - 1);
-    const int64_t pix = (int64_t)h * a.W + w;
-    const float fx = __ldg(gv + pix * 3), fy = __ldg(gv + pix * 3 + 1), fz = __ldg(gv + pix * 3 + 2);
-    // are_points_close (fusionutils.py:130): ||frame - map|| < dist_th
-    const float dx = fx - px, dy = fy - py, dz = fz - pz;
-    const float d2 = (dx * dx + dy * dy) + dz * dz;
-    if (!(sqrtf(d2) < a.dist_th)) continue;
-    // are_normals_similar (fusionutils.py:187-195): n_frame . n_map > dot_th
-    const float nx = __ldg(gn + pix * 3), ny = __ldg(gn + pix * 3 + 1), nz = __ldg(gn + pix * 3 + 2);
-    const float mx = __ldg(nrm + n * 3), my = __ldg(nrm + n * 3 + 1), mz = __ldg(nrm + n * 3 + 2);
-    const float dot = (nx * mx + ny * my) + nz * mz;
-    if (!(dot > a.dot_th)) continue;
-    // sort key of find_best_unique_correspondences (fusionutils.py:491-517): 1/(cc+1e-20), then the squared
-    // distance (map - frame)^2 (same value as d2: the squares are sign-independent), then n.
-    const float inv_cc = 1.0f / (__ldg(cc + n) + 1e-20f);
-    // positive floats order like their bit patterns; flip negatives so the order stays total.
-    unsigned int kb = __float_as_uint(inv_cc);
-    kb = (kb & 0x80000000u) ? ~kb : (kb | 0x80000000u);
-    const unsigned int rb = __float_as_uint(d2) | 0x80000000u;  // d2 >= 0
-    const unsigned long long hi = ((unsigned long long)kb << 32) | rb;
-    atomic_min_key128(best + pix, hi, (unsigned long long)n);
+  unsigned int n_active = 0;
+  for (int64_t base = (int64_t)blockIdx.x * chunk; base < count; base += (int64_t)gridDim.x * chunk) {
+    int n[kPts], pix[kPts];
+    float px[kPts], py[kPts], pz[kPts], d2[kPts];
+    bool live[kPts];
+    // stage 1: positions (independent coalesced loads), projection, frustum test
+#pragma unroll
+    for (int j = 0; j < kPts; ++j) {
+      n[j] = (int)(base + j * kBlock + threadIdx.x);
+      live[j] = n[j] < count;
+      const int nn = live[j] ? n[j] : 0;
+      px[j] = __ldg(pts + (int64_t)nn * 3);
+      py[j] = __ldg(pts + (int64_t)nn * 3 + 1);
+      pz[j] = __ldg(pts + (int64_t)nn * 3 + 2);
+    }
+#pragma unroll
+    for (int j = 0; j < kPts; ++j) {
+      // world -> camera (pointclouds.py:526-573), then pinhole projection with the 4x4 K on the homogeneous
+      // point (projutils.py:92-238): z == 0 divides by 1.
+      const float3 q = rigid_apply(Tinv, px[j], py[j], pz[j]);
+      const float hx = ((k[0] * q.x + k[1] * q.y) + k[2] * q.z) + k[3];
+      const float hy = ((k[4] * q.x + k[5] * q.y) + k[6] * q.z) + k[7];
+      const float hz = ((k[8] * q.x + k[9] * q.y) + k[10] * q.z) + k[11];
+      const float den = (hz != 0.0f) ? hz : 1.0f;
+      const float u = hx / den, v = hy / den;
+      // fusionutils.py:259-266
+      live[j] = live[j] && (u > -1e-3f) && (u < a.u_hi) && (v > -1e-3f) && (v < a.v_hi) && (q.z > 0.0f);
+      // round-half-even like torch.round, then clamp (fusionutils.py:267-274)
+      int w = (int)rintf(u), h = (int)rintf(v);
+      w = min(max(w, 0), a.W - 1);
+      h = min(max(h, 0), a.H - 1);
+      pix[j] = live[j] ? h * a.W + w : 0;
+      n_active += live[j] ? 1u : 0u;
+    }
+    // stage 2: frame vertex under the projection; are_points_close (fusionutils.py:130): ||frame - map|| < dist_th
+    float fx[kPts], fy[kPts], fz[kPts];
+#pragma unroll
+    for (int j = 0; j < kPts; ++j) {
+      if (live[j]) {
+        fx[j] = __ldg(gv + (int64_t)pix[j] * 3);
+        fy[j] = __ldg(gv + (int64_t)pix[j] * 3 + 1);
+        fz[j] = __ldg(gv + (int64_t)pix[j] * 3 + 2);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < kPts; ++j) {
+      if (live[j]) {
+        const float dx = fx[j] - px[j], dy = fy[j] - py[j], dz = fz[j] - pz[j];
+        d2[j] = (dx * dx + dy * dy) + dz * dz;
+        live[j] = sqrtf(d2[j]) < a.dist_th;
+      }
+    }
+    // stage 3: are_normals_similar (fusionutils.py:187-195): n_frame . n_map > dot_th; confidence count
+    float nx[kPts], ny[kPts], nz[kPts], mx[kPts], my[kPts], mz[kPts], c0[kPts];
+#pragma unroll
+    for (int j = 0; j < kPts; ++j) {
+      if (live[j]) {
+        nx[j] = __ldg(gn + (int64_t)pix[j] * 3);
+        ny[j] = __ldg(gn + (int64_t)pix[j] * 3 + 1);
+        nz[j] = __ldg(gn + (int64_t)pix[j] * 3 + 2);
+        mx[j] = __ldg(nrm + (int64_t)n[j] * 3);
+        my[j] = __ldg(nrm + (int64_t)n[j] * 3 + 1);
+        mz[j] = __ldg(nrm + (int64_t)n[j] * 3 + 2);
+        c0[j] = __ldg(cc + n[j]);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < kPts; ++j) {
+      if (live[j]) {
+        const float dot = (nx[j] * mx[j] + ny[j] * my[j]) + nz[j] * mz[j];
+        if (dot > a.dot_th) {
+          // sort key of find_best_unique_correspondences (fusionutils.py:491-517): 1/(cc+1e-20), then the
+          // squared distance (map - frame)^2 (== d2: squares are sign-independent), then n.
+          const float inv_cc = 1.0f / (c0[j] + 1e-20f);
+          // positive floats order like their bit patterns; flip negatives so the order stays total.
+          unsigned int kb = __float_as_uint(inv_cc);
+          kb = (kb & 0x80000000u) ? ~kb : (kb | 0x80000000u);
+          const unsigned int rb = __float_as_uint(d2[j]) | 0x80000000u;  // d2 >= 0
+          const unsigned long long hi = ((unsigned long long)kb << 32) | rb;
+          atomic_min_key128(best + pix[j], hi, (unsigned long long)n[j]);
+        }
+      }
+    }
   }
+  // bookkeeping for the roofline's algorithmic-byte count: one atomic per warp
+  n_active = __reduce_add_sync(0xffffffffu, n_active);
+  if ((threadIdx.x & 31) == 0 && n_active) atomicAdd(a.stats + 2 * b, (unsigned long long)n_active);
 }
 
 // ---- K4 -------------------------------------------------------------------------------------------------
@@ -153,10 +226,41 @@ __device__ __forceinline__ void st_release_u64(unsigned long long *p, unsigned l
   asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 
+#ifndef GSX_KPIX
+#define GSX_KPIX 4
+#endif
+constexpr int kPix = GSX_KPIX;             // pixels per thread
+constexpr int kMergeTile = kBlock * kPix;  // pixels per CTA
+static_assert(kMergeTile == kTilePix, "workspace tile size");
+
+// exclusive prefix of the new-point counts of all preceding tiles (decoupled look-back, one warp, 32
+// predecessors per step)
+__device__ __forceinline__ unsigned int lookback_warp(const unsigned long long *state, int tile, unsigned int epoch,
+                                                      int lane) {
+  unsigned int excl = 0;
+  for (int base = tile - 1; base >= 0; base -= 32) {
+    const int j = base - lane;
+    unsigned long long s = 0ull;
+    if (j >= 0) {
+      do {
+        s = ld_acquire_u64(state + j);
+      } while ((unsigned int)(s >> 34) != epoch);
+    }
+    const bool is_prefix = (j >= 0) && (((s >> 32) & 3ull) == kFlagPrefix);
+    const unsigned int pm = __ballot_sync(0xffffffffu, is_prefix);
+    const int first = pm ? (__ffs(pm) - 1) : 32;  // nearest predecessor that already knows its inclusive prefix
+    const unsigned int v = (j >= 0 && lane <= first) ? (unsigned int)s : 0u;
+    excl += __reduce_add_sync(0xffffffffu, v);
+    if (pm) break;
+  }
+  return excl;
+}
+
 __global__ void __launch_bounds__(kBlock) k_merge_append(MergeArgs a) {
   __shared__ int s_tile;
-  __shared__ int s_warp_sums[kBlock / 32];
+  __shared__ int s_warp_sums[kPix][kBlock / 32];
   __shared__ int s_excl;
+  __shared__ KInv s_k;
   const int b = blockIdx.y;
   const int T = a.ws.tiles;
   if (threadIdx.x == 0) {
@@ -164,105 +268,148 @@ __global__ void __launch_bounds__(kBlock) k_merge_append(MergeArgs a) {
     const unsigned int t = atomicAdd(a.ws.ticket + b, 1u);
     s_tile = (int)(t - (a.epoch - 1u) * (unsigned int)T);
   }
+  if (threadIdx.x == 32) s_k = load_kinv(a.K + b * a.K_bstride);
   __syncthreads();
   const int tile = s_tile;
-  const int64_t P = (int64_t)a.H * a.W;
-  const int64_t pix = (int64_t)tile * kBlock + threadIdx.x;
-  const bool in_img = pix < P;
+  const int P = a.H * a.W;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  U128 *best = a.ws.best + (int64_t)b * P;
+  const float *depth = a.depth + b * a.depth_bstride;
 
-  U128 rec{0ull, 0ull};
-  float d = 0.0f;
-  if (in_img) {
-    U128 *slot = a.ws.best + (int64_t)b * P + pix;
-    rec = *slot;
-    if (rec.lo | rec.hi) *slot = U128{0ull, 0ull};  // leave the workspace clean for the next frame
-    d = __ldg(a.depth + b * a.depth_bstride + pix);
-  }
-  const bool matched = (rec.lo | rec.hi) != 0ull;
-  const bool valid = d > 0.0f;
-  const bool is_new = in_img && valid && !matched;
-
-  // block-wide exclusive scan of is_new
-  const unsigned int ballot = __ballot_sync(0xffffffffu, is_new);
-  const int warp_excl = __popc(ballot & ((1u << lane) - 1u));
-  if (lane == 0) s_warp_sums[warp] = __popc(ballot);
-  __syncthreads();
-  int block_excl = 0, block_total = 0;
+  int pix[kPix];
+  U128 rec[kPix];
+  float d[kPix];
+  bool matched[kPix], is_new[kPix];
+  int warp_excl[kPix];
 #pragma unroll
-  for (int i = 0; i < kBlock / 32; ++i) {
-    const int s = s_warp_sums[i];
-    if (i < warp) block_excl += s;
-    block_total += s;
+  for (int j = 0; j < kPix; ++j) {
+    pix[j] = tile * kMergeTile + j * kBlock + threadIdx.x;
+    rec[j] = U128{0ull, 0ull};
+    d[j] = 0.0f;
+    if (pix[j] < P) {
+      rec[j] = best[pix[j]];
+      d[j] = __ldg(depth + pix[j]);
+    }
+  }
+  int n_matched = 0;
+#pragma unroll
+  for (int j = 0; j < kPix; ++j) {
+    matched[j] = (rec[j].lo | rec[j].hi) != 0ull;
+    if (matched[j]) best[pix[j]] = U128{0ull, 0ull};  // leave the workspace clean for the next frame
+    is_new[j] = (pix[j] < P) && (d[j] > 0.0f) && !matched[j];
+    n_matched += matched[j] ? 1 : 0;
+    // row-major order inside the tile: chunk j (256 consecutive pixels), then warp, then lane
+    const unsigned int ballot = __ballot_sync(0xffffffffu, is_new[j]);
+    warp_excl[j] = __popc(ballot & ((1u << lane) - 1u));
+    if (lane == 0) s_warp_sums[j][warp] = __popc(ballot);
+  }
+  n_matched = __reduce_add_sync(0xffffffffu, n_matched);
+  if (lane == 0 && n_matched) atomicAdd(a.ws.stats + 2 * b + 1, (unsigned long long)n_matched);
+  __syncthreads();
+  int block_total = 0;
+  int block_excl[kPix];
+#pragma unroll
+  for (int j = 0; j < kPix; ++j) {
+    block_excl[j] = block_total;
+#pragma unroll
+    for (int i = 0; i < kBlock / 32; ++i) {
+      const int c = s_warp_sums[j][i];
+      if (i < warp) block_excl[j] += c;
+      block_total += c;
+    }
   }
   unsigned long long *state = a.ws.tile_state + (int64_t)b * T;
   if (threadIdx.x == 0 && tile + 1 < T) st_release_u64(state + tile, pack_state(a.epoch, kFlagAgg, (unsigned)block_total));
 
-  // per-pixel frame sample: alpha from the LOCAL vertex (fusionutils.py:657, 69-72)
-  float alpha = 0.0f;
-  float3 fp, fn, fc;
-  if (in_img && (matched || is_new)) {
-    const int h = (int)(pix / a.W), w = (int)(pix - (int64_t)h * a.W);
-    const KInv k = load_kinv(a.K + b * a.K_bstride);
-    const float3 v = backproject(k, (float)w, (float)h, d);
-    const float s = (v.x * v.x + v.y * v.y) + v.z * v.z;
-    alpha = fminf(fmaxf(expf((-s) / a.two_sigma_sq), 1e-7f), 1.01f);
-    const float *gv = a.gv + ((int64_t)b * P + pix) * 3;
-    const float *gn = a.gn + ((int64_t)b * P + pix) * 3;
-    const float *c = a.rgb + b * a.rgb_bstride + pix * 3;
-    fp = make_float3(__ldg(gv), __ldg(gv + 1), __ldg(gv + 2));
-    fn = make_float3(__ldg(gn), __ldg(gn + 1), __ldg(gn + 2));
-    fc = make_float3(__ldg(c), __ldg(c + 1), __ldg(c + 2));
-  }
   float *pts = a.pts + (int64_t)b * a.cap * 3;
   float *nrm = a.nrm + (int64_t)b * a.cap * 3;
   float *col = a.col + (int64_t)b * a.cap * 3;
   float *cc = a.cc ? a.cc + (int64_t)b * a.cap : nullptr;
+  const KInv k = s_k;
+  const float *gvb = a.gv + (int64_t)b * P * 3;
+  const float *gnb = a.gn + (int64_t)b * P * 3;
+  const float *rgb = a.rgb + b * a.rgb_bstride;
 
-  if (matched && cc) {
-    // confidence-weighted running mean (fusionutils.py:678-699); exactly one pixel owns this map row
-    const int64_t n = (int64_t)(~rec.lo);
-    const float c0 = cc[n];
-    const float tot = c0 + alpha;
-    const float inv = 1.0f / ((tot == 0.0f) ? 1.0f : tot);
-    pts[n * 3 + 0] = ((c0 * pts[n * 3 + 0]) + (alpha * fp.x)) * inv;
-    pts[n * 3 + 1] = ((c0 * pts[n * 3 + 1]) + (alpha * fp.y)) * inv;
-    pts[n * 3 + 2] = ((c0 * pts[n * 3 + 2]) + (alpha * fp.z)) * inv;
-    nrm[n * 3 + 0] = ((c0 * nrm[n * 3 + 0]) + (alpha * fn.x)) * inv;
-    nrm[n * 3 + 1] = ((c0 * nrm[n * 3 + 1]) + (alpha * fn.y)) * inv;
-    nrm[n * 3 + 2] = ((c0 * nrm[n * 3 + 2]) + (alpha * fn.z)) * inv;
-    col[n * 3 + 0] = ((c0 * col[n * 3 + 0]) + (alpha * fc.x)) * inv;
-    col[n * 3 + 1] = ((c0 * col[n * 3 + 1]) + (alpha * fc.y)) * inv;
-    col[n * 3 + 2] = ((c0 * col[n * 3 + 2]) + (alpha * fc.z)) * inv;
-    cc[n] = tot;
+  // per-pixel frame sample (loads of the 4 pixels are independent)
+  float alpha[kPix];
+  float3 fp[kPix], fn[kPix], fc[kPix];
+#pragma unroll
+  for (int j = 0; j < kPix; ++j) {
+    if (matched[j] || is_new[j]) {
+      const float *g = gvb + (int64_t)pix[j] * 3;
+      const float *h = gnb + (int64_t)pix[j] * 3;
+      const float *c = rgb + (int64_t)pix[j] * 3;
+      fp[j] = make_float3(__ldg(g), __ldg(g + 1), __ldg(g + 2));
+      fn[j] = make_float3(__ldg(h), __ldg(h + 1), __ldg(h + 2));
+      fc[j] = make_float3(__ldg(c), __ldg(c + 1), __ldg(c + 2));
+    }
+  }
+  // matched map rows: issue all loads first, then the arithmetic and the stores
+  float mp[kPix][10];
+#pragma unroll
+  for (int j = 0; j < kPix; ++j) {
+    if (matched[j] && cc) {
+      const int64_t n = (int64_t)(~rec[j].lo);
+#pragma unroll
+      for (int q = 0; q < 3; ++q) {
+        mp[j][q] = pts[n * 3 + q];
+        mp[j][3 + q] = nrm[n * 3 + q];
+        mp[j][6 + q] = col[n * 3 + q];
+      }
+      mp[j][9] = cc[n];
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < kPix; ++j) {
+    if (matched[j] || is_new[j]) {
+      // alpha from the LOCAL vertex (fusionutils.py:657, 69-72)
+      const int h = pix[j] / a.W, w = pix[j] - h * a.W;
+      const float3 v = backproject(k, (float)w, (float)h, d[j]);
+      const float s = (v.x * v.x + v.y * v.y) + v.z * v.z;
+      alpha[j] = fminf(fmaxf(expf((-s) / a.two_sigma_sq), 1e-7f), 1.01f);
+    }
+    if (matched[j] && cc) {
+      // confidence-weighted running mean (fusionutils.py:678-699); exactly one pixel owns this map row
+      const int64_t n = (int64_t)(~rec[j].lo);
+      const float c0 = mp[j][9];
+      const float tot = c0 + alpha[j];
+      const float inv = 1.0f / ((tot == 0.0f) ? 1.0f : tot);
+      pts[n * 3 + 0] = ((c0 * mp[j][0]) + (alpha[j] * fp[j].x)) * inv;
+      pts[n * 3 + 1] = ((c0 * mp[j][1]) + (alpha[j] * fp[j].y)) * inv;
+      pts[n * 3 + 2] = ((c0 * mp[j][2]) + (alpha[j] * fp[j].z)) * inv;
+      nrm[n * 3 + 0] = ((c0 * mp[j][3]) + (alpha[j] * fn[j].x)) * inv;
+      nrm[n * 3 + 1] = ((c0 * mp[j][4]) + (alpha[j] * fn[j].y)) * inv;
+      nrm[n * 3 + 2] = ((c0 * mp[j][5]) + (alpha[j] * fn[j].z)) * inv;
+      col[n * 3 + 0] = ((c0 * mp[j][6]) + (alpha[j] * fc[j].x)) * inv;
+      col[n * 3 + 1] = ((c0 * mp[j][7]) + (alpha[j] * fc[j].y)) * inv;
+      col[n * 3 + 2] = ((c0 * mp[j][8]) + (alpha[j] * fc[j].z)) * inv;
+      cc[n] = tot;
+    }
   }
 
-  // decoupled look-back: exclusive prefix of new-point counts over preceding tiles of this element
-  if (threadIdx.x == 0) {
-    unsigned int excl = 0;
-    for (int j = tile - 1; j >= 0; --j) {
-      unsigned long long s;
-      do {
-        s = ld_acquire_u64(state + j);
-      } while ((unsigned int)(s >> 34) != a.epoch);
-      excl += (unsigned int)s;
-      if (((s >> 32) & 3ull) == kFlagPrefix) break;
+  // decoupled look-back (warp 0): exclusive prefix of new-point counts over preceding tiles of this element
+  if (warp == 0) {
+    const unsigned int excl = lookback_warp(state, tile, a.epoch, lane);
+    if (lane == 0) {
+      if (tile + 1 < T) st_release_u64(state + tile, pack_state(a.epoch, kFlagPrefix, excl + (unsigned)block_total));
+      s_excl = (int)excl;
     }
-    if (tile + 1 < T) st_release_u64(state + tile, pack_state(a.epoch, kFlagPrefix, excl + (unsigned)block_total));
-    s_excl = (int)excl;
   }
   __syncthreads();
   const int64_t base = (int64_t)a.counts_in[b] + s_excl;
-  if (is_new) {
-    // append in row-major pixel order (fusionutils.py:702-720; pointclouds.py:1203-1235)
-    const int64_t n = base + block_excl + warp_excl;
-    if (n < a.cap) {
-      pts[n * 3 + 0] = fp.x; pts[n * 3 + 1] = fp.y; pts[n * 3 + 2] = fp.z;
-      nrm[n * 3 + 0] = fn.x; nrm[n * 3 + 1] = fn.y; nrm[n * 3 + 2] = fn.z;
-      col[n * 3 + 0] = fc.x; col[n * 3 + 1] = fc.y; col[n * 3 + 2] = fc.z;
-      if (cc) cc[n] = alpha;
-    } else {
-      *a.overflow = 1;
+#pragma unroll
+  for (int j = 0; j < kPix; ++j) {
+    if (is_new[j]) {
+      // append in row-major pixel order (fusionutils.py:702-720; pointclouds.py:1203-1235)
+      const int64_t n = base + block_excl[j] + warp_excl[j];
+      if (n < a.cap) {
+        pts[n * 3 + 0] = fp[j].x; pts[n * 3 + 1] = fp[j].y; pts[n * 3 + 2] = fp[j].z;
+        nrm[n * 3 + 0] = fn[j].x; nrm[n * 3 + 1] = fn[j].y; nrm[n * 3 + 2] = fn[j].z;
+        col[n * 3 + 0] = fc[j].x; col[n * 3 + 1] = fc[j].y; col[n * 3 + 2] = fc[j].z;
+        if (cc) cc[n] = alpha[j];
+      } else {
+        *a.overflow = 1;
+      }
     }
   }
   if (tile == T - 1 && threadIdx.x == 0) {
@@ -273,8 +420,9 @@ __global__ void __launch_bounds__(kBlock) k_merge_append(MergeArgs a) {
 
 int launch_project_select(const ProjectArgs &a, int64_t max_count, cudaStream_t stream) {
   if (a.B == 0 || max_count <= 0) return 0;
-  int64_t bx = (max_count + kBlock - 1) / kBlock;
-  const int64_t cap_blocks = (int64_t)kNumSMs * 8;  // grid-stride beyond 8 CTAs per SM
+  const int64_t chunk = (int64_t)kBlock * kPts;
+  int64_t bx = (max_count + chunk - 1) / chunk;
+  const int64_t cap_blocks = (int64_t)kNumSMs * 16;  // grid-stride beyond 16 CTAs per SM
   if (bx * a.B > cap_blocks) bx = (cap_blocks + a.B - 1) / a.B;
   if (bx < 1) bx = 1;
   k_project_select<<<dim3((unsigned)bx, (unsigned)a.B), kBlock, 0, stream>>>(a);
@@ -298,6 +446,11 @@ extern "C" int64_t gsx_fusion_workspace_bytes(int B, int H, int W) {
   return workspace_bytes(B, H, W);
 }
 
+extern "C" int64_t gsx_fusion_workspace_stats_offset(int B, int H, int W) {
+  if (B < 0 || H < 0 || W < 0) return -1;
+  return stats_offset(B, H, W);
+}
+
 extern "C" int gsx_fusion_project_select(const float *map_points, const float *map_normals,
                                          const float *map_ccounts, const int32_t *counts, int64_t capacity,
                                          int64_t max_count, const float *poses, int64_t pose_bstride,
@@ -312,7 +465,7 @@ extern "C" int gsx_fusion_project_select(const float *map_points, const float *m
                 (long long)max_count, (long long)capacity);
   const Workspace ws = carve(workspace, B, H, W);
   ProjectArgs a{map_points, map_normals, map_ccounts, counts, capacity, poses, pose_bstride, intrinsics, K_bstride,
-                gvertex, gnormal, B, H, W, dist_th, dot_th, (float)(W - 0.999), (float)(H - 0.999), ws.best};
+                gvertex, gnormal, B, H, W, dist_th, dot_th, (float)(W - 0.999), (float)(H - 0.999), ws.best, ws.stats};
   return launch_project_select(a, max_count, (cudaStream_t)stream);
 }
 

@@ -43,31 +43,65 @@ class PointFusion(ICPSLAM):
     def _map(self, pointclouds: Pointclouds, live_frame: RGBDImages, inplace: bool = False):
         return update_map_fusion(pointclouds, live_frame, self.dist_th, self.dot_th, self.sigma, inplace)
 
-    def _forward_sequence(self, frames: RGBDImages):
-        """odom='gt': the whole (B, L) sequence is ONE C call chaining K1 -> K2/K3 -> K4 per frame."""
+    def _forward_sequence(self, frames: RGBDImages, chunk: int = 4):
+        """odom='gt': the whole (B, L) sequence runs as C calls chaining K1 -> K2/K3 -> K4 per frame with no
+        host synchronisation.  Frames that live in HOST memory are uploaded `chunk` frames at a time on a side
+        stream, so the copy of chunk i+1 overlaps the fusion of chunk i (pin the host tensors for this)."""
         if self.odom != "gt" or frames.poses is None or torch.is_tensor(self.sigma):
             return None
-        frames = frames.to(self.device).to_channels_last()
+        if frames.channels_first:
+            frames = frames.to_channels_last()
+        dev = self.device
         B, L, H, W = frames.shape
-        depth, rgb = frames.depth_image.contiguous(), frames.rgb_image.contiguous()
-        _C.require_cuda(depth, "depth_image")
-        K, poses = frames.intrinsics.contiguous(), frames.poses.contiguous()
         P = H * W
-        pc = Pointclouds(device=self.device)
-        pc._allocate(B, L * P, 1)
-        ws = _Workspace.get(self.device, B, H, W)
-        scratch = torch.empty((2, B, H, W, 3), dtype=torch.float32, device=self.device)
+        K = frames.intrinsics.to(dev).contiguous()
+        poses = frames.poses.to(dev).contiguous()
+        src_depth, src_rgb = frames.depth_image, frames.rgb_image
+        on_device = src_depth.device == dev
+        if on_device:
+            depth, rgb = src_depth.contiguous(), src_rgb.contiguous()
+            chunk = L
+        else:
+            depth = torch.empty((B, L, H, W, 1), dtype=torch.float32, device=dev)
+            rgb = torch.empty((B, L, H, W, 3), dtype=torch.float32, device=dev)
+            copy_stream = torch.cuda.Stream(device=dev)
+        _C.require_cuda(depth, "depth_image")
+        pc = Pointclouds(device=dev)
+        pc._allocate(B, L * P, 1, zero=False)
+        ws = _Workspace.get(dev, B, H, W)
+        scratch = torch.empty((2, B, H, W, 3), dtype=torch.float32, device=dev)
         st = pc._store
-        with torch.cuda.device(self.device):
-            rc = _C.lib().gsx_pointfusion_sequence_gt(
-                _C.ptr(st["points"]), _C.ptr(st["normals"]), _C.ptr(st["colors"]), _C.ptr(st["features"]),
-                _C.ptr(pc._counts_dev), pc.capacity, 0, _C.ptr(depth), _C.ptr(rgb), _C.ptr(K), _C.ptr(poses),
-                B, L, H, W, float(self.dist_th), float(self.dot_th), float(self.sigma), _C.ptr(scratch),
-                _C.ptr(ws.buf), ws.next_epochs(L), _C.ptr(pc._overflow_flag()), _C.stream_ptr(self.device))
-        _C.check(rc, "gsx_pointfusion_sequence_gt")
-        if L & 1:
-            pc._cur ^= 1
+        main = torch.cuda.current_stream(dev)
+        with torch.cuda.device(dev):
+            ready = []
+            if not on_device:
+                copy_stream.wait_stream(main)  # the fresh buffers must exist before the copies start
+                with torch.cuda.stream(copy_stream):
+                    for s0 in range(0, L, chunk):
+                        s1 = min(L, s0 + chunk)
+                        for b in range(B):  # per-element slices are contiguous: true async DMA from pinned memory
+                            depth[b, s0:s1].copy_(src_depth[b, s0:s1], non_blocking=True)
+                            rgb[b, s0:s1].copy_(src_rgb[b, s0:s1], non_blocking=True)
+                        ev = torch.cuda.Event()
+                        ev.record(copy_stream)
+                        ready.append(ev)
+            for i, s0 in enumerate(range(0, L, chunk)):
+                s1 = min(L, s0 + chunk)
+                if ready:
+                    main.wait_event(ready[i])
+                rc = _C.lib().gsx_pointfusion_sequence_gt(
+                    _C.ptr(st["points"]), _C.ptr(st["normals"]), _C.ptr(st["colors"]), _C.ptr(st["features"]),
+                    _C.ptr(pc._counts_dev), pc.capacity, min(s0 * P, pc.capacity), _C.ptr(depth), _C.ptr(rgb),
+                    _C.ptr(K), _C.ptr(poses), B, L, s0, s1, H, W, float(self.dist_th), float(self.dot_th),
+                    float(self.sigma), _C.ptr(scratch), _C.ptr(ws.buf), ws.next_epochs(s1 - s0),
+                    _C.ptr(pc._overflow_flag()), _C.stream_ptr(dev))
+                _C.check(rc, "gsx_pointfusion_sequence_gt")
+            if not on_device:
+                depth.record_stream(copy_stream)
+                rgb.record_stream(copy_stream)
+        pc._cur = L & 1
         pc._counts_host = None
         pc._bound = pc.capacity
         pc._list_cache = {}
+        pc._tail_dirty = pc._uninit
         return pc, poses.clone()

@@ -42,6 +42,8 @@ class Pointclouds(object):
         self._overflow = None  # int32 device flag set by kernels if capacity was exceeded
         self._B = 0
         self._list_cache = {}
+        self._uninit = False  # store was allocated without zero-fill: rows >= counts[b] may hold garbage
+        self._tail_dirty = False  # the ragged tail [counts[b], max(counts)) must be zeroed before a padded view
 
         if isinstance(points, list):
             shapes = [p.shape for p in points]
@@ -107,6 +109,7 @@ class Pointclouds(object):
         self._counts_dev = t
         self._cur = 0
         self._list_cache = {}
+        self._tail_dirty = self._uninit
 
     def _host_counts(self) -> List[int]:
         """Per-element sizes on the host; synchronises with the device only if kernels changed them."""
@@ -127,14 +130,19 @@ class Pointclouds(object):
         self._counts_host = None
         self._bound = min(int(new_bound), self.capacity)
         self._list_cache = {}
+        self._tail_dirty = self._uninit
 
-    def _allocate(self, B: int, capacity: int, features_dim: int = 1, dtype=torch.float32):
-        """Turns an EMPTY object into B empty maps with the given capacity (used by the fusion ops)."""
+    def _allocate(self, B: int, capacity: int, features_dim: int = 1, dtype=torch.float32, zero: bool = True):
+        """Turns an EMPTY object into B empty maps with the given capacity (used by the fusion ops).
+        zero=False skips the fill: the kernels never read rows >= counts[b]; the zero padding that the
+        `*_padded` views promise is then restored lazily, only for the ragged tail (see _padded)."""
         assert not self.has_points
         self._B = int(B)
+        alloc = torch.zeros if zero else torch.empty
         for key, C in (("points", 3), ("normals", 3), ("colors", 3), ("features", features_dim)):
             if C > 0:
-                self._store[key] = torch.zeros((self._B, int(capacity), C), dtype=dtype, device=self.device)
+                self._store[key] = alloc((self._B, int(capacity), C), dtype=dtype, device=self.device)
+        self._uninit = not zero
         self._set_counts([0] * self._B)
 
     def _overflow_flag(self):
@@ -154,7 +162,7 @@ class Pointclouds(object):
                 continue
             grown = torch.zeros((st.shape[0], new_cap, st.shape[2]), dtype=st.dtype, device=st.device)
             if cap > 0:
-                grown[:, :cap] = st
+                grown[:, :cap] = st  # (a dirty tail, if any, is copied too and stays flagged)
             self._store[key] = grown
         self._list_cache = {}
 
@@ -198,9 +206,36 @@ class Pointclouds(object):
     def _N(self):
         return max(self._host_counts()) if self.has_points else 0
 
+    def _clean_tail(self):
+        """Zeroes rows [counts[b], max(counts)) of every attribute (only needed after a zero=False allocation)."""
+        if self._tail_dirty and self.has_points:
+            counts, n = self._host_counts(), self._N
+            for st in self._store.values():
+                if st is None:
+                    continue
+                for b, c in enumerate(counts):
+                    if c < n:
+                        st[b, c:n].zero_()
+            self._tail_dirty = False
+
+    def _zero_rows_upto(self, n: int):
+        """Zeroes rows [counts[b], n) of every attribute (padding contract for an externally chosen width)."""
+        counts = self._host_counts()
+        if not self._uninit:  # zero-initialised stores already satisfy the contract
+            return
+        for st in self._store.values():
+            if st is None:
+                continue
+            for b, c in enumerate(counts):
+                if c < n:
+                    st[b, c:n].zero_()
+
     def _padded(self, key):
         st = self._store[key]
-        return None if st is None else st[:, : self._N]
+        if st is None:
+            return None
+        self._clean_tail()
+        return st[:, : self._N]
 
     def _list(self, key):
         st = self._store[key]
@@ -443,6 +478,7 @@ class Pointclouds(object):
         other._counts_host = None if self._counts_host is None else list(self._counts_host)
         other._bound = self._bound
         other._overflow = None if self._overflow is None else self._overflow.clone().to(other.device)
+        other._uninit, other._tail_dirty = self._uninit, self._tail_dirty
         return other
 
     def clone(self):
@@ -481,6 +517,7 @@ class Pointclouds(object):
             self._store, self._B = src._store, src._B
             self._counts_dev, self._cur = src._counts_dev, src._cur
             self._counts_host, self._bound, self._overflow = src._counts_host, src._bound, src._overflow
+            self._uninit, self._tail_dirty = src._uninit, src._tail_dirty
             self._list_cache = {}
             return self
         if len(pointclouds) != len(self):

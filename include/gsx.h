@@ -60,6 +60,9 @@ int gsx_backproject_normals_fwd(const float *depth, int64_t depth_bstride, const
  * (cudaMemset 0); the kernels leave it clean for the next frame.  `epoch` must increase by one with
  * every gsx_fusion_merge_append call on the same workspace, starting at 1.                        */
 int64_t gsx_fusion_workspace_bytes(int B, int H, int W);
+/* byte offset inside the workspace of uint64 stats[B][2] = running totals of {map points inside the
+ * live frustum ("active"), map points merged}; used for the roofline's algorithmic-byte count. */
+int64_t gsx_fusion_workspace_stats_offset(int B, int H, int W);
 
 /* K2+K3: project every map point into the live camera, keep points that are in the frustum, close to
  * the frame vertex they land on and with a similar normal, and reduce per pixel to the best candidate
@@ -84,17 +87,21 @@ int gsx_fusion_merge_append(float *map_points, float *map_normals, float *map_co
                             const float *gnormal, int B, int H, int W, double sigma, void *workspace,
                             uint32_t epoch, int32_t *overflow_flag, void *stream);
 
-/* Whole-sequence driver with ground-truth poses: for s in [0,L): K1 -> K2/K3 -> K4, no host sync.
+/* Whole-sequence driver with ground-truth poses: for s in [s_begin,s_end): K1 -> K2/K3 -> K4, no host sync.
  * replaces ICPSLAM.forward with odom='gt' + PointFusion._map   gradslam/slam/icpslam.py:99-138,
  *          gradslam/slam/pointfusion.py:107-112
  * depth (B,L,H,W), rgb (B,L,H,W,3) dense; poses (B,L,4,4) dense; intrinsics (B,4,4) dense.
- * counts: int32 (2,B) ping-pong buffer; counts[0] holds the current sizes on entry; on return the
- * current sizes are in counts[L & 1].  scratch_maps: 2*B*H*W*3 floats (gvertex, gnormal of one frame).
- * epoch0 = first epoch to use (the call consumes L epochs). */
+ * counts: int32 (2,B) ping-pong buffer; row (s_begin & 1) holds the current sizes on entry; on return the
+ * current sizes are in row (s_end & 1).  max_count0 = host upper bound of the sizes on entry.
+ * scratch_maps: 2*B*H*W*3 floats (gvertex, gnormal of one frame).
+ * epoch0 = epoch of frame s_begin (the call consumes s_end - s_begin epochs).  Splitting a sequence
+ * into several calls (s_begin..s_end chunks) lets the caller overlap host->device copies of later
+ * frames with the fusion of earlier ones. */
 int gsx_pointfusion_sequence_gt(float *map_points, float *map_normals, float *map_colors, float *map_ccounts,
                                 int32_t *counts, int64_t capacity, int64_t max_count0, const float *depth,
                                 const float *rgb, const float *intrinsics, const float *poses, int B, int L,
-                                int H, int W, float dist_th, float dot_th, double sigma, float *scratch_maps,
+                                int s_begin, int s_end, int H, int W, float dist_th, float dot_th,
+                                double sigma, float *scratch_maps,
                                 void *workspace, uint32_t epoch0, int32_t *overflow_flag, void *stream);
 
 #ifdef __cplusplus

@@ -1,0 +1,123 @@
+"""Freezes outputs of the UNMODIFIED gradslam reference as fixtures (run in the build container only).
+
+    python tests/golden/make_golden.py
+
+Imports the reference from /root/reference through tests/golden/ref_loader.py (four in-memory shims, see
+there) and writes
+
+  tests/golden/msrd_b2s3.npz   the reference's own golden vectors for K1 (tests/data/msrd_b2s3/*.npy:
+                               depths, intrinsics, poses -> vertex / normal / global maps), re-packed losslessly
+  tests/golden/ref_slam.npz    reference outputs on seeded synthetic sequences (gradslam_b200.synthetic,
+                               isolated_holes=True): PointFusion / ICPSLAM final maps + poses for odom in
+                               {gt, icp, gradicp}, the three correspondence tables of one fusion step, and
+                               an ICP / gradICP transform recovery case.
+
+The inputs of ref_slam.npz are NOT stored: the tests regenerate them from the recorded seeds.
+"""
+import os
+import sys
+import warnings
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, HERE)
+sys.path.insert(0, ROOT)
+warnings.simplefilter("ignore")
+
+from ref_loader import REFERENCE_ROOT, load_reference  # noqa: E402
+
+load_reference()
+from gradslam.odometry.icputils import point_to_plane_gradICP, point_to_plane_ICP  # noqa: E402
+from gradslam.slam import fusionutils as ref_fu  # noqa: E402
+from gradslam.slam.icpslam import ICPSLAM  # noqa: E402
+from gradslam.slam.pointfusion import PointFusion  # noqa: E402
+from gradslam.structures.pointclouds import Pointclouds  # noqa: E402
+from gradslam.structures.rgbdimages import RGBDImages  # noqa: E402
+
+from gradslam_b200.synthetic import make_sequence  # noqa: E402
+
+# (name, class, B, L, H, W, seed, kwargs)
+SLAM_CASES = [
+    ("pf_gt_64", "PointFusion", 2, 4, 64, 64, 0, dict(odom="gt")),
+    ("pf_gt_120", "PointFusion", 1, 4, 120, 160, 1, dict(odom="gt")),
+    ("pf_icp_64", "PointFusion", 1, 3, 64, 64, 0, dict(odom="icp", numiters=10)),
+    ("pf_gradicp_64", "PointFusion", 2, 3, 64, 64, 2, dict(odom="gradicp", numiters=10)),
+    ("icpslam_gradicp_64", "ICPSLAM", 2, 3, 64, 64, 0, dict(odom="gradicp", numiters=5)),
+    ("icpslam_icp_64", "ICPSLAM", 1, 2, 64, 64, 3, dict(odom="icp", numiters=8)),
+]
+
+
+def pack_map(prefix, pc, out):
+    out[prefix + "/counts"] = np.array([int(c) for c in pc.num_points_per_pointcloud], dtype=np.int64)
+    for b in range(len(pc)):
+        out["%s/points/%d" % (prefix, b)] = pc.points_list[b].numpy()
+        out["%s/normals/%d" % (prefix, b)] = pc.normals_list[b].numpy()
+        out["%s/colors/%d" % (prefix, b)] = pc.colors_list[b].numpy()
+        if pc.has_features:
+            out["%s/ccounts/%d" % (prefix, b)] = pc.features_list[b].numpy()
+
+
+def main():
+    # ---- the reference's own golden vectors (K1) ---------------------------------------------------------
+    d = os.path.join(REFERENCE_ROOT, "tests", "data", "msrd_b2s3")
+    msrd = {k: np.load(os.path.join(d, k + ".npy")) for k in
+            ("depths", "intrinsics", "poses", "vertex_map", "normal_map", "global_vertex_map", "global_normal_map")}
+    np.savez_compressed(os.path.join(HERE, "msrd_b2s3.npz"), **msrd)
+
+    out = {}
+    # ---- full SLAM runs ----------------------------------------------------------------------------------
+    for name, cls, B, L, H, W, seed, kw in SLAM_CASES:
+        rgb, depth, K, poses = make_sequence(B, L, H, W, seed=seed, isolated_holes=True)
+        slam = (PointFusion if cls == "PointFusion" else ICPSLAM)(**kw)
+        pc, rec = slam(RGBDImages(rgb, depth, K, poses))
+        pack_map(name, pc, out)
+        out[name + "/poses"] = rec.numpy()
+        print(name, out[name + "/counts"])
+
+    # ---- one fusion step, table by table -----------------------------------------------------------------
+    rgb, depth, K, poses = make_sequence(2, 3, 64, 64, seed=4, isolated_holes=True)
+    frames = RGBDImages(rgb, depth, K, poses)
+    slam = PointFusion(odom="gt")
+    pc = Pointclouds()
+    for s in range(2):
+        pc, _ = slam.step(pc, frames[:, s], None, inplace=True)
+    live = frames[:, 2]
+    t_active = ref_fu.find_active_map_points(pc, live)
+    t_similar, mask = ref_fu.find_similar_map_points(pc, live, t_active, slam.dist_th, slam.dot_th)
+    t_unique = ref_fu.find_best_unique_correspondences(pc, live, t_similar)
+    out["tables/active"] = t_active.numpy()
+    out["tables/similar"] = t_similar.numpy()
+    out["tables/similar_mask"] = mask.numpy()
+    out["tables/unique"] = t_unique.numpy()
+    pack_map("tables/map_before", pc, out)
+    fused = ref_fu.fuse_with_map(pc.clone(), live, t_unique, slam.sigma, inplace=False)
+    pack_map("tables/map_after", fused, out)
+    print("tables", t_active.shape, t_similar.shape, t_unique.shape)
+
+    # ---- ICP / gradICP transform recovery (like tests/odometry/test_icp.py, smaller) ----------------------
+    rgb, depth, K, poses = make_sequence(1, 1, 48, 64, seed=5, hole_fraction=0.0)
+    fr = RGBDImages(rgb, depth, K, poses)
+    tgt = fr.global_vertex_map[0, 0].reshape(1, -1, 3)
+    tgt_n = fr.global_normal_map[0, 0].reshape(1, -1, 3)
+    from gradslam.geometry.se3utils import se3_exp
+
+    T_true = se3_exp(torch.tensor([0.02, -0.01, 0.015, 0.03, -0.02, 0.01]))
+    src = (tgt[0] @ T_true[:3, :3].t() + T_true[:3, 3]).unsqueeze(0)
+    T_icp, _ = point_to_plane_ICP(src, tgt, tgt_n, torch.eye(4), numiters=12, damp=1e-8, dist_thresh=None)
+    T_grad, _ = point_to_plane_gradICP(src, tgt, tgt_n, torch.eye(4), numiters=12, damp=1e-8, dist_thresh=None)
+    out["icp/T_true"] = T_true.numpy()
+    out["icp/T_icp"] = T_icp.numpy()
+    out["icp/T_gradicp"] = T_grad.numpy()
+    print("icp err", (T_icp @ T_true - torch.eye(4)).abs().max().item(),
+          (T_grad @ T_true - torch.eye(4)).abs().max().item())
+
+    np.savez_compressed(os.path.join(HERE, "ref_slam.npz"), **out)
+    for f in ("msrd_b2s3.npz", "ref_slam.npz"):
+        print(f, os.path.getsize(os.path.join(HERE, f)) // 1024, "KiB")
+
+
+if __name__ == "__main__":
+    main()

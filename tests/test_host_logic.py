@@ -1,0 +1,208 @@
+"""Host-side mirror logic on CPU tensors: containers, validation, error behaviour (reference conventions:
+TypeError for wrong types, ValueError for wrong shapes, raised before any compute)."""
+import math
+
+import pytest
+import torch
+
+import gradslam_b200 as gs
+from gradslam_b200.geometry import geometryutils, projutils, se3utils
+from gradslam_b200.slam import fusionutils
+
+
+def _clouds():
+    pts = [torch.rand(3, 3), torch.rand(5, 3)]
+    return gs.Pointclouds(pts, [p.clone() for p in pts], [p.clone() for p in pts], [torch.rand(3, 1), torch.rand(5, 1)]), pts
+
+
+def test_pointclouds_list_padded_views():
+    pc, pts = _clouds()
+    assert len(pc) == 2 and pc.has_points and pc.has_normals and pc.has_colors and pc.has_features
+    assert pc.points_padded.shape == (2, 5, 3)
+    assert torch.equal(pc.points_list[0], pts[0]) and torch.equal(pc.points_list[1], pts[1])
+    assert pc.points_padded[0, 3:].abs().sum() == 0  # zero padding
+    assert pc.nonpad_mask.tolist() == [[True] * 3 + [False] * 2, [True] * 5]
+    assert pc.num_points_per_pointcloud.tolist() == [3, 5]
+    assert pc.num_features == 1
+
+
+def test_pointclouds_from_padded_and_empty():
+    t = torch.rand(2, 4, 3)
+    pc = gs.Pointclouds(t)
+    assert pc.points_padded.shape == (2, 4, 3) and pc.equisized
+    empty = gs.Pointclouds()
+    assert not empty.has_points and len(empty) == 0
+    with pytest.raises(IndexError):
+        empty[0]
+    with pytest.raises(TypeError):
+        gs.Pointclouds(3)
+    with pytest.raises(ValueError):
+        gs.Pointclouds([])
+    with pytest.raises(ValueError):
+        gs.Pointclouds([torch.rand(3, 2)])
+    with pytest.raises(ValueError):
+        gs.Pointclouds(torch.rand(2, 4, 3), normals=torch.rand(2, 5, 3))
+    with pytest.raises(TypeError):
+        gs.Pointclouds([torch.rand(3, 3)], normals=torch.rand(1, 3, 3))
+
+
+def test_pointclouds_append_clone_index():
+    pc, pts = _clouds()
+    other, pts2 = _clouds()
+    before = pc.clone()
+    pc.append_points(other)
+    assert pc.num_points_per_pointcloud.tolist() == [6, 10]
+    assert torch.equal(pc.points_list[0], torch.cat([pts[0], pts2[0]]))
+    assert torch.equal(pc.points_list[1], torch.cat([pts[1], pts2[1]]))
+    assert before.num_points_per_pointcloud.tolist() == [3, 5]  # clone is deep
+    assert pc.points_padded[0, 6:].abs().sum() == 0
+    sub = pc[1]
+    assert len(sub) == 1 and sub.points_list[0].shape == (10, 3)
+    sub = pc[[0, 1]]
+    assert len(sub) == 2
+    e = gs.Pointclouds()
+    e.append_points(other)
+    assert e.num_points_per_pointcloud.tolist() == [3, 5]
+    with pytest.raises(TypeError):
+        pc.append_points(torch.rand(3))
+    with pytest.raises(ValueError):
+        pc.append_points(gs.Pointclouds([torch.rand(2, 3)]))  # batch size mismatch
+    with pytest.raises(ValueError):
+        pc.append_points(gs.Pointclouds([torch.rand(2, 3), torch.rand(2, 3)]))  # missing normals
+
+
+def test_pointclouds_rigid_ops_and_projection():
+    pc, pts = _clouds()
+    T = torch.eye(4)
+    T[:3, 3] = torch.tensor([1.0, 2.0, 3.0])
+    moved = pc.transform(T)
+    torch.testing.assert_close(moved.points_list[1], pts[1] + T[:3, 3])
+    assert moved.points_padded[0, 3:].abs().sum() == 0  # padding is not offset
+    assert torch.equal(pc.points_list[1], pts[1])  # out of place
+    R = torch.tensor([[0.0, -1, 0], [1, 0, 0], [0, 0, 1]])
+    rot = pc.rotate(R)
+    torch.testing.assert_close(rot.points_list[0], pts[0] @ R.t())
+    torch.testing.assert_close(rot.normals_list[0], pts[0] @ R.t())
+    torch.testing.assert_close((pc + 1.0).points_list[0], pts[0] + 1.0)
+    torch.testing.assert_close((pc * 2.0).points_list[0], pts[0] * 2.0)
+    K = torch.eye(4)
+    K[0, 0] = K[1, 1] = 100.0
+    K[0, 2], K[1, 2] = 32.0, 24.0
+    proj = pc.pinhole_projection(K)
+    want = torch.stack([100 * pts[0][:, 0] / pts[0][:, 2] + 32, 100 * pts[0][:, 1] / pts[0][:, 2] + 24,
+                        torch.ones(3)], -1)
+    torch.testing.assert_close(proj.points_list[0], want, rtol=1e-5, atol=1e-5)
+    with pytest.raises(ValueError):
+        pc.transform(torch.eye(3))
+    with pytest.raises(TypeError):
+        pc.rotate_(3)
+
+
+def test_pointclouds_setters():
+    pc, _ = _clouds()
+    new = torch.rand(2, 5, 3)
+    pc.points_padded = new
+    assert torch.equal(pc.points_padded, new)
+    with pytest.raises(ValueError):
+        pc.points_padded = torch.rand(2, 6, 3)
+    pc.features_padded = torch.rand(2, 5, 4)
+    assert pc.num_features == 4
+
+
+def test_rgbdimages_validation_and_slicing():
+    rgb, depth = torch.rand(2, 3, 8, 10, 3), torch.rand(2, 3, 8, 10, 1)
+    K, poses = torch.eye(4).repeat(2, 1, 1, 1), torch.eye(4).repeat(2, 3, 1, 1)
+    fr = gs.RGBDImages(rgb, depth, K, poses)
+    assert fr.shape == (2, 3, 8, 10) and len(fr) == 2 and not fr.channels_first and fr.cdim == 4
+    sub = fr[:, 1]
+    assert sub.shape == (2, 1, 8, 10) and sub.poses.shape == (2, 1, 4, 4)
+    assert sub.depth_image.data_ptr() == depth[:, 1:2].data_ptr()  # a view, not a copy
+    assert fr[1, 0:2].shape == (1, 2, 8, 10)
+    assert torch.equal(fr.valid_depth_mask, depth > 0)
+    with pytest.raises(TypeError):
+        gs.RGBDImages(3, depth, K)
+    with pytest.raises(ValueError):
+        gs.RGBDImages(rgb[0], depth, K)
+    with pytest.raises(ValueError):
+        gs.RGBDImages(rgb, depth[..., :0], K)
+    with pytest.raises(ValueError):
+        gs.RGBDImages(rgb, depth, torch.eye(4).repeat(2, 2, 1, 1))
+    with pytest.raises(IndexError):
+        fr[5]
+    with pytest.raises(IndexError):
+        fr[0, 0, 0]
+    cf = fr.to_channels_first()
+    assert cf.channels_first and cf.rgb_image.shape == (2, 3, 3, 8, 10) and cf.depth_image.shape == (2, 3, 1, 8, 10)
+    assert torch.equal(cf.to_channels_last().rgb_image, rgb)
+    fr.poses = poses * 2  # setter validates shape
+    with pytest.raises(ValueError):
+        fr.poses = torch.eye(4)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        fr.vertex_map  # compute needs CUDA tensors: no CPU path
+
+
+def test_geometry_helpers():
+    K = torch.eye(4)
+    K[0, 0], K[1, 1], K[0, 2], K[1, 2] = 120.3, -120.0, 79.875, 59.875
+    torch.testing.assert_close(projutils.inverse_intrinsics(K) @ K, torch.eye(4), rtol=1e-5, atol=1e-5)
+    p = torch.tensor([[1.0, 2.0, 4.0], [0.0, 0.0, 0.0]])
+    uv = projutils.project_points(p, K)
+    torch.testing.assert_close(uv[0], torch.tensor([120.3 * 0.25 + 79.875, -120.0 * 0.5 + 59.875]))
+    assert uv[1].tolist() == [0.0, 0.0]  # z == 0 divides by 1
+    assert projutils.homogenize_points(p).shape == (2, 4)
+    torch.testing.assert_close(projutils.unhomogenize_points(torch.tensor([[2.0, 4.0, 2.0]])), torch.tensor([[1.0, 2.0]]))
+    back = projutils.unproject_points(torch.tensor([[1.0, 1.0]]), torch.eye(3), torch.tensor([2.0]))
+    torch.testing.assert_close(back, torch.tensor([[2.0, 2.0, 2.0]]))
+    with pytest.raises(TypeError):
+        projutils.project_points(3, K)
+    with pytest.raises(ValueError):
+        projutils.inverse_intrinsics(torch.eye(5))
+    T = se3utils.se3_exp(torch.tensor([0.1, 0.2, 0.3, 0.0, 0.0, math.pi / 2]))
+    torch.testing.assert_close(T[:3, :3], torch.tensor([[0.0, -1, 0], [1, 0, 0], [0, 0, 1]]), rtol=1e-6, atol=1e-6)
+    Tinv = geometryutils.inverse_transformation(T)
+    torch.testing.assert_close(geometryutils.compose_transformations(T, Tinv), torch.eye(4), rtol=1e-6, atol=1e-6)
+    torch.testing.assert_close(geometryutils.relative_transformation(T, T), torch.eye(4), rtol=1e-5, atol=1e-6)
+    cloud = torch.rand(7, 3)
+    torch.testing.assert_close(geometryutils.transform_pointcloud(cloud, T), cloud @ T[:3, :3].t() + T[:3, 3])
+    g = geometryutils.create_meshgrid(3, 4, normalized_coords=False)
+    assert g.shape == (1, 3, 4, 2) and g[0, 2, 3].tolist() == [2.0, 3.0]
+
+
+def test_fusionutils_small_helpers_and_errors():
+    pts = torch.tensor([[-1.0, 0.0, 1.0], [0.0, 0.0, 0.0]])
+    a = fusionutils.get_alpha(pts, 0.6)
+    torch.testing.assert_close(a, torch.tensor([6.2177e-02, 1.0]), rtol=1e-3, atol=1e-6)
+    assert fusionutils.are_points_close(pts, pts + 0.01, 0.05).all()
+    assert not fusionutils.are_points_close(pts, pts + 1.0, 0.05).any()
+    n = torch.tensor([[0.0, 0.0, 1.0]])
+    assert fusionutils.are_normals_similar(n, n, 0.9).all()
+    with pytest.warns(RuntimeWarning):
+        fusionutils.are_normals_similar(n * 2, n * 2, 0.9)
+    with pytest.raises(TypeError):
+        fusionutils.get_alpha(3, 0.6)
+    with pytest.raises(ValueError):
+        fusionutils.get_alpha(torch.rand(4, 2), 0.6)
+    with pytest.raises(TypeError):
+        fusionutils.update_map_fusion(3, None, 0.05, 0.9, 0.6)
+    pc = gs.Pointclouds()
+    with pytest.raises(TypeError):
+        fusionutils.update_map_fusion(pc, 3, 0.05, 0.9, 0.6)
+    rgb, depth = torch.rand(1, 2, 8, 8, 3), torch.rand(1, 2, 8, 8, 1)
+    fr = gs.RGBDImages(rgb, depth, torch.eye(4).view(1, 1, 4, 4), torch.eye(4).repeat(1, 2, 1, 1))
+    with pytest.raises(ValueError):  # sequence length must be 1
+        fusionutils.update_map_fusion(pc, fr, 0.05, 0.9, 0.6)
+
+
+def test_slam_constructors_and_defaults():
+    slam = gs.PointFusion(odom="gt")
+    assert slam.dist_th == 0.05 and slam.sigma == 0.6 and slam.dsratio == 4
+    assert abs(slam.dot_th - math.cos(math.radians(20))) < 1e-12
+    with pytest.raises(ValueError):
+        gs.PointFusion(odom="nope")
+    with pytest.raises(TypeError):
+        gs.PointFusion(odom="gt", dist_th="x")
+    with pytest.warns(UserWarning):
+        gs.PointFusion(odom="gt", angle_th=120)
+    with pytest.raises(TypeError):
+        slam(3)
+    assert gs.ICPSLAM(odom="gt").odomprov is None
