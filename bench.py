@@ -6,7 +6,8 @@
     torchrun ... bench.py --gpus N ...                         one rank per GPU (weak scaling: B=8 per GPU)
 
 One "step" = one whole `PointFusion(odom='gt')(frames)` call over a (B, L) batch of synthetic RGB-D
-sequences = B*L frame updates (K1 backproject+normals, K2/K3 project+select, K4 merge+append per frame).
+sequences = B*L frame updates (K2/K3 project+select and K4 merge+append per frame; the frame's vertex /
+normal geometry (K1) is evaluated on the fly inside both kernels).
 Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement" for what each key means.
 """
 import argparse
@@ -290,7 +291,7 @@ def main():
             "config": workload_config(args, world),
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": ms_e2e / args.steps},
-            "gpu_launches": 3 * L * args.steps - args.steps,  # K1,K2,K4 per frame; K2 is skipped on the empty map
+            "gpu_launches": 2 * L * args.steps - args.steps,  # K2/K3 + K4 per frame; K2 is skipped on the empty map
             "roofline": roofline, "cpu_baseline": cpu_baseline, "clocks": clocks, "kernels": kernels,
             "final_map_points_per_sequence": (frames_info[-1]["map_points"] + frames_info[-1]["new"]) // B
             if frames_info else None,

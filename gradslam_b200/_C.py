@@ -31,14 +31,24 @@ SIGNATURES = {
     "gsx_fusion_workspace_bytes": (c_i64, [c_int, c_int, c_int]),
     "gsx_fusion_workspace_stats_offset": (c_i64, [c_int, c_int, c_int]),
     "gsx_fusion_project_select": (
-        c_int, [c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_vp, c_i64, c_vp, c_i64, c_vp, c_vp, c_int, c_int, c_int,
-                c_float, c_float, c_vp, c_vp]),
+        c_int, [c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_vp, c_i64, c_vp, c_i64, c_vp, c_i64, c_vp, c_vp, c_int, c_int,
+                c_int, c_float, c_float, c_vp, c_vp]),
     "gsx_fusion_merge_append": (
-        c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_vp, c_i64, c_vp, c_i64, c_vp, c_i64, c_vp, c_vp, c_int,
-                c_int, c_int, c_double, c_vp, c_u32, c_vp, c_vp]),
+        c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_vp, c_i64, c_vp, c_i64, c_vp, c_i64, c_vp, c_i64, c_vp,
+                c_vp, c_int, c_int, c_int, c_double, c_vp, c_u32, c_vp, c_vp]),
     "gsx_pointfusion_sequence_gt": (
         c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_int,
                 c_int, c_float, c_float, c_double, c_vp, c_vp, c_u32, c_vp, c_vp]),
+    "gsx_knn1": (c_int, [c_vp, c_vp, c_int, c_vp, c_vp, c_int, c_int, c_vp, c_vp, c_vp, c_i64, c_vp]),
+    "gsx_icp_align_scratch_bytes": (c_i64, [c_int, c_int]),
+    "gsx_icp_align": (
+        c_int, [c_vp, c_vp, c_int, c_vp, c_vp, c_vp, c_int, c_int, c_vp, c_int, c_int, c_float, c_int, c_float,
+                c_float, c_float, c_float, c_float, c_vp, c_vp, c_vp, c_i64, c_vp]),
+    "gsx_icp_workspace_bytes": (c_i64, [c_int, c_int, c_int, c_int, c_i64]),
+    "gsx_icp_localize": (
+        c_int, [c_vp, c_vp, c_vp, c_i64, c_i64, c_vp, c_i64, c_vp, c_i64, c_vp, c_i64, c_int, c_int, c_int, c_int,
+                c_int, c_int, c_float, c_int, c_float, c_float, c_float, c_float, c_float, c_vp, c_i64, c_vp, c_i64,
+                c_vp, c_u32, c_vp]),
 }
 
 _lib = None

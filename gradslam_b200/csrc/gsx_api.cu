@@ -29,28 +29,24 @@ extern "C" int gsx_pointfusion_sequence_gt(float *map_points, float *map_normals
                                            void *stream) {
   GSX_CHECK_ARG(B >= 0 && L >= 0 && H >= 2 && W >= 2, "gsx_pointfusion_sequence_gt: bad extents");
   GSX_CHECK_ARG(0 <= s_begin && s_begin <= s_end && s_end <= L, "gsx_pointfusion_sequence_gt: bad frame range");
-  GSX_CHECK_ARG(scratch_maps && counts && depth && rgb && intrinsics && poses,
-                "gsx_pointfusion_sequence_gt: null pointer");
+  GSX_CHECK_ARG(counts && depth && rgb && intrinsics && poses, "gsx_pointfusion_sequence_gt: null pointer");
+  (void)scratch_maps;
   const int64_t P = (int64_t)H * W;
-  float *gv = scratch_maps;
-  float *gn = scratch_maps + (int64_t)B * P * 3;
   for (int s = s_begin; s < s_end; ++s) {
-    int rc = gsx_backproject_normals_fwd(depth + (int64_t)s * P, (int64_t)L * P, intrinsics, 16,
-                                         poses + (int64_t)s * 16, (int64_t)L * 16, B, 1, H, W, nullptr, nullptr,
-                                         gv, gn, stream);
-    if (rc) return rc;
     int32_t *cin = counts + (int64_t)(s & 1) * B;
     int32_t *cout = counts + (int64_t)((s + 1) & 1) * B;
     int64_t max_count = max_count0 + (int64_t)(s - s_begin) * P;
     if (max_count > capacity) max_count = capacity;
-    rc = gsx_fusion_project_select(map_points, map_normals, map_ccounts, cin, capacity, max_count,
-                                   poses + (int64_t)s * 16, (int64_t)L * 16, intrinsics, 16, gv, gn, B, H, W,
-                                   dist_th, dot_th, workspace, stream);
+    int rc = gsx_fusion_project_select(map_points, map_normals, map_ccounts, cin, capacity, max_count,
+                                       poses + (int64_t)s * 16, (int64_t)L * 16, intrinsics, 16,
+                                       depth + (int64_t)s * P, (int64_t)L * P, nullptr, nullptr, B, H, W, dist_th,
+                                       dot_th, workspace, stream);
     if (rc) return rc;
     rc = gsx_fusion_merge_append(map_points, map_normals, map_colors, map_ccounts, cin, cout, capacity,
                                  depth + (int64_t)s * P, (int64_t)L * P, rgb + (int64_t)s * P * 3,
-                                 (int64_t)L * P * 3, intrinsics, 16, gv, gn, B, H, W, sigma, workspace,
-                                 epoch0 + (uint32_t)(s - s_begin), overflow_flag, stream);
+                                 (int64_t)L * P * 3, intrinsics, 16, poses + (int64_t)s * 16, (int64_t)L * 16,
+                                 nullptr, nullptr, B, H, W, sigma, workspace, epoch0 + (uint32_t)(s - s_begin),
+                                 overflow_flag, stream);
     if (rc) return rc;
   }
   return 0;

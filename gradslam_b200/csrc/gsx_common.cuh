@@ -99,6 +99,57 @@ __device__ __forceinline__ float3 backproject(const KInv &k, float u, float v, f
   return p;
 }
 
+// Vertex and normal of pixel (h,w) of depth image `dimg`, in the camera frame and (if pose != nullptr) in the
+// world frame: the whole op chain of gradslam/structures/rgbdimages.py:643-762 for one pixel.  Used by K1 (to
+// materialise maps) and, on the fly, by the fusion kernels, so both see bit-identical values.
+//   v  = K^-1 (w,h,1) d, zeroed where d <= 0            n  = normalize(dh x dv) * valid(centre)
+//   dh = forward difference along w (last column re-uses its neighbour's), dv along h likewise
+//   gv = (R v + t) * valid                              gn = R n
+struct FrameSample {
+  float3 v, n, gv, gn;
+  float d;
+};
+template <bool kWantNormal>
+__device__ __forceinline__ FrameSample frame_sample(const float *__restrict__ dimg, const KInv &k, const Rigid *pose,
+                                                    int h, int w, int H, int W) {
+  FrameSample s;
+  const int wa = (w < W - 1) ? w : w - 1;
+  const int ha = (h < H - 1) ? h : h - 1;
+  const float dc = __ldg(dimg + h * W + w);
+  s.d = dc;
+  const float vf = dc > 0.0f ? 1.0f : 0.0f;
+  s.v = backproject(k, (float)w, (float)h, dc);
+  if (kWantNormal) {
+    const float dr = __ldg(dimg + h * W + wa + 1);
+    const float db = __ldg(dimg + (ha + 1) * W + w);
+    const float3 a1 = backproject(k, (float)(wa + 1), (float)h, dr);
+    const float3 b1 = backproject(k, (float)w, (float)(ha + 1), db);
+    const float3 a0 = (wa == w) ? s.v : backproject(k, (float)wa, (float)h, __ldg(dimg + h * W + wa));
+    const float3 b0 = (ha == h) ? s.v : backproject(k, (float)w, (float)ha, __ldg(dimg + ha * W + w));
+    const float dhx = a1.x - a0.x, dhy = a1.y - a0.y, dhz = a1.z - a0.z;
+    const float dvx = b1.x - b0.x, dvy = b1.y - b0.y, dvz = b1.z - b0.z;
+    const float cx = dhy * dvz - dhz * dvy;
+    const float cy = dhz * dvx - dhx * dvz;
+    const float cz = dhx * dvy - dhy * dvx;
+    const float nrm = sqrtf((cx * cx + cy * cy) + cz * cz);
+    const float den = (nrm == 0.0f) ? 1.0f : nrm;
+    s.n.x = (cx / den) * vf;
+    s.n.y = (cy / den) * vf;
+    s.n.z = (cz / den) * vf;
+  } else {
+    s.n = make_float3(0.f, 0.f, 0.f);
+  }
+  if (pose) {
+    s.gv = rigid_apply(*pose, s.v.x, s.v.y, s.v.z);
+    s.gv.x *= vf; s.gv.y *= vf; s.gv.z *= vf;
+    s.gn = kWantNormal ? rotate(*pose, s.n.x, s.n.y, s.n.z) : s.n;
+  } else {
+    s.gv = s.v;
+    s.gn = s.n;
+  }
+  return s;
+}
+
 // 128-bit record used for the per-pixel arg-min.  The workspace is zero-initialised and zero means
 // "no candidate", so a key (hi:lo) is stored as its bitwise complement and the arg-min over keys
 // becomes an atomic MAX over the stored 128-bit unsigned integers.
@@ -124,6 +175,20 @@ __device__ __forceinline__ U128 load128_relaxed(const U128 *addr) {
   U128 v;
   asm volatile("ld.relaxed.gpu.global.v2.u64 {%0, %1}, [%2];" : "=l"(v.lo), "=l"(v.hi) : "l"(addr) : "memory");
   return v;
+}
+
+__device__ __forceinline__ bool rec_greater(const U128 &a, const U128 &b) {
+  return a.hi > b.hi || (a.hi == b.hi && a.lo > b.lo);
+}
+
+// Finishes an arg-min update whose first (optimistic, expected = empty) CAS returned `old`.
+__device__ __forceinline__ void atomic_max_rec128_finish(U128 *addr, const U128 &mine, U128 old) {
+  U128 cur{0ull, 0ull};
+  while (!(old.hi == cur.hi && old.lo == cur.lo)) {  // the CAS did not take effect
+    cur = old;
+    if (!rec_greater(mine, cur)) return;  // somebody better is already there
+    old = cas128(addr, cur, mine);
+  }
 }
 
 // arg-min over keys == max over complemented records

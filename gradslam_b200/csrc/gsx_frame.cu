@@ -20,11 +20,6 @@ struct FrameArgs {
   float *out[4];  // vertex, normal, gvertex, gnormal (any may be null)
 };
 
-__device__ __forceinline__ float3 vertex_at(const float *__restrict__ dimg, const KInv &k, int h, int w, int W) {
-  const float d = __ldg(dimg + h * W + w);
-  return backproject(k, (float)w, (float)h, d);
-}
-
 __global__ void __launch_bounds__(kTile) k_backproject_normals(FrameArgs a) {
   __shared__ __align__(16) float stage[4][kTile * 3];
   __shared__ KInv s_k;
@@ -42,41 +37,15 @@ __global__ void __launch_bounds__(kTile) k_backproject_normals(FrameArgs a) {
   if (pix < P) {
     const float *dimg = a.depth + b * a.depth_bstride + (int64_t)l * P;
     const int h = pix / a.W, w = pix - h * a.W;
-    const float d = __ldg(dimg + pix);
-    const float vf = d > 0.0f ? 1.0f : 0.0f;
-    const float3 v = backproject(k, (float)w, (float)h, d);
-    // forward differences; the last column / row re-uses its neighbour's difference (rgbdimages.py:724-731)
-    const int wa = (w < a.W - 1) ? w : w - 1;
-    const int ha = (h < a.H - 1) ? h : h - 1;
-    const float3 a0 = (wa == w) ? v : vertex_at(dimg, k, h, wa, a.W);
-    const float3 a1 = vertex_at(dimg, k, h, wa + 1, a.W);
-    const float3 b0 = (ha == h) ? v : vertex_at(dimg, k, ha, w, a.W);
-    const float3 b1 = vertex_at(dimg, k, ha + 1, w, a.W);
-    const float dhx = a1.x - a0.x, dhy = a1.y - a0.y, dhz = a1.z - a0.z;
-    const float dvx = b1.x - b0.x, dvy = b1.y - b0.y, dvz = b1.z - b0.z;
-    const float cx = dhy * dvz - dhz * dvy;
-    const float cy = dhz * dvx - dhx * dvz;
-    const float cz = dhx * dvy - dhy * dvx;
-    const float nrm = sqrtf((cx * cx + cy * cy) + cz * cz);
-    const float den = (nrm == 0.0f) ? 1.0f : nrm;
-    float3 n;
-    n.x = (cx / den) * vf;
-    n.y = (cy / den) * vf;
-    n.z = (cz / den) * vf;
+    const FrameSample f = frame_sample<true>(dimg, k, a.poses ? &s_pose : nullptr, h, w, a.H, a.W);
     const int t3 = threadIdx.x * 3;
     if (want_local) {
-      stage[0][t3] = v.x; stage[0][t3 + 1] = v.y; stage[0][t3 + 2] = v.z;
-      stage[1][t3] = n.x; stage[1][t3 + 1] = n.y; stage[1][t3 + 2] = n.z;
+      stage[0][t3] = f.v.x; stage[0][t3 + 1] = f.v.y; stage[0][t3 + 2] = f.v.z;
+      stage[1][t3] = f.n.x; stage[1][t3 + 1] = f.n.y; stage[1][t3 + 2] = f.n.z;
     }
     if (want_global) {
-      float3 gv = v, gn = n;
-      if (a.poses) {
-        gv = rigid_apply(s_pose, v.x, v.y, v.z);
-        gv.x *= vf; gv.y *= vf; gv.z *= vf;
-        gn = rotate(s_pose, n.x, n.y, n.z);
-      }
-      stage[2][t3] = gv.x; stage[2][t3 + 1] = gv.y; stage[2][t3 + 2] = gv.z;
-      stage[3][t3] = gn.x; stage[3][t3 + 1] = gn.y; stage[3][t3 + 2] = gn.z;
+      stage[2][t3] = f.gv.x; stage[2][t3 + 1] = f.gv.y; stage[2][t3 + 2] = f.gv.z;
+      stage[3][t3] = f.gn.x; stage[3][t3 + 1] = f.gn.y; stage[3][t3 + 2] = f.gn.z;
     }
   }
   __syncthreads();

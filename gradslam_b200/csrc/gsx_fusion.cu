@@ -13,7 +13,7 @@ namespace gsx {
 
 constexpr int kBlock = 256;
 #ifndef GSX_KPIX
-#define GSX_KPIX 4
+#define GSX_KPIX 2
 #endif
 constexpr int kTilePix = kBlock * GSX_KPIX;  // pixels per merge tile (must equal kMergeTile)
 
@@ -69,7 +69,9 @@ struct ProjectArgs {
   int64_t pose_bstride;
   const float *K;
   int64_t K_bstride;
-  const float *gv, *gn;  // (B,H,W,3)
+  const float *gv, *gn;  // (B,H,W,3) materialised frame maps, or null: sample the depth image on the fly
+  const float *depth;    // (B,H,W) live depth (used when gv/gn are null)
+  int64_t depth_bstride;
   int B, H, W;
   float dist_th, dot_th, u_hi, v_hi;  // u_hi = float(W - 0.999), v_hi = float(H - 0.999)
   U128 *best;
@@ -77,35 +79,46 @@ struct ProjectArgs {
 };
 
 #ifndef GSX_KPTS
-#define GSX_KPTS 4
+#define GSX_KPTS 1
 #endif
 constexpr int kPts = GSX_KPTS;  // map points per thread (independent chains -> 4x memory-level parallelism)
 
-__global__ void __launch_bounds__(kBlock) k_project_select(ProjectArgs a) {
-  __shared__ Rigid s_tinv;
+#ifndef GSX_K2_MINB
+#define GSX_K2_MINB 5
+#endif
+template <bool kFused>
+__global__ void __launch_bounds__(kBlock, GSX_K2_MINB) k_project_select(ProjectArgs a) {
+  __shared__ Rigid s_pose, s_tinv;
   __shared__ float s_k[12];
+  __shared__ KInv s_kinv;
   const int b = blockIdx.y;
   const int count = a.counts[b];
   const int chunk = kBlock * kPts;
   if ((int64_t)blockIdx.x * chunk >= count) return;
-  if (threadIdx.x == 0) s_tinv = rigid_inverse(load_rigid(a.poses + b * a.pose_bstride));
+  if (threadIdx.x == 0) {
+    s_pose = load_rigid(a.poses + b * a.pose_bstride);
+    s_tinv = rigid_inverse(s_pose);
+  }
   if (threadIdx.x >= 32 && threadIdx.x < 44) s_k[threadIdx.x - 32] = __ldg(a.K + b * a.K_bstride + (threadIdx.x - 32));
+  if (threadIdx.x == 64) s_kinv = load_kinv(a.K + b * a.K_bstride);
   __syncthreads();
-  const Rigid Tinv = s_tinv;
-  float k[12];
-#pragma unroll
-  for (int i = 0; i < 12; ++i) k[i] = s_k[i];
   const int P = a.H * a.W;
   const float *pts = a.pts + (int64_t)b * a.cap * 3;
   const float *nrm = a.nrm + (int64_t)b * a.cap * 3;
   const float *cc = a.cc + (int64_t)b * a.cap;
-  const float *gv = a.gv + (int64_t)b * P * 3;
-  const float *gn = a.gn + (int64_t)b * P * 3;
+  const float *gv = kFused ? nullptr : a.gv + (int64_t)b * P * 3;
+  const float *gn = kFused ? nullptr : a.gn + (int64_t)b * P * 3;
+  const float *dimg = a.depth + b * a.depth_bstride;
   U128 *best = a.best + (int64_t)b * P;
   unsigned int n_active = 0;
+  // CAS results are consumed one iteration late, so the ~L2 round trip of the atomic overlaps the next points
+  U128 mine[kPts], old[kPts];
+  int pend_pix[kPts];
+#pragma unroll
+  for (int j = 0; j < kPts; ++j) pend_pix[j] = -1;
   for (int64_t base = (int64_t)blockIdx.x * chunk; base < count; base += (int64_t)gridDim.x * chunk) {
     int n[kPts], pix[kPts];
-    float px[kPts], py[kPts], pz[kPts], d2[kPts];
+    float px[kPts], py[kPts], pz[kPts];
     bool live[kPts];
     // stage 1: positions (independent coalesced loads), projection, frustum test
 #pragma unroll
@@ -121,10 +134,10 @@ __global__ void __launch_bounds__(kBlock) k_project_select(ProjectArgs a) {
     for (int j = 0; j < kPts; ++j) {
       // world -> camera (pointclouds.py:526-573), then pinhole projection with the 4x4 K on the homogeneous
       // point (projutils.py:92-238): z == 0 divides by 1.
-      const float3 q = rigid_apply(Tinv, px[j], py[j], pz[j]);
-      const float hx = ((k[0] * q.x + k[1] * q.y) + k[2] * q.z) + k[3];
-      const float hy = ((k[4] * q.x + k[5] * q.y) + k[6] * q.z) + k[7];
-      const float hz = ((k[8] * q.x + k[9] * q.y) + k[10] * q.z) + k[11];
+      const float3 q = rigid_apply(s_tinv, px[j], py[j], pz[j]);
+      const float hx = ((s_k[0] * q.x + s_k[1] * q.y) + s_k[2] * q.z) + s_k[3];
+      const float hy = ((s_k[4] * q.x + s_k[5] * q.y) + s_k[6] * q.z) + s_k[7];
+      const float hz = ((s_k[8] * q.x + s_k[9] * q.y) + s_k[10] * q.z) + s_k[11];
       const float den = (hz != 0.0f) ? hz : 1.0f;
       const float u = hx / den, v = hy / den;
       // fusionutils.py:259-266
@@ -136,56 +149,61 @@ __global__ void __launch_bounds__(kBlock) k_project_select(ProjectArgs a) {
       pix[j] = live[j] ? h * a.W + w : 0;
       n_active += live[j] ? 1u : 0u;
     }
-    // stage 2: frame vertex under the projection; are_points_close (fusionutils.py:130): ||frame - map|| < dist_th
-    float fx[kPts], fy[kPts], fz[kPts];
+    // stage 2: the frame sample under each projection (vertex + normal in the world frame) and the map normal
+    float3 fv[kPts], fnm[kPts];
+    float mx[kPts], my[kPts], mz[kPts], c0[kPts];
 #pragma unroll
     for (int j = 0; j < kPts; ++j) {
       if (live[j]) {
-        fx[j] = __ldg(gv + (int64_t)pix[j] * 3);
-        fy[j] = __ldg(gv + (int64_t)pix[j] * 3 + 1);
-        fz[j] = __ldg(gv + (int64_t)pix[j] * 3 + 2);
-      }
-    }
-#pragma unroll
-    for (int j = 0; j < kPts; ++j) {
-      if (live[j]) {
-        const float dx = fx[j] - px[j], dy = fy[j] - py[j], dz = fz[j] - pz[j];
-        d2[j] = (dx * dx + dy * dy) + dz * dz;
-        live[j] = sqrtf(d2[j]) < a.dist_th;
-      }
-    }
-    // stage 3: are_normals_similar (fusionutils.py:187-195): n_frame . n_map > dot_th; confidence count
-    float nx[kPts], ny[kPts], nz[kPts], mx[kPts], my[kPts], mz[kPts], c0[kPts];
-#pragma unroll
-    for (int j = 0; j < kPts; ++j) {
-      if (live[j]) {
-        nx[j] = __ldg(gn + (int64_t)pix[j] * 3);
-        ny[j] = __ldg(gn + (int64_t)pix[j] * 3 + 1);
-        nz[j] = __ldg(gn + (int64_t)pix[j] * 3 + 2);
+        if (kFused) {
+          const int h = pix[j] / a.W, w = pix[j] - h * a.W;
+          const FrameSample f = frame_sample<true>(dimg, s_kinv, &s_pose, h, w, a.H, a.W);
+          fv[j] = f.gv;
+          fnm[j] = f.gn;
+        } else {
+          const float *g = gv + (int64_t)pix[j] * 3, *q = gn + (int64_t)pix[j] * 3;
+          fv[j] = make_float3(__ldg(g), __ldg(g + 1), __ldg(g + 2));
+          fnm[j] = make_float3(__ldg(q), __ldg(q + 1), __ldg(q + 2));
+        }
         mx[j] = __ldg(nrm + (int64_t)n[j] * 3);
         my[j] = __ldg(nrm + (int64_t)n[j] * 3 + 1);
         mz[j] = __ldg(nrm + (int64_t)n[j] * 3 + 2);
         c0[j] = __ldg(cc + n[j]);
       }
     }
+    // stage 3: tests + first (optimistic) CAS of every surviving candidate; nothing is awaited here
 #pragma unroll
     for (int j = 0; j < kPts; ++j) {
+      if (pend_pix[j] >= 0) {  // settle the previous iteration's CAS before re-using its slot
+        atomic_max_rec128_finish(best + pend_pix[j], mine[j], old[j]);
+        pend_pix[j] = -1;
+      }
       if (live[j]) {
-        const float dot = (nx[j] * mx[j] + ny[j] * my[j]) + nz[j] * mz[j];
-        if (dot > a.dot_th) {
+        // are_points_close (fusionutils.py:130): ||frame - map|| < dist_th
+        const float dx = fv[j].x - px[j], dy = fv[j].y - py[j], dz = fv[j].z - pz[j];
+        const float d2 = (dx * dx + dy * dy) + dz * dz;
+        // are_normals_similar (fusionutils.py:187-195): n_frame . n_map > dot_th
+        const float dot = (fnm[j].x * mx[j] + fnm[j].y * my[j]) + fnm[j].z * mz[j];
+        live[j] = (sqrtf(d2) < a.dist_th) && (dot > a.dot_th);
+        if (live[j]) {
           // sort key of find_best_unique_correspondences (fusionutils.py:491-517): 1/(cc+1e-20), then the
           // squared distance (map - frame)^2 (== d2: squares are sign-independent), then n.
           const float inv_cc = 1.0f / (c0[j] + 1e-20f);
           // positive floats order like their bit patterns; flip negatives so the order stays total.
           unsigned int kb = __float_as_uint(inv_cc);
           kb = (kb & 0x80000000u) ? ~kb : (kb | 0x80000000u);
-          const unsigned int rb = __float_as_uint(d2[j]) | 0x80000000u;  // d2 >= 0
+          const unsigned int rb = __float_as_uint(d2) | 0x80000000u;  // d2 >= 0
           const unsigned long long hi = ((unsigned long long)kb << 32) | rb;
-          atomic_min_key128(best + pix[j], hi, (unsigned long long)n[j]);
+          mine[j] = U128{~(unsigned long long)n[j], ~hi};
+          old[j] = cas128(best + pix[j], U128{0ull, 0ull}, mine[j]);
+          pend_pix[j] = pix[j];
         }
       }
     }
   }
+#pragma unroll
+  for (int j = 0; j < kPts; ++j)
+    if (pend_pix[j] >= 0) atomic_max_rec128_finish(best + pend_pix[j], mine[j], old[j]);
   // bookkeeping for the roofline's algorithmic-byte count: one atomic per warp
   n_active = __reduce_add_sync(0xffffffffu, n_active);
   if ((threadIdx.x & 31) == 0 && n_active) atomicAdd(a.stats + 2 * b, (unsigned long long)n_active);
@@ -203,7 +221,9 @@ struct MergeArgs {
   int64_t rgb_bstride;
   const float *K;
   int64_t K_bstride;
-  const float *gv, *gn;
+  const float *gv, *gn;  // materialised (B,H,W,3) maps to merge / append, or null: sample the depth on the fly
+  const float *poses;    // (used when gv/gn are null)
+  int64_t pose_bstride;
   int B, H, W;
   float two_sigma_sq;
   Workspace ws;
@@ -227,7 +247,7 @@ __device__ __forceinline__ void st_release_u64(unsigned long long *p, unsigned l
 }
 
 #ifndef GSX_KPIX
-#define GSX_KPIX 4
+#define GSX_KPIX 2
 #endif
 constexpr int kPix = GSX_KPIX;             // pixels per thread
 constexpr int kMergeTile = kBlock * kPix;  // pixels per CTA
@@ -256,7 +276,12 @@ __device__ __forceinline__ unsigned int lookback_warp(const unsigned long long *
   return excl;
 }
 
-__global__ void __launch_bounds__(kBlock) k_merge_append(MergeArgs a) {
+#ifndef GSX_K4_MINB
+#define GSX_K4_MINB 4
+#endif
+template <bool kFused>
+__global__ void __launch_bounds__(kBlock, GSX_K4_MINB) k_merge_append(MergeArgs a) {
+  __shared__ Rigid s_pose;
   __shared__ int s_tile;
   __shared__ int s_warp_sums[kPix][kBlock / 32];
   __shared__ int s_excl;
@@ -269,6 +294,8 @@ __global__ void __launch_bounds__(kBlock) k_merge_append(MergeArgs a) {
     s_tile = (int)(t - (a.epoch - 1u) * (unsigned int)T);
   }
   if (threadIdx.x == 32) s_k = load_kinv(a.K + b * a.K_bstride);
+  if (kFused && threadIdx.x == 64) s_pose = load_rigid(a.poses + b * a.pose_bstride);
+  const int count_in = a.counts_in[b];  // loaded early: its latency hides behind everything below
   __syncthreads();
   const int tile = s_tile;
   const int P = a.H * a.W;
@@ -326,8 +353,8 @@ __global__ void __launch_bounds__(kBlock) k_merge_append(MergeArgs a) {
   float *col = a.col + (int64_t)b * a.cap * 3;
   float *cc = a.cc ? a.cc + (int64_t)b * a.cap : nullptr;
   const KInv k = s_k;
-  const float *gvb = a.gv + (int64_t)b * P * 3;
-  const float *gnb = a.gn + (int64_t)b * P * 3;
+  const float *gvb = kFused ? nullptr : a.gv + (int64_t)b * P * 3;
+  const float *gnb = kFused ? nullptr : a.gn + (int64_t)b * P * 3;
   const float *rgb = a.rgb + b * a.rgb_bstride;
 
   // per-pixel frame sample (loads of the 4 pixels are independent)
@@ -336,12 +363,26 @@ __global__ void __launch_bounds__(kBlock) k_merge_append(MergeArgs a) {
 #pragma unroll
   for (int j = 0; j < kPix; ++j) {
     if (matched[j] || is_new[j]) {
-      const float *g = gvb + (int64_t)pix[j] * 3;
-      const float *h = gnb + (int64_t)pix[j] * 3;
       const float *c = rgb + (int64_t)pix[j] * 3;
-      fp[j] = make_float3(__ldg(g), __ldg(g + 1), __ldg(g + 2));
-      fn[j] = make_float3(__ldg(h), __ldg(h + 1), __ldg(h + 2));
       fc[j] = make_float3(__ldg(c), __ldg(c + 1), __ldg(c + 2));
+      if (kFused) {
+        const int h = pix[j] / a.W, w = pix[j] - h * a.W;
+        const FrameSample f = frame_sample<true>(depth, k, &s_pose, h, w, a.H, a.W);
+        fp[j] = f.gv;
+        fn[j] = f.gn;
+        // alpha from the LOCAL vertex (fusionutils.py:657, 69-72)
+        const float s = (f.v.x * f.v.x + f.v.y * f.v.y) + f.v.z * f.v.z;
+        alpha[j] = fminf(fmaxf(expf((-s) / a.two_sigma_sq), 1e-7f), 1.01f);
+      } else {
+        const float *g = gvb + (int64_t)pix[j] * 3;
+        const float *q = gnb + (int64_t)pix[j] * 3;
+        fp[j] = make_float3(__ldg(g), __ldg(g + 1), __ldg(g + 2));
+        fn[j] = make_float3(__ldg(q), __ldg(q + 1), __ldg(q + 2));
+        const int h = pix[j] / a.W, w = pix[j] - h * a.W;
+        const float3 v = backproject(k, (float)w, (float)h, d[j]);
+        const float s = (v.x * v.x + v.y * v.y) + v.z * v.z;
+        alpha[j] = fminf(fmaxf(expf((-s) / a.two_sigma_sq), 1e-7f), 1.01f);
+      }
     }
   }
   // matched map rows: issue all loads first, then the arithmetic and the stores
@@ -361,13 +402,6 @@ __global__ void __launch_bounds__(kBlock) k_merge_append(MergeArgs a) {
   }
 #pragma unroll
   for (int j = 0; j < kPix; ++j) {
-    if (matched[j] || is_new[j]) {
-      // alpha from the LOCAL vertex (fusionutils.py:657, 69-72)
-      const int h = pix[j] / a.W, w = pix[j] - h * a.W;
-      const float3 v = backproject(k, (float)w, (float)h, d[j]);
-      const float s = (v.x * v.x + v.y * v.y) + v.z * v.z;
-      alpha[j] = fminf(fmaxf(expf((-s) / a.two_sigma_sq), 1e-7f), 1.01f);
-    }
     if (matched[j] && cc) {
       // confidence-weighted running mean (fusionutils.py:678-699); exactly one pixel owns this map row
       const int64_t n = (int64_t)(~rec[j].lo);
@@ -396,7 +430,7 @@ __global__ void __launch_bounds__(kBlock) k_merge_append(MergeArgs a) {
     }
   }
   __syncthreads();
-  const int64_t base = (int64_t)a.counts_in[b] + s_excl;
+  const int64_t base = (int64_t)count_in + s_excl;
 #pragma unroll
   for (int j = 0; j < kPix; ++j) {
     if (is_new[j]) {
@@ -425,14 +459,20 @@ int launch_project_select(const ProjectArgs &a, int64_t max_count, cudaStream_t 
   const int64_t cap_blocks = (int64_t)kNumSMs * 16;  // grid-stride beyond 16 CTAs per SM
   if (bx * a.B > cap_blocks) bx = (cap_blocks + a.B - 1) / a.B;
   if (bx < 1) bx = 1;
-  k_project_select<<<dim3((unsigned)bx, (unsigned)a.B), kBlock, 0, stream>>>(a);
+  if (a.gv)
+    k_project_select<false><<<dim3((unsigned)bx, (unsigned)a.B), kBlock, 0, stream>>>(a);
+  else
+    k_project_select<true><<<dim3((unsigned)bx, (unsigned)a.B), kBlock, 0, stream>>>(a);
   GSX_CHECK_LAUNCH("gsx_fusion_project_select");
   return 0;
 }
 
 int launch_merge_append(const MergeArgs &a, cudaStream_t stream) {
   if (a.B == 0) return 0;
-  k_merge_append<<<dim3((unsigned)a.ws.tiles, (unsigned)a.B), kBlock, 0, stream>>>(a);
+  if (a.gv)
+    k_merge_append<false><<<dim3((unsigned)a.ws.tiles, (unsigned)a.B), kBlock, 0, stream>>>(a);
+  else
+    k_merge_append<true><<<dim3((unsigned)a.ws.tiles, (unsigned)a.B), kBlock, 0, stream>>>(a);
   GSX_CHECK_LAUNCH("gsx_fusion_merge_append");
   return 0;
 }
@@ -454,18 +494,21 @@ extern "C" int64_t gsx_fusion_workspace_stats_offset(int B, int H, int W) {
 extern "C" int gsx_fusion_project_select(const float *map_points, const float *map_normals,
                                          const float *map_ccounts, const int32_t *counts, int64_t capacity,
                                          int64_t max_count, const float *poses, int64_t pose_bstride,
-                                         const float *intrinsics, int64_t K_bstride, const float *gvertex,
-                                         const float *gnormal, int B, int H, int W, float dist_th, float dot_th,
-                                         void *workspace, void *stream) {
+                                         const float *intrinsics, int64_t K_bstride, const float *depth,
+                                         int64_t depth_bstride, const float *gvertex, const float *gnormal, int B,
+                                         int H, int W, float dist_th, float dot_th, void *workspace, void *stream) {
   GSX_CHECK_ARG(B >= 0 && H >= 2 && W >= 2, "gsx_fusion_project_select: bad extents B=%d H=%d W=%d", B, H, W);
   if (max_count <= 0 || B == 0) return 0;
   GSX_CHECK_ARG(map_points && map_normals && map_ccounts && counts, "gsx_fusion_project_select: null map pointer");
-  GSX_CHECK_ARG(poses && intrinsics && gvertex && gnormal && workspace, "gsx_fusion_project_select: null frame pointer");
+  GSX_CHECK_ARG(poses && intrinsics && workspace, "gsx_fusion_project_select: null frame pointer");
+  GSX_CHECK_ARG((gvertex && gnormal) || (depth && !gvertex && !gnormal),
+                "gsx_fusion_project_select: pass both frame maps, or neither together with the depth image");
   GSX_CHECK_ARG(max_count <= capacity, "gsx_fusion_project_select: max_count %lld > capacity %lld",
                 (long long)max_count, (long long)capacity);
   const Workspace ws = carve(workspace, B, H, W);
   ProjectArgs a{map_points, map_normals, map_ccounts, counts, capacity, poses, pose_bstride, intrinsics, K_bstride,
-                gvertex, gnormal, B, H, W, dist_th, dot_th, (float)(W - 0.999), (float)(H - 0.999), ws.best, ws.stats};
+                gvertex, gnormal, depth, depth_bstride, B, H, W, dist_th, dot_th, (float)(W - 0.999), (float)(H - 0.999), ws.best,
+                ws.stats};
   return launch_project_select(a, max_count, (cudaStream_t)stream);
 }
 
@@ -473,20 +516,22 @@ extern "C" int gsx_fusion_merge_append(float *map_points, float *map_normals, fl
                                        float *map_ccounts, const int32_t *counts_in, int32_t *counts_out,
                                        int64_t capacity, const float *depth, int64_t depth_bstride,
                                        const float *rgb, int64_t rgb_bstride, const float *intrinsics,
-                                       int64_t K_bstride, const float *gvertex, const float *gnormal, int B,
-                                       int H, int W, double sigma, void *workspace, uint32_t epoch,
-                                       int32_t *overflow_flag, void *stream) {
+                                       int64_t K_bstride, const float *poses, int64_t pose_bstride,
+                                       const float *gvertex, const float *gnormal, int B, int H, int W,
+                                       double sigma, void *workspace, uint32_t epoch, int32_t *overflow_flag,
+                                       void *stream) {
   GSX_CHECK_ARG(B >= 0 && H >= 2 && W >= 2, "gsx_fusion_merge_append: bad extents B=%d H=%d W=%d", B, H, W);
   if (B == 0) return 0;
   GSX_CHECK_ARG(map_points && map_normals && map_colors && counts_in && counts_out,
                 "gsx_fusion_merge_append: null map pointer");  // map_ccounts may be NULL (aggregation-only maps)
   GSX_CHECK_ARG(counts_in != counts_out, "gsx_fusion_merge_append: counts_in and counts_out must not alias");
-  GSX_CHECK_ARG(depth && rgb && intrinsics && gvertex && gnormal && workspace && overflow_flag,
-                "gsx_fusion_merge_append: null frame pointer");
+  GSX_CHECK_ARG(depth && rgb && intrinsics && workspace && overflow_flag, "gsx_fusion_merge_append: null frame pointer");
+  GSX_CHECK_ARG((gvertex && gnormal) || (poses && !gvertex && !gnormal),
+                "gsx_fusion_merge_append: pass both frame maps, or neither together with the poses");
   GSX_CHECK_ARG(epoch >= 1 && epoch < (1u << 30), "gsx_fusion_merge_append: epoch out of range");
   const Workspace ws = carve(workspace, B, H, W);
   MergeArgs a{map_points, map_normals, map_colors, map_ccounts, counts_in, counts_out, capacity, depth, depth_bstride,
-              rgb, rgb_bstride, intrinsics, K_bstride, gvertex, gnormal, B, H, W,
+              rgb, rgb_bstride, intrinsics, K_bstride, gvertex, gnormal, poses, pose_bstride, B, H, W,
               (float)(2.0 * (sigma * sigma)), ws, epoch, overflow_flag};
   return launch_merge_append(a, (cudaStream_t)stream);
 }

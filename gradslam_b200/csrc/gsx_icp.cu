@@ -1,0 +1,724 @@
+// Point-to-plane ICP / gradICP odometry for sm_100a, batched over B elements, no host synchronisation.
+//
+//   k_icp_gather_src     live frame -> source cloud: lattice pixels (every ds-th row/column) with valid depth,
+//                        world-frame vertex at the PREVIOUS pose, stable row-major compaction
+//                        (downsample_rgbdimages, gradslam/odometry/icputils.py:623-669)
+//   k_icp_gather_tgt     map -> target cloud: map points inside the previous frame's frustum whose pixel lies on
+//                        the lattice, stable compaction in point order (find_active_map_points +
+//                        downsample_pointclouds, slam/fusionutils.py:198-287, odometry/icputils.py:548-620)
+//   k_icp_knn_linearize  exact 1-NN of every source point in the target cloud (brute force over shared-memory
+//                        tiles, lowest index wins ties; restates chamferdist knn_points, icputils.py:200) fused
+//                        with the point-to-plane row build and the reduction of J^T J (21), J^T r (6), r^T r (1)
+//                        (gauss_newton_solve + the normal equations, icputils.py:85-90, 203-232).  A pending
+//                        4x4 transform is applied to the source on load (transform_pointcloud, geometryutils.py
+//                        :737-794) and optionally written back.
+//   k_icp_solve          one warp per element: fixed-order reduction of the block partials, damped 6x6 solve
+//                        (solve_linear_system, icputils.py:22-90), se3_exp (geometry/se3utils.py:77-115)
+//   k_icp_update         one warp per element: look-ahead error, LM accept/reject (icputils.py:356-365) or gradLM
+//                        smooth gates (icputils.py:527-543), pose accumulation
+#include "gsx_common.cuh"
+#include "../../include/gsx.h"
+
+namespace gsx {
+
+constexpr int kIcpBlock = 256;
+constexpr int kTgtTile = 1024;  // target points staged in shared memory per step (16 KB as float4)
+constexpr int kNumSums = 28;    // 21 upper-triangular J^T J + 6 J^T r + r^T r
+
+// ---------------------------------------------------------------------------------------------------------
+// gather: source cloud
+// ---------------------------------------------------------------------------------------------------------
+struct GatherSrcArgs {
+  const float *depth;
+  int64_t depth_bstride;
+  const float *K;
+  int64_t K_bstride;
+  const float *poses;  // pose to place the frame at (the previous frame's pose)
+  int64_t pose_bstride;
+  int B, H, W, ds;
+  float *src;        // (B, ns_cap, 3)
+  int32_t *src_count;  // (B)
+  int ns_cap;
+};
+
+__global__ void __launch_bounds__(1024) k_icp_gather_src(GatherSrcArgs a) {
+  __shared__ int s_warp[32];
+  __shared__ int s_base;
+  __shared__ KInv s_k;
+  __shared__ Rigid s_pose;
+  const int b = blockIdx.x;
+  if (threadIdx.x == 0) {
+    s_k = load_kinv(a.K + b * a.K_bstride);
+    s_base = 0;
+  }
+  if (threadIdx.x == 32) s_pose = load_rigid(a.poses + b * a.pose_bstride);
+  __syncthreads();
+  const int Hs = (a.H + a.ds - 1) / a.ds, Ws = (a.W + a.ds - 1) / a.ds;
+  const int total = Hs * Ws;
+  const float *dimg = a.depth + b * a.depth_bstride;
+  float *out = a.src + (int64_t)b * a.ns_cap * 3;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int base = 0; base < total; base += 1024) {
+    const int i = base + threadIdx.x;
+    bool flag = false;
+    float3 gv = make_float3(0.f, 0.f, 0.f);
+    if (i < total) {
+      const int hs = i / Ws, ws = i - hs * Ws;
+      const FrameSample f = frame_sample<false>(dimg, s_k, &s_pose, hs * a.ds, ws * a.ds, a.H, a.W);
+      flag = f.d > 0.0f;
+      gv = f.gv;
+    }
+    const unsigned int ballot = __ballot_sync(0xffffffffu, flag);
+    if (lane == 0) s_warp[warp] = __popc(ballot);
+    __syncthreads();
+    int excl = s_base, tot = 0;
+    for (int w = 0; w < 32; ++w) {
+      const int c = s_warp[w];
+      if (w < warp) excl += c;
+      tot += c;
+    }
+    excl += __popc(ballot & ((1u << lane) - 1u));
+    if (flag && excl < a.ns_cap) {
+      out[(int64_t)excl * 3 + 0] = gv.x;
+      out[(int64_t)excl * 3 + 1] = gv.y;
+      out[(int64_t)excl * 3 + 2] = gv.z;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) s_base += tot;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) a.src_count[b] = min(s_base, a.ns_cap);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// gather: target cloud (stable compaction of lattice-active map points; decoupled look-back over tiles)
+// ---------------------------------------------------------------------------------------------------------
+struct GatherTgtArgs {
+  const float *pts, *nrm;
+  const int32_t *counts;
+  int64_t cap;
+  const float *poses;
+  int64_t pose_bstride;
+  const float *K;
+  int64_t K_bstride;
+  int B, H, W, ds;
+  float u_hi, v_hi;
+  float *tgt_p, *tgt_n;  // (B, nt_cap, 3)
+  int32_t *tgt_count;    // (B)
+  int nt_cap;
+  unsigned long long *tile_state;  // (B, tiles)
+  unsigned int *ticket;            // (B)
+  int tiles;                       // tiles per element (= ceil(max_count / 1024))
+  unsigned int epoch;
+};
+
+constexpr unsigned long long kAgg = 1ull, kPrefix = 2ull;
+__device__ __forceinline__ unsigned long long icp_pack(unsigned int epoch, unsigned long long flag, unsigned int v) {
+  return ((unsigned long long)epoch << 34) | (flag << 32) | v;
+}
+__device__ __forceinline__ unsigned long long icp_ld_acquire(const unsigned long long *p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void icp_st_release(unsigned long long *p, unsigned long long v) {
+  asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+__global__ void __launch_bounds__(kIcpBlock) k_icp_gather_tgt(GatherTgtArgs a) {
+  __shared__ Rigid s_tinv;
+  __shared__ float s_k[12];
+  __shared__ int s_tile, s_excl;
+  __shared__ int s_warp[4][kIcpBlock / 32];
+  const int b = blockIdx.y;
+  if (threadIdx.x == 0) {
+    // dynamic tile id.  The block that draws the last ticket re-arms the counter for the next launch (nobody
+    // else will touch it any more in this one), so the number of tiles may differ from launch to launch.
+    const unsigned int t = atomicAdd(a.ticket + b, 1u);
+    if (t == (unsigned int)a.tiles - 1u) a.ticket[b] = 0u;
+    s_tile = (int)t;
+    s_tinv = rigid_inverse(load_rigid(a.poses + b * a.pose_bstride));
+  }
+  if (threadIdx.x >= 32 && threadIdx.x < 44) s_k[threadIdx.x - 32] = __ldg(a.K + b * a.K_bstride + (threadIdx.x - 32));
+  __syncthreads();
+  const int tile = s_tile;
+  const int count = a.counts[b];
+  const float *pts = a.pts + (int64_t)b * a.cap * 3;
+  const float *nrm = a.nrm + (int64_t)b * a.cap * 3;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int n[4], wexcl[4];
+  bool keep[4];
+  float px[4], py[4], pz[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    n[j] = tile * 1024 + j * kIcpBlock + threadIdx.x;
+    keep[j] = n[j] < count;
+    const int nn = keep[j] ? n[j] : 0;
+    px[j] = __ldg(pts + (int64_t)nn * 3);
+    py[j] = __ldg(pts + (int64_t)nn * 3 + 1);
+    pz[j] = __ldg(pts + (int64_t)nn * 3 + 2);
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    // identical to the projection of k_project_select (fusionutils.py:249-274)
+    const float3 q = rigid_apply(s_tinv, px[j], py[j], pz[j]);
+    const float hx = ((s_k[0] * q.x + s_k[1] * q.y) + s_k[2] * q.z) + s_k[3];
+    const float hy = ((s_k[4] * q.x + s_k[5] * q.y) + s_k[6] * q.z) + s_k[7];
+    const float hz = ((s_k[8] * q.x + s_k[9] * q.y) + s_k[10] * q.z) + s_k[11];
+    const float den = (hz != 0.0f) ? hz : 1.0f;
+    const float u = hx / den, v = hy / den;
+    keep[j] = keep[j] && (u > -1e-3f) && (u < a.u_hi) && (v > -1e-3f) && (v < a.v_hi) && (q.z > 0.0f);
+    int w = (int)rintf(u), h = (int)rintf(v);
+    w = min(max(w, 0), a.W - 1);
+    h = min(max(h, 0), a.H - 1);
+    keep[j] = keep[j] && (h % a.ds == 0) && (w % a.ds == 0);  // icputils.py:596-597
+    const unsigned int ballot = __ballot_sync(0xffffffffu, keep[j]);
+    wexcl[j] = __popc(ballot & ((1u << lane) - 1u));
+    if (lane == 0) s_warp[j][warp] = __popc(ballot);
+  }
+  __syncthreads();
+  int total = 0, bexcl[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    bexcl[j] = total;
+#pragma unroll
+    for (int i = 0; i < kIcpBlock / 32; ++i) {
+      const int c = s_warp[j][i];
+      if (i < warp) bexcl[j] += c;
+      total += c;
+    }
+  }
+  unsigned long long *state = a.tile_state + (int64_t)b * a.tiles;
+  if (threadIdx.x == 0 && tile + 1 < a.tiles) icp_st_release(state + tile, icp_pack(a.epoch, kAgg, (unsigned)total));
+  if (warp == 0) {
+    unsigned int excl = 0;
+    for (int base = tile - 1; base >= 0; base -= 32) {
+      const int j = base - lane;
+      unsigned long long s = 0ull;
+      if (j >= 0) {
+        do {
+          s = icp_ld_acquire(state + j);
+        } while ((unsigned int)(s >> 34) != a.epoch);
+      }
+      const bool is_prefix = (j >= 0) && (((s >> 32) & 3ull) == kPrefix);
+      const unsigned int pm = __ballot_sync(0xffffffffu, is_prefix);
+      const int first = pm ? (__ffs(pm) - 1) : 32;
+      const unsigned int v = (j >= 0 && lane <= first) ? (unsigned int)s : 0u;
+      excl += __reduce_add_sync(0xffffffffu, v);
+      if (pm) break;
+    }
+    if (lane == 0) {
+      if (tile + 1 < a.tiles) icp_st_release(state + tile, icp_pack(a.epoch, kPrefix, excl + (unsigned)total));
+      s_excl = (int)excl;
+    }
+  }
+  __syncthreads();
+  float *op = a.tgt_p + (int64_t)b * a.nt_cap * 3;
+  float *on = a.tgt_n + (int64_t)b * a.nt_cap * 3;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    if (keep[j]) {
+      const int pos = s_excl + bexcl[j] + wexcl[j];
+      if (pos < a.nt_cap) {
+        op[(int64_t)pos * 3 + 0] = px[j];
+        op[(int64_t)pos * 3 + 1] = py[j];
+        op[(int64_t)pos * 3 + 2] = pz[j];
+        on[(int64_t)pos * 3 + 0] = __ldg(nrm + (int64_t)n[j] * 3);
+        on[(int64_t)pos * 3 + 1] = __ldg(nrm + (int64_t)n[j] * 3 + 1);
+        on[(int64_t)pos * 3 + 2] = __ldg(nrm + (int64_t)n[j] * 3 + 2);
+      }
+    }
+  }
+  if (tile == a.tiles - 1 && threadIdx.x == 0) a.tgt_count[b] = min(s_excl + total, a.nt_cap);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// exact 1-NN + point-to-plane linearisation + block reduction
+// ---------------------------------------------------------------------------------------------------------
+struct KnnArgs {
+  float *src;  // (B, ns_stride, 3); read, optionally rewritten with the transformed points
+  const int32_t *src_count;
+  int ns_stride;
+  const float *tgt_p, *tgt_n;  // (B, nt_stride, 3)
+  const int32_t *tgt_count;
+  int nt_stride;
+  const float *pre;  // (B,16) transform applied to src on load, or null
+  int write_back;
+  float dist_thresh;  // compared with the SQUARED nn distance as the reference does (icputils.py:206)
+  int use_thresh;
+  float *partials;  // (B, gridDim.x, 28)
+  int64_t *nn_idx;  // optional (B, ns_stride): nn index per source point (-1 = filtered / invalid)
+  float *nn_d2;     // optional (B, ns_stride)
+};
+
+__global__ void __launch_bounds__(kIcpBlock) k_icp_knn_linearize(KnnArgs a) {
+  __shared__ float4 s_t[kTgtTile];
+  __shared__ float s_red[kIcpBlock / 32][kNumSums];
+  __shared__ Rigid s_pre;
+  const int b = blockIdx.y;
+  const int ns = a.src_count[b], nt = a.tgt_count[b];
+  const int i = blockIdx.x * kIcpBlock + threadIdx.x;
+  if (a.pre && threadIdx.x == 0) s_pre = load_rigid(a.pre + b * 16);
+  __syncthreads();
+  float *src = a.src + (int64_t)b * a.ns_stride * 3;
+  const float *tp = a.tgt_p + (int64_t)b * a.nt_stride * 3;
+  const float *tn = a.tgt_n + (int64_t)b * a.nt_stride * 3;
+  const bool valid = i < ns;
+  float sx = 0.f, sy = 0.f, sz = 0.f;
+  if (valid) {
+    sx = src[(int64_t)i * 3];
+    sy = src[(int64_t)i * 3 + 1];
+    sz = src[(int64_t)i * 3 + 2];
+    if (a.pre) {
+      const float3 q = rigid_apply(s_pre, sx, sy, sz);
+      sx = q.x; sy = q.y; sz = q.z;
+      if (a.write_back) {
+        src[(int64_t)i * 3] = sx;
+        src[(int64_t)i * 3 + 1] = sy;
+        src[(int64_t)i * 3 + 2] = sz;
+      }
+    }
+  }
+  float best = 0.0f;
+  int bi = -1;
+  if (blockIdx.x * kIcpBlock < ns) {  // whole block idle otherwise (uniform)
+    for (int base = 0; base < nt; base += kTgtTile) {
+      const int m = min(kTgtTile, nt - base);
+      __syncthreads();
+      for (int t = threadIdx.x; t < m; t += kIcpBlock) {
+        const float *p = tp + (int64_t)(base + t) * 3;
+        s_t[t] = make_float4(__ldg(p), __ldg(p + 1), __ldg(p + 2), 0.0f);
+      }
+      __syncthreads();
+      if (valid) {
+#pragma unroll 8
+        for (int t = 0; t < m; ++t) {
+          const float4 p = s_t[t];
+          const float dx = sx - p.x, dy = sy - p.y, dz = sz - p.z;
+          const float d = (dx * dx + dy * dy) + dz * dz;
+          if (bi < 0 || d < best) {  // strict '<' on an ascending scan: lowest index wins ties
+            best = d;
+            bi = base + t;
+          }
+        }
+      }
+    }
+  }
+  bool use = valid && bi >= 0;
+  if (use && a.use_thresh) use = best < a.dist_thresh;
+  if (a.nn_idx && valid) {
+    a.nn_idx[(int64_t)b * a.ns_stride + i] = use ? (int64_t)bi : -1;
+    if (a.nn_d2) a.nn_d2[(int64_t)b * a.ns_stride + i] = best;
+  }
+  float acc[kNumSums];
+#pragma unroll
+  for (int k = 0; k < kNumSums; ++k) acc[k] = 0.0f;
+  if (use) {
+    const float dx = __ldg(tp + (int64_t)bi * 3), dy = __ldg(tp + (int64_t)bi * 3 + 1), dz = __ldg(tp + (int64_t)bi * 3 + 2);
+    const float nx = __ldg(tn + (int64_t)bi * 3), ny = __ldg(tn + (int64_t)bi * 3 + 1), nz = __ldg(tn + (int64_t)bi * 3 + 2);
+    // rows of gauss_newton_solve (icputils.py:227-230)
+    float A[6];
+    A[0] = nx; A[1] = ny; A[2] = nz;
+    A[3] = nz * sy - ny * sz;
+    A[4] = nx * sz - nz * sx;
+    A[5] = ny * sx - nx * sy;
+    const float r = (nx * (dx - sx) + ny * (dy - sy)) + nz * (dz - sz);
+    int k = 0;
+#pragma unroll
+    for (int p = 0; p < 6; ++p)
+#pragma unroll
+      for (int q = p; q < 6; ++q) acc[k++] = A[p] * A[q];
+#pragma unroll
+    for (int p = 0; p < 6; ++p) acc[21 + p] = A[p] * r;
+    acc[27] = r * r;
+  }
+  // deterministic block reduction: butterfly inside the warp, then warps in index order
+#pragma unroll
+  for (int k = 0; k < kNumSums; ++k) {
+    float v = acc[k];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    acc[k] = v;
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane == 0) {
+#pragma unroll
+    for (int k = 0; k < kNumSums; ++k) s_red[warp][k] = acc[k];
+  }
+  __syncthreads();
+  if (threadIdx.x < kNumSums) {
+    float v = 0.0f;
+#pragma unroll
+    for (int w = 0; w < kIcpBlock / 32; ++w) v += s_red[w][threadIdx.x];
+    a.partials[((int64_t)b * gridDim.x + blockIdx.x) * kNumSums + threadIdx.x] = v;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// small per-element kernels: solve, update
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void mat4_mul(const float *A, const float *B, float *C) {
+  // plain 4x4 product, k accumulated left to right (torch.mm on 4x4, icputils.py:362, 543)
+  for (int i = 0; i < 4; ++i)
+    for (int j = 0; j < 4; ++j) {
+      float acc = A[i * 4 + 0] * B[0 * 4 + j];
+      for (int k = 1; k < 4; ++k) acc = acc + A[i * 4 + k] * B[k * 4 + j];
+      C[i * 4 + j] = acc;
+    }
+}
+
+// se3_exp (se3utils.py:77-115): xi = (v, omega) -> 4x4; for ||omega|| < 1e-6 both R and V are I + hat(omega)
+__device__ void se3_exp_dev(const float *xi, float *T) {
+  const float vx = xi[0], vy = xi[1], vz = xi[2], wx = xi[3], wy = xi[4], wz = xi[5];
+  const float W[9] = {0.f, -wz, wy, wz, 0.f, -wx, -wy, wx, 0.f};
+  const float theta = sqrtf((wx * wx + wy * wy) + wz * wz);
+  float R[9], V[9];
+  if (theta < 1e-6f) {
+    for (int i = 0; i < 9; ++i) {
+      const float I = (i % 4 == 0) ? 1.0f : 0.0f;
+      R[i] = I + W[i];
+      V[i] = I + W[i];
+    }
+  } else {
+    const float s = sinf(theta), c = cosf(theta);
+    float W2[9];
+    for (int i = 0; i < 3; ++i)
+      for (int j = 0; j < 3; ++j) {
+        float acc = W[i * 3 + 0] * W[0 * 3 + j];
+        for (int k = 1; k < 3; ++k) acc = acc + W[i * 3 + k] * W[k * 3 + j];
+        W2[i * 3 + j] = acc;
+      }
+    const float Ac = s / theta;
+    const float Bc = (1.0f - c) / (theta * theta);
+    const float Cc = (theta - s) / ((theta * theta) * theta);
+    for (int i = 0; i < 9; ++i) {
+      const float I = (i % 4 == 0) ? 1.0f : 0.0f;
+      R[i] = (I + Ac * W[i]) + Bc * W2[i];
+      V[i] = (I + Bc * W[i]) + Cc * W2[i];
+    }
+  }
+  for (int i = 0; i < 3; ++i) {
+    T[i * 4 + 0] = R[i * 3 + 0];
+    T[i * 4 + 1] = R[i * 3 + 1];
+    T[i * 4 + 2] = R[i * 3 + 2];
+    T[i * 4 + 3] = (V[i * 3 + 0] * vx + V[i * 3 + 1] * vy) + V[i * 3 + 2] * vz;
+  }
+  T[12] = 0.f; T[13] = 0.f; T[14] = 0.f; T[15] = 1.f;
+}
+
+struct IcpState {     // per element, device resident
+  float *T_total;     // (B,16) accumulated transform
+  float *T_pend;      // (B,16) transform still to be applied to the source cloud
+  float *dT;          // (B,16) Gauss-Newton step of this iteration
+  float *xi;          // (B,6)
+  float *err;         // (B)
+  float *damp;        // (B)
+};
+
+__device__ float reduce_partial(const float *partials, int nblocks, int k) {
+  float v = 0.0f;
+  for (int j = 0; j < nblocks; ++j) v += partials[(int64_t)j * kNumSums + k];
+  return v;
+}
+
+__global__ void k_icp_solve(const float *partials, int nblocks, IcpState st) {
+  __shared__ float s_sum[kNumSums];
+  const int b = blockIdx.x;
+  const float *p = partials + (int64_t)b * nblocks * kNumSums;
+  if (threadIdx.x < kNumSums) s_sum[threadIdx.x] = reduce_partial(p, nblocks, threadIdx.x);
+  __syncwarp();
+  if (threadIdx.x != 0) return;
+  // (A^T A + damp I) x = A^T b by Gauss-Jordan inversion with partial pivoting, then x = inv * A^T b
+  float M[6][12];
+  int k = 0;
+  for (int i = 0; i < 6; ++i)
+    for (int j = i; j < 6; ++j) {
+      M[i][j] = s_sum[k];
+      M[j][i] = s_sum[k];
+      ++k;
+    }
+  const float damp = st.damp[b];
+  for (int i = 0; i < 6; ++i) {
+    M[i][i] = M[i][i] + damp;
+    for (int j = 0; j < 6; ++j) M[i][6 + j] = (i == j) ? 1.0f : 0.0f;
+  }
+  for (int c = 0; c < 6; ++c) {
+    int piv = c;
+    float mx = fabsf(M[c][c]);
+    for (int r = c + 1; r < 6; ++r)
+      if (fabsf(M[r][c]) > mx) {
+        mx = fabsf(M[r][c]);
+        piv = r;
+      }
+    if (piv != c)
+      for (int j = 0; j < 12; ++j) {
+        const float t = M[c][j];
+        M[c][j] = M[piv][j];
+        M[piv][j] = t;
+      }
+    const float inv = 1.0f / M[c][c];
+    for (int j = 0; j < 12; ++j) M[c][j] *= inv;
+    for (int r = 0; r < 6; ++r) {
+      if (r == c) continue;
+      const float f = M[r][c];
+      for (int j = 0; j < 12; ++j) M[r][j] -= f * M[c][j];
+    }
+  }
+  float xi[6];
+  for (int i = 0; i < 6; ++i) {
+    float acc = 0.0f;
+    for (int j = 0; j < 6; ++j) acc += M[i][6 + j] * s_sum[21 + j];
+    xi[i] = acc;
+    st.xi[b * 6 + i] = acc;
+  }
+  se3_exp_dev(xi, st.dT + b * 16);
+  st.err[b] = s_sum[27];
+}
+
+struct UpdateArgs {
+  int mode;  // 0 = LM accept/reject (point_to_plane_ICP), 1 = gradLM (point_to_plane_gradICP)
+  float lambda_min, lambda_max, B, B2, inv_nu;
+};
+
+__global__ void k_icp_update(const float *partials, int nblocks, IcpState st, UpdateArgs u) {
+  const int b = blockIdx.x;
+  if (threadIdx.x != 0) return;
+  const float new_err = reduce_partial(partials + (int64_t)b * nblocks * kNumSums, nblocks, 27);
+  const float err = st.err[b];
+  float Tn[16], Tp[16];
+  float *T = st.T_total + b * 16;
+  if (u.mode == 0) {
+    if (new_err < err) {  // trust region: accept the step
+      for (int i = 0; i < 16; ++i) Tp[i] = st.dT[b * 16 + i];
+      st.damp[b] = st.damp[b] / 2.0f;
+      mat4_mul(Tp, T, Tn);
+      for (int i = 0; i < 16; ++i) T[i] = Tn[i];
+    } else {
+      for (int i = 0; i < 16; ++i) Tp[i] = (i % 5 == 0) ? 1.0f : 0.0f;
+      st.damp[b] = st.damp[b] * 2.0f;
+    }
+  } else {
+    float diff = new_err - err;
+    diff = fminf(fmaxf(diff, -70.0f), 70.0f);
+    const float gate = u.lambda_min + (u.lambda_max - u.lambda_min) / (1.0f + expf(-u.B * diff));
+    st.damp[b] = st.damp[b] * gate;
+    const float sig = 1.0f / powf(1.0f + expf(-u.B2 * diff), u.inv_nu);
+    float xs[6];
+    for (int i = 0; i < 6; ++i) xs[i] = sig * st.xi[b * 6 + i];
+    se3_exp_dev(xs, Tp);
+    mat4_mul(Tp, T, Tn);
+    for (int i = 0; i < 16; ++i) T[i] = Tn[i];
+  }
+  for (int i = 0; i < 16; ++i) st.T_pend[b * 16 + i] = Tp[i];
+}
+
+__global__ void k_icp_init(IcpState st, const float *T0, float damp0, int B) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  for (int i = 0; i < 16; ++i) {
+    const float v = T0 ? T0[b * 16 + i] : ((i % 5 == 0) ? 1.0f : 0.0f);
+    st.T_total[b * 16 + i] = v;
+    st.T_pend[b * 16 + i] = v;
+  }
+  st.damp[b] = damp0;
+}
+
+// new pose = T_icp · prev pose (kornia compose_transformations as used at slam/icpslam.py:245-247)
+__global__ void k_pose_compose(const float *T, const float *prev, int64_t prev_bstride, float *out, int64_t out_bstride,
+                               int B) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  const float *A = T + b * 16;
+  const float *P = prev + b * prev_bstride;
+  float *O = out + b * out_bstride;
+  for (int i = 0; i < 3; ++i) {
+    for (int j = 0; j < 3; ++j) O[i * 4 + j] = dot3(A[i * 4], A[i * 4 + 1], A[i * 4 + 2], P[j], P[4 + j], P[8 + j]);
+    O[i * 4 + 3] = dot3(A[i * 4], A[i * 4 + 1], A[i * 4 + 2], P[3], P[7], P[11]) + A[i * 4 + 3];
+  }
+  O[12] = 0.f; O[13] = 0.f; O[14] = 0.f; O[15] = 1.f;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// workspace
+// ---------------------------------------------------------------------------------------------------------
+struct IcpWorkspace {
+  float *src;  // (B, ns_cap, 3)
+  int32_t *src_count, *tgt_count;
+  float *partials;  // (B, nblk, 28)
+  IcpState st;
+  unsigned long long *tile_state;
+  unsigned int *ticket;
+  int ns_cap, nblk, tiles_cap;
+};
+
+inline int64_t up256(int64_t x) { return (x + 255) / 256 * 256; }
+
+inline int icp_ns_cap(int H, int W, int ds) { return ((H + ds - 1) / ds) * ((W + ds - 1) / ds); }
+
+inline int64_t icp_workspace_bytes(int B, int H, int W, int ds, int64_t map_capacity) {
+  const int ns = icp_ns_cap(H, W, ds);
+  const int nblk = (ns + kIcpBlock - 1) / kIcpBlock;
+  const int64_t tiles = (map_capacity + 1023) / 1024;
+  return up256((int64_t)B * ns * 12) + 2 * up256((int64_t)B * 4) + up256((int64_t)B * nblk * kNumSums * 4) +
+         4 * up256((int64_t)B * 64) + 3 * up256((int64_t)B * 24) + up256(B * tiles * 8) + up256((int64_t)B * 4);
+}
+
+inline IcpWorkspace icp_carve(void *ws, int B, int H, int W, int ds, int64_t map_capacity) {
+  IcpWorkspace w;
+  w.ns_cap = icp_ns_cap(H, W, ds);
+  w.nblk = (w.ns_cap + kIcpBlock - 1) / kIcpBlock;
+  w.tiles_cap = (int)((map_capacity + 1023) / 1024);
+  char *p = (char *)ws;
+  w.src = (float *)p;            p += up256((int64_t)B * w.ns_cap * 12);
+  w.src_count = (int32_t *)p;    p += up256((int64_t)B * 4);
+  w.tgt_count = (int32_t *)p;    p += up256((int64_t)B * 4);
+  w.partials = (float *)p;       p += up256((int64_t)B * w.nblk * kNumSums * 4);
+  w.st.T_total = (float *)p;     p += up256((int64_t)B * 64);
+  w.st.T_pend = (float *)p;      p += up256((int64_t)B * 64);
+  w.st.dT = (float *)p;          p += up256((int64_t)B * 64);
+  p += up256((int64_t)B * 64);   // spare
+  w.st.xi = (float *)p;          p += up256((int64_t)B * 24);
+  w.st.err = (float *)p;         p += up256((int64_t)B * 24);
+  w.st.damp = (float *)p;        p += up256((int64_t)B * 24);
+  w.tile_state = (unsigned long long *)p;  p += up256((int64_t)B * w.tiles_cap * 8);
+  w.ticket = (unsigned int *)p;
+  return w;
+}
+
+// runs the LM / gradLM loop on clouds that are already in place
+int run_icp_loop(float *src, const int32_t *src_count, int ns_stride, const float *tgt_p, const float *tgt_n,
+                 const int32_t *tgt_count, int nt_stride, int B, const float *T0, int mode, int numiters, float damp,
+                 int use_thresh, float dist_thresh, float lambda_max, float Bp, float B2p, float nu, float *partials,
+                 int nblk_cap, IcpState st, int64_t *nn_idx, cudaStream_t stream) {
+  const int nblk = (ns_stride + kIcpBlock - 1) / kIcpBlock;
+  if (nblk > nblk_cap) {
+    set_error("icp: source cloud larger than workspace");
+    return 1;
+  }
+  k_icp_init<<<(B + 63) / 64, 64, 0, stream>>>(st, T0, damp, B);
+  UpdateArgs u{mode, 1.0f / lambda_max, lambda_max, Bp, B2p, 1.0f / nu};
+  KnnArgs ka{src, src_count, ns_stride, tgt_p, tgt_n, tgt_count, nt_stride, nullptr, 0, dist_thresh, use_thresh,
+             partials, nullptr, nullptr};
+  const dim3 grid((unsigned)nblk, (unsigned)B);
+  for (int it = 0; it < numiters; ++it) {
+    ka.pre = st.T_pend;
+    ka.write_back = 1;
+    ka.nn_idx = (it == numiters - 1) ? nn_idx : nullptr;
+    k_icp_knn_linearize<<<grid, kIcpBlock, 0, stream>>>(ka);
+    k_icp_solve<<<B, 32, 0, stream>>>(partials, nblk, st);
+    ka.pre = st.dT;
+    ka.write_back = 0;
+    ka.nn_idx = nullptr;
+    k_icp_knn_linearize<<<grid, kIcpBlock, 0, stream>>>(ka);
+    k_icp_update<<<B, 32, 0, stream>>>(partials, nblk, st, u);
+  }
+  GSX_CHECK_LAUNCH("gsx_icp");
+  return 0;
+}
+
+}  // namespace gsx
+
+using namespace gsx;
+
+extern "C" int64_t gsx_icp_workspace_bytes(int B, int H, int W, int ds, int64_t map_capacity) {
+  if (B < 0 || H < 1 || W < 1 || ds < 1 || map_capacity < 0) return -1;
+  return icp_workspace_bytes(B, H, W, ds, map_capacity);
+}
+
+extern "C" int gsx_icp_align(const float *src_points, const int32_t *src_count, int ns_stride, const float *tgt_points,
+                             const float *tgt_normals, const int32_t *tgt_count, int nt_stride, int B,
+                             const float *initial_transform, int mode, int numiters, float damp, int use_dist_thresh,
+                             float dist_thresh, float lambda_max, float Bp, float B2p, float nu, float *transform_out,
+                             int64_t *nn_idx_out, void *scratch, int64_t scratch_bytes, void *stream) {
+  GSX_CHECK_ARG(src_points && src_count && tgt_points && tgt_normals && tgt_count && transform_out && scratch,
+                "gsx_icp_align: null pointer");
+  GSX_CHECK_ARG(B >= 1 && ns_stride >= 1 && nt_stride >= 1 && numiters >= 0, "gsx_icp_align: bad extents");
+  GSX_CHECK_ARG(mode == 0 || mode == 1, "gsx_icp_align: mode must be 0 (ICP) or 1 (gradICP)");
+  // scratch: working copy of src (B,ns,3) + partials + state
+  const int nblk = (ns_stride + kIcpBlock - 1) / kIcpBlock;
+  const int64_t need = up256((int64_t)B * ns_stride * 12) + up256((int64_t)B * nblk * kNumSums * 4) +
+                       3 * up256((int64_t)B * 64) + 3 * up256((int64_t)B * 24);
+  GSX_CHECK_ARG(scratch_bytes >= need, "gsx_icp_align: scratch too small (%lld < %lld)", (long long)scratch_bytes,
+                (long long)need);
+  char *p = (char *)scratch;
+  float *src = (float *)p;       p += up256((int64_t)B * ns_stride * 12);
+  float *partials = (float *)p;  p += up256((int64_t)B * nblk * kNumSums * 4);
+  IcpState st;
+  st.T_total = (float *)p;       p += up256((int64_t)B * 64);
+  st.T_pend = (float *)p;        p += up256((int64_t)B * 64);
+  st.dT = (float *)p;            p += up256((int64_t)B * 64);
+  st.xi = (float *)p;            p += up256((int64_t)B * 24);
+  st.err = (float *)p;           p += up256((int64_t)B * 24);
+  st.damp = (float *)p;
+  cudaStream_t s = (cudaStream_t)stream;
+  cudaMemcpyAsync(src, src_points, (size_t)B * ns_stride * 12, cudaMemcpyDeviceToDevice, s);
+  const int rc = run_icp_loop(src, src_count, ns_stride, tgt_points, tgt_normals, tgt_count, nt_stride, B,
+                              initial_transform, mode, numiters, damp, use_dist_thresh, dist_thresh, lambda_max, Bp,
+                              B2p, nu, partials, nblk, st, nn_idx_out, s);
+  if (rc) return rc;
+  cudaMemcpyAsync(transform_out, st.T_total, (size_t)B * 64, cudaMemcpyDeviceToDevice, s);
+  return 0;
+}
+
+extern "C" int64_t gsx_icp_align_scratch_bytes(int B, int ns_stride) {
+  if (B < 1 || ns_stride < 1) return -1;
+  const int nblk = (ns_stride + kIcpBlock - 1) / kIcpBlock;
+  return up256((int64_t)B * ns_stride * 12) + up256((int64_t)B * nblk * kNumSums * 4) + 3 * up256((int64_t)B * 64) +
+         3 * up256((int64_t)B * 24);
+}
+
+extern "C" int gsx_icp_localize(const float *map_points, const float *map_normals, const int32_t *counts,
+                                int64_t capacity, int64_t max_count, const float *depth, int64_t depth_bstride,
+                                const float *intrinsics, int64_t K_bstride, const float *prev_poses,
+                                int64_t prev_pose_bstride, int B, int H, int W, int ds, int mode, int numiters,
+                                float damp, int use_dist_thresh, float dist_thresh, float lambda_max, float Bp,
+                                float B2p, float nu, float *tgt_scratch, int64_t tgt_capacity, float *poses_out,
+                                int64_t poses_out_bstride, void *workspace, uint32_t epoch, void *stream) {
+  GSX_CHECK_ARG(map_points && map_normals && counts && depth && intrinsics && prev_poses && poses_out && workspace &&
+                    tgt_scratch,
+                "gsx_icp_localize: null pointer");
+  GSX_CHECK_ARG(B >= 1 && H >= 2 && W >= 2 && ds >= 1, "gsx_icp_localize: bad extents");
+  GSX_CHECK_ARG(mode == 0 || mode == 1, "gsx_icp_localize: mode must be 0 (ICP) or 1 (gradICP)");
+  GSX_CHECK_ARG(max_count <= capacity && tgt_capacity >= 1, "gsx_icp_localize: bad capacities");
+  GSX_CHECK_ARG(epoch >= 1 && epoch < (1u << 30), "gsx_icp_localize: epoch out of range");
+  cudaStream_t s = (cudaStream_t)stream;
+  IcpWorkspace w = icp_carve(workspace, B, H, W, ds, capacity);
+  float *tgt_p = tgt_scratch;
+  float *tgt_n = tgt_scratch + (int64_t)B * tgt_capacity * 3;
+  GatherSrcArgs gs{depth, depth_bstride, intrinsics, K_bstride, prev_poses, prev_pose_bstride, B, H, W, ds,
+                   w.src, w.src_count, w.ns_cap};
+  k_icp_gather_src<<<B, 1024, 0, s>>>(gs);
+  int tiles = (int)((max_count + 1023) / 1024);
+  if (tiles > w.tiles_cap) tiles = w.tiles_cap;
+  if (tiles == 0) cudaMemsetAsync(w.tgt_count, 0, (size_t)B * 4, s);
+  if (tiles > 0) {
+    GatherTgtArgs gt{map_points, map_normals, counts, capacity, prev_poses, prev_pose_bstride, intrinsics, K_bstride,
+                     B, H, W, ds, (float)(W - 0.999), (float)(H - 0.999), tgt_p, tgt_n, w.tgt_count,
+                     (int)tgt_capacity, w.tile_state, w.ticket, tiles, epoch};
+    k_icp_gather_tgt<<<dim3((unsigned)tiles, (unsigned)B), kIcpBlock, 0, s>>>(gt);
+  }
+  GSX_CHECK_LAUNCH("gsx_icp_localize(gather)");
+  const int rc = run_icp_loop(w.src, w.src_count, w.ns_cap, tgt_p, tgt_n, w.tgt_count, (int)tgt_capacity, B, nullptr,
+                              mode, numiters, damp, use_dist_thresh, dist_thresh, lambda_max, Bp, B2p, nu, w.partials,
+                              w.nblk, w.st, nullptr, s);
+  if (rc) return rc;
+  k_pose_compose<<<(B + 63) / 64, 64, 0, s>>>(w.st.T_total, prev_poses, prev_pose_bstride, poses_out,
+                                              poses_out_bstride, B);
+  GSX_CHECK_LAUNCH("gsx_icp_localize(compose)");
+  return 0;
+}
+
+extern "C" int gsx_knn1(const float *src_points, const int32_t *src_count, int ns_stride, const float *tgt_points,
+                        const int32_t *tgt_count, int nt_stride, int B, int64_t *idx_out, float *d2_out,
+                        void *scratch, int64_t scratch_bytes, void *stream) {
+  GSX_CHECK_ARG(src_points && src_count && tgt_points && tgt_count && idx_out && scratch, "gsx_knn1: null pointer");
+  GSX_CHECK_ARG(B >= 1 && ns_stride >= 1 && nt_stride >= 1, "gsx_knn1: bad extents");
+  const int nblk = (ns_stride + kIcpBlock - 1) / kIcpBlock;
+  GSX_CHECK_ARG(scratch_bytes >= (int64_t)B * nblk * kNumSums * 4, "gsx_knn1: scratch too small");
+  // the target normals are not needed for the association itself: reuse the points as a placeholder
+  KnnArgs ka{const_cast<float *>(src_points), src_count, ns_stride, tgt_points, tgt_points, tgt_count, nt_stride,
+             nullptr, 0, 0.0f, 0, (float *)scratch, idx_out, d2_out};
+  k_icp_knn_linearize<<<dim3((unsigned)nblk, (unsigned)B), kIcpBlock, 0, (cudaStream_t)stream>>>(ka);
+  GSX_CHECK_LAUNCH("gsx_knn1");
+  return 0;
+}

@@ -1,6 +1,269 @@
-"""Point-to-plane ICP building blocks (mirror of gradslam/odometry/icputils.py) — filled in with csrc/gsx_icp.cu."""
-__all__ = []
+"""Point-to-plane ICP building blocks.
+
+Host-side mirror of gradslam/odometry/icputils.py (same names, arguments, errors).  The association
+(`chamferdist.knn_points` in the reference), the row build, the normal-equation reduction, the damped solve,
+the SE(3) exponential and the LM / gradLM update all run in csrc/gsx_icp.cu; nothing here loops over points.
+"""
+from typing import Optional, Union
+
+import torch
+
+from .. import _C
+from ..structures.pointclouds import Pointclouds
+from ..structures.rgbdimages import RGBDImages, _frame_base
+
+__all__ = ["solve_linear_system", "gauss_newton_solve", "point_to_plane_ICP", "point_to_plane_gradICP",
+           "downsample_pointclouds", "downsample_rgbdimages"]
+
+
+def _need_tensor(x, name):
+    if not torch.is_tensor(x):
+        raise TypeError("Expected {} to be of type torch.Tensor. Got {}.".format(name, type(x)))
+
+
+def solve_linear_system(A: torch.Tensor, b: torch.Tensor, damp: Union[float, torch.Tensor] = 1e-8):
+    """x = (A^T A + damp I)^-1 A^T b — the normal equations, not the system itself (icputils.py:22-90)."""
+    _need_tensor(A, "A")
+    _need_tensor(b, "b")
+    if not (isinstance(damp, float) or torch.is_tensor(damp)):
+        raise TypeError("Expected damp to be of type float or torch.Tensor. Got {0}.".format(type(damp)))
+    if torch.is_tensor(damp) and damp.ndim != 0:
+        raise ValueError("Expected torch.Tensor damp to have ndim=0 (scalar). Got {0}.".format(damp.ndim))
+    if A.ndim != 2:
+        raise ValueError("A should have ndim=2, but had ndim={}".format(A.ndim))
+    if b.ndim != 2:
+        raise ValueError("b should have ndim=2, but had ndim={}".format(b.ndim))
+    if b.shape[1] != 1:
+        raise ValueError("b.shape[1] should 1, but was {0}".format(b.shape[1]))
+    if A.shape[0] != b.shape[0]:
+        raise ValueError("A.shape[0] and b.shape[0] should be equal ({0} != {1})".format(A.shape[0], b.shape[0]))
+    damp = damp if torch.is_tensor(damp) else torch.tensor(damp, dtype=A.dtype, device=A.device)
+    At = A.transpose(0, 1)
+    normal = At @ A + torch.eye(A.shape[1], dtype=A.dtype, device=A.device) * damp
+    return torch.inverse(normal) @ (At @ b)
+
+
+def _check_clouds(src_pc, tgt_pc, tgt_normals, dist_thresh):
+    _need_tensor(src_pc, "src_pc")
+    _need_tensor(tgt_pc, "tgt_pc")
+    _need_tensor(tgt_normals, "tgt_normals")
+    if not (isinstance(dist_thresh, (float, int)) or dist_thresh is None):
+        raise TypeError("Expected dist_thresh to be of type float or int. Got {0}.".format(type(dist_thresh)))
+    for name, t in (("src_pc", src_pc), ("tgt_pc", tgt_pc), ("tgt_normals", tgt_normals)):
+        if t.ndim != 3:
+            raise ValueError("{} should have ndim=3, but had ndim={}".format(name, t.ndim))
+    for name, t in (("src_pc", src_pc), ("tgt_pc", tgt_pc), ("tgt_normals", tgt_normals)):
+        if t.shape[0] != 1:
+            raise ValueError("{}.shape[0] should be 1, but was {} instead".format(name, t.shape[0]))
+    if tgt_pc.shape[1] != tgt_normals.shape[1]:
+        raise ValueError("tgt_pc.shape[1] and tgt_normals.shape[1] must be equal. Got {0}!={1}".format(
+            tgt_pc.shape[1], tgt_normals.shape[1]))
+    for name, t in (("src_pc", src_pc), ("tgt_pc", tgt_pc), ("tgt_normals", tgt_normals)):
+        if t.shape[2] != 3:
+            raise ValueError("{}.shape[2] should be 3, but was {} instead".format(name, t.shape[2]))
+
+
+def _counts(n, B, device):
+    return torch.full((B,), n, dtype=torch.int32, device=device)
+
+
+def knn1(src: torch.Tensor, tgt: torch.Tensor):
+    """Exact 1-NN of every row of src (B,Ns,3) in tgt (B,Nt,3).  Returns (squared distances (B,Ns), idx int64 (B,Ns));
+    ties resolve to the lowest target index.  CUDA kernel k_icp_knn_linearize."""
+    _C.require_cuda(src, "src")
+    _C.require_cuda(tgt, "tgt")
+    src, tgt = src.contiguous(), tgt.contiguous()
+    B, Ns, _ = src.shape
+    Nt = tgt.shape[1]
+    idx = torch.empty((B, Ns), dtype=torch.int64, device=src.device)
+    d2 = torch.empty((B, Ns), dtype=torch.float32, device=src.device)
+    scratch = torch.empty(B * ((Ns + 255) // 256) * 112, dtype=torch.uint8, device=src.device)
+    with torch.cuda.device(src.device):
+        rc = _C.lib().gsx_knn1(_C.ptr(src), _C.ptr(_counts(Ns, B, src.device)), Ns, _C.ptr(tgt),
+                               _C.ptr(_counts(Nt, B, src.device)), Nt, B, _C.ptr(idx), _C.ptr(d2), _C.ptr(scratch),
+                               scratch.numel(), _C.stream_ptr(src.device))
+    _C.check(rc, "gsx_knn1")
+    return d2, idx
+
+
+def gauss_newton_solve(src_pc: torch.Tensor, tgt_pc: torch.Tensor, tgt_normals: torch.Tensor,
+                       dist_thresh: Union[float, int, None] = None):
+    """Point-to-plane rows for one Gauss-Newton step: A (Nsf,6), b (Nsf,1), nn indices (Nsf,) (icputils.py:93-232).
+    The association is the CUDA exact 1-NN; the row algebra below is differentiable torch (as in the reference)."""
+    _check_clouds(src_pc, tgt_pc, tgt_normals, dist_thresh)
+    src_pc, tgt_pc, tgt_normals = src_pc.contiguous(), tgt_pc.contiguous(), tgt_normals.contiguous()
+    d2, idx = knn1(src_pc.detach(), tgt_pc.detach())
+    keep = torch.ones_like(d2[0], dtype=torch.bool) if dist_thresh is None else d2[0] < dist_thresh
+    idx = idx[0][keep]
+    s = src_pc[0][keep]
+    p = tgt_pc[0].index_select(0, idx)
+    n = tgt_normals[0].index_select(0, idx)
+    sx, sy, sz = s[:, 0:1], s[:, 1:2], s[:, 2:3]
+    nx, ny, nz = n[:, 0:1], n[:, 1:2], n[:, 2:3]
+    A = torch.cat([nx, ny, nz, nz * sy - ny * sz, nx * sz - nz * sx, ny * sx - nx * sy], 1)
+    b = nx * (p[:, 0:1] - sx) + ny * (p[:, 1:2] - sy) + nz * (p[:, 2:3] - sz)
+    return A, b, idx
+
+
+def _check_icp_args(src_pc, tgt_pc, tgt_normals, initial_transform, numiters):
+    _need_tensor(src_pc, "src_pc")
+    _need_tensor(tgt_pc, "tgt_pc")
+    _need_tensor(tgt_normals, "tgt_normals")
+    if not (torch.is_tensor(initial_transform) or initial_transform is None):
+        raise TypeError("Expected initial_transform to be of type torch.Tensor. Got {0}.".format(
+            type(initial_transform)))
+    if not isinstance(numiters, int):
+        raise TypeError("Expected numiters to be of type int. Got {0}.".format(type(numiters)))
+    if initial_transform is not None:
+        if initial_transform.ndim != 2:
+            raise ValueError("Expected initial_transform.ndim to be 2. Got {0}.".format(initial_transform.ndim))
+        if not (initial_transform.shape[0] == 4 and initial_transform.shape[1] == 4):
+            raise ValueError("Expected initial_transform.shape to be (4, 4). Got {0}.".format(initial_transform.shape))
+
+
+def icp_align(src, src_counts, tgt, tgt_normals, tgt_counts, T0, mode, numiters, damp, dist_thresh, lambda_max=2.0,
+              B=1.0, B2=1.0, nu=200.0, want_idx=False):
+    """Batched ICP (mode 0) / gradICP (mode 1) on padded clouds (Bn, N, 3) with int32 sizes.  One C call."""
+    for name, t in (("src", src), ("tgt", tgt), ("tgt_normals", tgt_normals)):
+        _C.require_cuda(t, name)
+    Bn, Ns, _ = src.shape
+    Nt = tgt.shape[1]
+    dev = src.device
+    out = torch.empty((Bn, 4, 4), dtype=torch.float32, device=dev)
+    idx = torch.empty((Bn, Ns), dtype=torch.int64, device=dev) if want_idx else None
+    lib = _C.lib()
+    nbytes = lib.gsx_icp_align_scratch_bytes(Bn, Ns)
+    scratch = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    T0c = None if T0 is None else T0.to(dev).float().contiguous()
+    with torch.cuda.device(dev):
+        rc = lib.gsx_icp_align(
+            _C.ptr(src.contiguous()), _C.ptr(src_counts), Ns, _C.ptr(tgt.contiguous()),
+            _C.ptr(tgt_normals.contiguous()), _C.ptr(tgt_counts), Nt, Bn, _C.ptr(T0c), int(mode), int(numiters),
+            float(damp), 0 if dist_thresh is None else 1, 0.0 if dist_thresh is None else float(dist_thresh),
+            float(lambda_max), float(B), float(B2), float(nu), _C.ptr(out), _C.ptr(idx), _C.ptr(scratch), nbytes,
+            _C.stream_ptr(dev))
+    _C.check(rc, "gsx_icp_align")
+    return out, idx
+
+
+def _single(src_pc, tgt_pc, tgt_normals, initial_transform, mode, numiters, damp, dist_thresh, **kw):
+    dev = src_pc.device
+    T0 = None if initial_transform is None else initial_transform.view(1, 4, 4)
+    T, idx = icp_align(src_pc.contiguous(), _counts(src_pc.shape[1], 1, dev), tgt_pc.contiguous(),
+                       tgt_normals.contiguous(), _counts(tgt_pc.shape[1], 1, dev), T0, mode, numiters, damp,
+                       dist_thresh, want_idx=True, **kw)
+    idx = idx[0]
+    return T[0], idx[idx >= 0]
+
+
+def point_to_plane_ICP(src_pc: torch.Tensor, tgt_pc: torch.Tensor, tgt_normals: torch.Tensor,
+                       initial_transform: Optional[torch.Tensor] = None, numiters: int = 20, damp: float = 1e-8,
+                       dist_thresh: Union[float, int, None] = None):
+    """Rigid transform aligning src to tgt with point-to-plane LM (icputils.py:235-367).  Returns (T (4,4), nn idx)."""
+    _check_icp_args(src_pc, tgt_pc, tgt_normals, initial_transform, numiters)
+    return _single(src_pc, tgt_pc, tgt_normals, initial_transform, 0, numiters, damp, dist_thresh)
+
+
+def point_to_plane_gradICP(src_pc: torch.Tensor, tgt_pc: torch.Tensor, tgt_normals: torch.Tensor,
+                           initial_transform: Optional[torch.Tensor] = None, numiters: int = 20, damp: float = 1e-8,
+                           dist_thresh: Union[float, int, None] = None, lambda_max: Union[float, int] = 2.0,
+                           B: Union[float, int] = 1.0, B2: Union[float, int] = 1.0, nu: Union[float, int] = 200.0):
+    """Same with the gradLM solver (icputils.py:370-545)."""
+    _check_icp_args(src_pc, tgt_pc, tgt_normals, initial_transform, numiters)
+    for name, v in (("lambda_max", lambda_max), ("B", B), ("B2", B2), ("nu", nu)):
+        if not isinstance(v, (float, int)):
+            raise TypeError("Expected {} to be of type float or int; got {}".format(name, type(v)))
+    return _single(src_pc, tgt_pc, tgt_normals, initial_transform, 1, numiters, damp, dist_thresh,
+                   lambda_max=lambda_max, B=B, B2=B2, nu=nu)
+
+
+def downsample_pointclouds(pointclouds: Pointclouds, pc2im_bnhw: torch.Tensor, ds_ratio: int) -> Pointclouds:
+    """Keeps the active map points whose pixel lies on the ds lattice (icputils.py:548-620)."""
+    if not isinstance(pointclouds, Pointclouds):
+        raise TypeError("Expected pointclouds to be of type gradslam.Pointclouds. Got {0}.".format(type(pointclouds)))
+    if not torch.is_tensor(pc2im_bnhw):
+        raise TypeError("Expected pc2im_bnhw to be of type torch.Tensor. Got {0}.".format(type(pc2im_bnhw)))
+    if not isinstance(ds_ratio, int):
+        raise TypeError("Expected ds_ratio to be of type int. Got {0}.".format(type(ds_ratio)))
+    if pc2im_bnhw.ndim != 2:
+        raise ValueError("Expected pc2im_bnhw to have ndim=2. Got {0}.".format(pc2im_bnhw.ndim))
+    if pc2im_bnhw.shape[1] != 4:
+        raise ValueError("pc2im_bnhw.shape[1] must be 4, but was {0}.".format(pc2im_bnhw.shape[1]))
+    t = pc2im_bnhw[(pc2im_bnhw[:, 2] % ds_ratio == 0) & (pc2im_bnhw[:, 3] % ds_ratio == 0)]
+    rows = [t[t[:, 0] == b][:, 1] for b in range(len(pointclouds))]
+    pick = lambda lst: None if lst is None else [lst[b][rows[b]] for b in range(len(pointclouds))]
+    return Pointclouds(points=pick(pointclouds.points_list), normals=pick(pointclouds.normals_list),
+                       colors=pick(pointclouds.colors_list))
+
+
+def downsample_rgbdimages(rgbdimages: RGBDImages, ds_ratio: int) -> Pointclouds:
+    """Strided subsample of the global maps + valid mask -> Pointclouds (icputils.py:623-669)."""
+    if not isinstance(rgbdimages, RGBDImages):
+        raise TypeError("Expected rgbdimages to be of type gradslam.RGBDImages. Got {0}.".format(type(rgbdimages)))
+    if not isinstance(ds_ratio, int):
+        raise TypeError("Expected ds_ratio to be of type int. Got {0}.".format(type(ds_ratio)))
+    if rgbdimages.shape[1] != 1:
+        raise ValueError("Sequence length of rgbdimages must be 1, but was {0}.".format(rgbdimages.shape[1]))
+    fr = rgbdimages.to_channels_last()
+    B = len(fr)
+    mask = fr.valid_depth_mask.squeeze(-1)[:, 0, ::ds_ratio, ::ds_ratio]
+    sub = lambda m: [m[b, 0, ::ds_ratio, ::ds_ratio][mask[b]] for b in range(B)]
+    return Pointclouds(points=sub(fr.global_vertex_map), normals=sub(fr.global_normal_map), colors=sub(fr.rgb_image))
+
+
+# --------------------------------------------------------------------------------------------- fused localisation
+class _IcpWorkspace:
+    _cache = {}
+
+    def __init__(self, device, B, H, W, ds, capacity):
+        n = _C.lib().gsx_icp_workspace_bytes(B, H, W, ds, capacity)
+        self.buf = torch.zeros(n, dtype=torch.uint8, device=device)
+        self.capacity = capacity
+        self.epoch = 0
+
+    @classmethod
+    def get(cls, device, B, H, W, ds, capacity):
+        key = (str(device), B, H, W, ds)
+        ws = cls._cache.get(key)
+        if ws is None or ws.capacity < capacity:
+            ws = cls(device, B, H, W, ds, capacity)
+            cls._cache[key] = ws
+        return ws
+
+    def next_epoch(self):
+        self.epoch += 1
+        if self.epoch >= (1 << 30) - 1:
+            self.buf.zero_()
+            self.epoch = 1
+        return self.epoch
 
 
 def localize_against_map(pointclouds, live_frame, prev_frame, dsratio, odomprov):
-    raise NotImplementedError("ICP odometry kernels are not built yet")
+    """ICPSLAM._localize for odom in {icp, gradicp} (slam/icpslam.py:238-247) as ONE C call: gathers the source
+    (live frame on the ds lattice at the previous pose) and target (lattice-active map points) clouds, runs the
+    batched ICP loop and returns the new poses (B,1,4,4) = T_icp · prev pose.  No host synchronisation."""
+    live = live_frame.to_channels_last()
+    B, _, H, W = live.shape
+    dev = pointclouds.device
+    _C.require_cuda(live.depth_image, "depth_image")
+    depth, d_bs = _frame_base(live.depth_image, H * W)
+    K = live.intrinsics.contiguous()
+    prev = prev_frame.poses.contiguous()
+    st = pointclouds._store
+    ws = _IcpWorkspace.get(dev, B, H, W, dsratio, pointclouds.capacity)
+    bound = max(1, pointclouds._bound)
+    tgt = torch.empty((2, B, bound, 3), dtype=torch.float32, device=dev)
+    out = torch.empty((B, 1, 4, 4), dtype=torch.float32, device=dev)
+    mode = 1 if hasattr(odomprov, "lambda_max") else 0
+    dth = odomprov.dist_thresh
+    with torch.cuda.device(dev):
+        rc = _C.lib().gsx_icp_localize(
+            _C.ptr(st["points"]), _C.ptr(st["normals"]), _C.ptr(pointclouds._counts_dev[pointclouds._cur]),
+            pointclouds.capacity, pointclouds._bound, _C.ptr(depth), d_bs, _C.ptr(K), 16, _C.ptr(prev), 16, B, H, W,
+            int(dsratio), mode, int(odomprov.numiters), float(odomprov.damp), 0 if dth is None else 1,
+            0.0 if dth is None else float(dth), float(getattr(odomprov, "lambda_max", 2.0)),
+            float(getattr(odomprov, "B", 1.0)), float(getattr(odomprov, "B2", 1.0)),
+            float(getattr(odomprov, "nu", 200.0)), _C.ptr(tgt), bound, _C.ptr(out), 16, _C.ptr(ws.buf),
+            ws.next_epoch(), _C.stream_ptr(dev))
+    _C.check(rc, "gsx_icp_localize")
+    return out

@@ -1,10 +1,9 @@
 """Per-kernel timing of the PointFusion(odom='gt') sequence, used by bench.py for the roofline line.
 
-Runs exactly the launches of gsx_pointfusion_sequence_gt (K1 -> K2/K3 -> K4 per frame, same arguments), but
+Runs exactly the launches of gsx_pointfusion_sequence_gt (K2/K3 -> K4 per frame, same arguments), but
 from Python with a CUDA event between launches, and reads the device-side counters after each frame so the
 algorithmic byte count of every launch comes from the run itself:
 
-    K1  backproject+normals (global maps only)   28 B/pixel         = B*P*(4 read + 24 write)
     K2  project+select                           12*M + 16*A        (map positions; normal+ccount of active)
     K4  merge+append                             16*P + 52*U + 40*New  (depth+rgb; read colour 12 + write 40 per
                                                                         merged point; write 40 per new point)
@@ -28,34 +27,28 @@ def profile_pointfusion_gt(depth, rgb, K, poses, dist_th, dot_th, sigma):
     ws = _Workspace.get(dev, B, H, W)
     off = lib.gsx_fusion_workspace_stats_offset(B, H, W)
     stats = ws.buf[off: off + B * 16].view(torch.int64).view(B, 2)
-    scratch = torch.empty((2, B, H, W, 3), dtype=torch.float32, device=dev)
-    gv, gn = scratch[0], scratch[1]
     st = pc._store
     stream = _C.stream_ptr(dev)
-    out = {"K1_backproject_normals": [], "K2_project_select": [], "K4_merge_append": []}
+    out = {"K2_project_select": [], "K4_merge_append": []}
     frames = []
     prev_stats = stats.sum(0).tolist()
     prev_counts = [0] * B
     for s in range(L):
-        ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
         cin = pc._counts_dev[s & 1]
         cout = pc._counts_dev[(s + 1) & 1]
         ev[0].record()
-        _C.check(lib.gsx_backproject_normals_fwd(
-            depth.data_ptr() + 4 * s * P, L * P, _C.ptr(K), 16, poses.data_ptr() + 64 * s, L * 16, B, 1, H, W,
-            None, None, _C.ptr(gv), _C.ptr(gn), stream), "K1")
-        ev[1].record()
         _C.check(lib.gsx_fusion_project_select(
             _C.ptr(st["points"]), _C.ptr(st["normals"]), _C.ptr(st["features"]), _C.ptr(cin), pc.capacity,
-            min(s * P, pc.capacity), poses.data_ptr() + 64 * s, L * 16, _C.ptr(K), 16, _C.ptr(gv), _C.ptr(gn),
-            B, H, W, float(dist_th), float(dot_th), _C.ptr(ws.buf), stream), "K2")
-        ev[2].record()
+            min(s * P, pc.capacity), poses.data_ptr() + 64 * s, L * 16, _C.ptr(K), 16, depth.data_ptr() + 4 * s * P,
+            L * P, None, None, B, H, W, float(dist_th), float(dot_th), _C.ptr(ws.buf), stream), "K2")
+        ev[1].record()
         _C.check(lib.gsx_fusion_merge_append(
             _C.ptr(st["points"]), _C.ptr(st["normals"]), _C.ptr(st["colors"]), _C.ptr(st["features"]),
             _C.ptr(cin), _C.ptr(cout), pc.capacity, depth.data_ptr() + 4 * s * P, L * P,
-            rgb.data_ptr() + 12 * s * P, L * P * 3, _C.ptr(K), 16, _C.ptr(gv), _C.ptr(gn), B, H, W, float(sigma),
-            _C.ptr(ws.buf), ws.next_epochs(1), _C.ptr(pc._overflow_flag()), stream), "K4")
-        ev[3].record()
+            rgb.data_ptr() + 12 * s * P, L * P * 3, _C.ptr(K), 16, poses.data_ptr() + 64 * s, L * 16, None, None,
+            B, H, W, float(sigma), _C.ptr(ws.buf), ws.next_epochs(1), _C.ptr(pc._overflow_flag()), stream), "K4")
+        ev[2].record()
         torch.cuda.synchronize(dev)
         counts = cout.tolist()
         cur_stats = stats.sum(0).tolist()
@@ -63,10 +56,9 @@ def profile_pointfusion_gt(depth, rgb, K, poses, dist_th, dot_th, sigma):
         New = sum(counts) - M
         A = cur_stats[0] - prev_stats[0]
         U = cur_stats[1] - prev_stats[1]
-        out["K1_backproject_normals"].append((ev[0].elapsed_time(ev[1]), 28 * B * P))
         if s > 0:
-            out["K2_project_select"].append((ev[1].elapsed_time(ev[2]), 12 * M + 16 * A))
-        out["K4_merge_append"].append((ev[2].elapsed_time(ev[3]), 16 * B * P + 52 * U + 40 * New))
+            out["K2_project_select"].append((ev[0].elapsed_time(ev[1]), 12 * M + 16 * A))
+        out["K4_merge_append"].append((ev[1].elapsed_time(ev[2]), 16 * B * P + 52 * U + 40 * New))
         frames.append({"frame": s, "map_points": M, "active": A, "merged": U, "new": New})
         prev_counts, prev_stats = counts, cur_stats
     return out, frames

@@ -110,7 +110,8 @@ def _check_frame(rgbdimages):
 
 
 def _launch_merge_append(pointclouds, frames, vmap, nmap, sigma):
-    """K4 on the current workspace state.  vmap/nmap: (B,1,H,W,3) maps to merge/append."""
+    """K4 on the current workspace state.  vmap/nmap: (B,1,H,W,3) maps to merge/append, or None for both:
+    the kernel then samples world-frame vertex/normal from depth on the fly (needs frames.poses)."""
     B, _, H, W = frames.shape
     P = H * W
     dev = pointclouds.device
@@ -118,6 +119,7 @@ def _launch_merge_append(pointclouds, frames, vmap, nmap, sigma):
     depth, d_bs = _frame_base(frames.depth_image, P)
     rgb, c_bs = _frame_base(frames.rgb_image, P * 3)
     K = frames.intrinsics.contiguous()
+    poses = None if vmap is not None else frames.poses.contiguous()
     st = pointclouds._store
     cin = pointclouds._counts_dev[pointclouds._cur]
     cout = pointclouds._counts_dev[pointclouds._cur ^ 1]
@@ -125,7 +127,7 @@ def _launch_merge_append(pointclouds, frames, vmap, nmap, sigma):
         rc = _C.lib().gsx_fusion_merge_append(
             _C.ptr(st["points"]), _C.ptr(st["normals"]), _C.ptr(st["colors"]), _C.ptr(st["features"]),
             _C.ptr(cin), _C.ptr(cout), pointclouds.capacity, _C.ptr(depth), d_bs, _C.ptr(rgb), c_bs, _C.ptr(K), 16,
-            _C.ptr(vmap), _C.ptr(nmap), B, H, W, float(sigma), _C.ptr(ws.buf), ws.next_epochs(1),
+            _C.ptr(poses), 16, _C.ptr(vmap), _C.ptr(nmap), B, H, W, float(sigma), _C.ptr(ws.buf), ws.next_epochs(1),
             _C.ptr(pointclouds._overflow_flag()), _C.stream_ptr(dev))
     _C.check(rc, "gsx_fusion_merge_append")
     pointclouds._mark_device_updated(pointclouds._bound + P)
@@ -153,8 +155,11 @@ def _append_valid_pixels(pointclouds, frames, global_coordinates=True, sigma=0.6
     had_points = pointclouds.has_points
     with_features = pointclouds.has_features if had_points else False
     _prepare_map(pointclouds, frames, with_features)
-    vmap = frames.global_vertex_map if global_coordinates else frames.vertex_map
-    nmap = frames.global_normal_map if global_coordinates else frames.normal_map
+    if global_coordinates and frames.poses is not None:
+        vmap = nmap = None  # sampled on the fly inside the kernel
+    else:
+        vmap = frames.global_vertex_map if global_coordinates else frames.vertex_map
+        nmap = frames.global_normal_map if global_coordinates else frames.normal_map
     _launch_merge_append(pointclouds, frames, vmap, nmap, sigma)
     return pointclouds
 
@@ -175,18 +180,23 @@ def _fused_update(pointclouds, frames, dist_th, dot_th, sigma):
     P = H * W
     _prepare_map(pointclouds, frames, True)
     dev = pointclouds.device
-    vmap, nmap = frames.global_vertex_map, frames.global_normal_map
+    # Frame geometry: if the caller already materialised the global maps (they are cached on `frames`) use
+    # them, otherwise let the kernels sample vertex / normal from depth on the fly (same bits, no K1 launch).
+    vmap, nmap = frames._global_vertex_map, frames._global_normal_map
+    if vmap is None or nmap is None:
+        vmap = nmap = None
     if pointclouds._bound > 0:
         ws = _Workspace.get(dev, B, H, W)
         st = pointclouds._store
         poses, p_bs = frames.poses.contiguous(), 16
         K = frames.intrinsics.contiguous()
+        depth, d_bs = _frame_base(frames.depth_image, P)
         with torch.cuda.device(dev):
             rc = _C.lib().gsx_fusion_project_select(
                 _C.ptr(st["points"]), _C.ptr(st["normals"]), _C.ptr(st["features"]),
                 _C.ptr(pointclouds._counts_dev[pointclouds._cur]), pointclouds.capacity, pointclouds._bound,
-                _C.ptr(poses), p_bs, _C.ptr(K), 16, _C.ptr(vmap), _C.ptr(nmap), B, H, W, float(dist_th),
-                float(dot_th), _C.ptr(ws.buf), _C.stream_ptr(dev))
+                _C.ptr(poses), p_bs, _C.ptr(K), 16, _C.ptr(depth), d_bs, _C.ptr(vmap), _C.ptr(nmap), B, H, W,
+                float(dist_th), float(dot_th), _C.ptr(ws.buf), _C.stream_ptr(dev))
         _C.check(rc, "gsx_fusion_project_select")
     _launch_merge_append(pointclouds, frames, vmap, nmap, sigma)
     return pointclouds

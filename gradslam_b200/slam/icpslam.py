@@ -11,7 +11,6 @@ from typing import Optional, Union
 import torch
 import torch.nn as nn
 
-from ..geometry.geometryutils import compose_transformations
 from ..structures.pointclouds import Pointclouds
 from ..structures.rgbdimages import RGBDImages
 from .fusionutils import update_map_aggregate
@@ -111,8 +110,8 @@ class ICPSLAM(nn.Module):
         from ..odometry.icputils import localize_against_map
 
         live_frame.poses = prev_frame.poses
-        transform = localize_against_map(pointclouds, live_frame, prev_frame, self.dsratio, self.odomprov)
-        return compose_transformations(transform.squeeze(1), prev_frame.poses.squeeze(1)).unsqueeze(1)
+        # source / target gathering, the ICP loop and the final T_icp · prev_pose all happen in one C call
+        return localize_against_map(pointclouds, live_frame, prev_frame, self.dsratio, self.odomprov)
 
     def _map(self, pointclouds: Pointclouds, live_frame: RGBDImages, inplace: bool = False):
         return update_map_aggregate(pointclouds, live_frame, inplace)

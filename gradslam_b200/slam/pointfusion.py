@@ -69,7 +69,6 @@ class PointFusion(ICPSLAM):
         pc = Pointclouds(device=dev)
         pc._allocate(B, L * P, 1, zero=False)
         ws = _Workspace.get(dev, B, H, W)
-        scratch = torch.empty((2, B, H, W, 3), dtype=torch.float32, device=dev)
         st = pc._store
         main = torch.cuda.current_stream(dev)
         with torch.cuda.device(dev):
@@ -93,7 +92,7 @@ class PointFusion(ICPSLAM):
                     _C.ptr(st["points"]), _C.ptr(st["normals"]), _C.ptr(st["colors"]), _C.ptr(st["features"]),
                     _C.ptr(pc._counts_dev), pc.capacity, min(s0 * P, pc.capacity), _C.ptr(depth), _C.ptr(rgb),
                     _C.ptr(K), _C.ptr(poses), B, L, s0, s1, H, W, float(self.dist_th), float(self.dot_th),
-                    float(self.sigma), _C.ptr(scratch), _C.ptr(ws.buf), ws.next_epochs(s1 - s0),
+                    float(self.sigma), None, _C.ptr(ws.buf), ws.next_epochs(s1 - s0),
                     _C.ptr(pc._overflow_flag()), _C.stream_ptr(dev))
                 _C.check(rc, "gsx_pointfusion_sequence_gt")
             if not on_device:

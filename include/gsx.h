@@ -67,33 +67,42 @@ int64_t gsx_fusion_workspace_stats_offset(int B, int H, int W);
 /* K2+K3: project every map point into the live camera, keep points that are in the frustum, close to
  * the frame vertex they land on and with a similar normal, and reduce per pixel to the best candidate
  * (largest confidence count, then smallest ray distance, then smallest index) with a 128-bit atomic
- * min.  max_count = host upper bound on counts[b] (sizes the grid). */
+ * min.  max_count = host upper bound on counts[b] (sizes the grid).
+ * Frame geometry: either pass the materialised world-frame maps gvertex / gnormal (B,H,W,3) (outputs of
+ * gsx_backproject_normals_fwd), or pass both as NULL and give the live depth image: the kernel then
+ * evaluates vertex and normal of the pixel each point lands on directly from depth (same arithmetic, bit
+ * for bit) and the maps never touch HBM. */
 int gsx_fusion_project_select(const float *map_points, const float *map_normals, const float *map_ccounts,
                               const int32_t *counts, int64_t capacity, int64_t max_count, const float *poses,
                               int64_t pose_bstride, const float *intrinsics, int64_t K_bstride,
-                              const float *gvertex, const float *gnormal, int B, int H, int W, float dist_th,
-                              float dot_th, void *workspace, void *stream);
+                              const float *depth, int64_t depth_bstride, const float *gvertex,
+                              const float *gnormal, int B, int H, int W, float dist_th, float dot_th,
+                              void *workspace, void *stream);
 
 /* K4: per pixel, merge the selected map point with the frame sample (confidence-weighted mean) or, for
  * valid pixels without a match, append a new surfel in row-major pixel order (stable single-pass scan).
  * counts_in -> counts_out (may not alias).  map_ccounts may be NULL for maps without confidence counts
  * (ICPSLAM aggregation, gradslam/slam/fusionutils.py:725-758): then nothing is merged and every valid
  * pixel is appended.  overflow_flag (int32, device) is set to 1 if capacity was
- * exceeded (the surplus points are dropped). */
+ * exceeded (the surplus points are dropped).  Frame geometry as for gsx_fusion_project_select: pass the
+ * maps to merge/append (gvertex, gnormal), or NULL for both plus the camera poses to sample depth on the
+ * fly. */
 int gsx_fusion_merge_append(float *map_points, float *map_normals, float *map_colors, float *map_ccounts,
                             const int32_t *counts_in, int32_t *counts_out, int64_t capacity,
                             const float *depth, int64_t depth_bstride, const float *rgb, int64_t rgb_bstride,
-                            const float *intrinsics, int64_t K_bstride, const float *gvertex,
-                            const float *gnormal, int B, int H, int W, double sigma, void *workspace,
-                            uint32_t epoch, int32_t *overflow_flag, void *stream);
+                            const float *intrinsics, int64_t K_bstride, const float *poses,
+                            int64_t pose_bstride, const float *gvertex, const float *gnormal, int B, int H,
+                            int W, double sigma, void *workspace, uint32_t epoch, int32_t *overflow_flag,
+                            void *stream);
 
-/* Whole-sequence driver with ground-truth poses: for s in [s_begin,s_end): K1 -> K2/K3 -> K4, no host sync.
+/* Whole-sequence driver with ground-truth poses: for s in [s_begin,s_end): K2/K3 -> K4 with the frame
+ * geometry sampled on the fly from depth (no K1 launch, no frame maps in HBM), no host sync.
  * replaces ICPSLAM.forward with odom='gt' + PointFusion._map   gradslam/slam/icpslam.py:99-138,
  *          gradslam/slam/pointfusion.py:107-112
  * depth (B,L,H,W), rgb (B,L,H,W,3) dense; poses (B,L,4,4) dense; intrinsics (B,4,4) dense.
  * counts: int32 (2,B) ping-pong buffer; row (s_begin & 1) holds the current sizes on entry; on return the
  * current sizes are in row (s_end & 1).  max_count0 = host upper bound of the sizes on entry.
- * scratch_maps: 2*B*H*W*3 floats (gvertex, gnormal of one frame).
+ * scratch_maps: unused (may be NULL); kept for ABI stability.
  * epoch0 = epoch of frame s_begin (the call consumes s_end - s_begin epochs).  Splitting a sequence
  * into several calls (s_begin..s_end chunks) lets the caller overlap host->device copies of later
  * frames with the fusion of earlier ones. */
@@ -103,6 +112,53 @@ int gsx_pointfusion_sequence_gt(float *map_points, float *map_normals, float *ma
                                 int s_begin, int s_end, int H, int W, float dist_th, float dot_th,
                                 double sigma, float *scratch_maps,
                                 void *workspace, uint32_t epoch0, int32_t *overflow_flag, void *stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Point-to-plane ICP / gradICP odometry (K5 exact 1-NN, K6 residual+Jacobian rows and the 6x6 normal
+ * equations, K7 damped solve + se3_exp + LM / gradLM update), batched over B, no host synchronisation.
+ * replaces chamferdist.chamfer.knn_points (third party, call site gradslam/odometry/icputils.py:200),
+ *          gauss_newton_solve :93-232, solve_linear_system :22-90, point_to_plane_ICP :235-367,
+ *          point_to_plane_gradICP :370-545, se3utils.se3_exp gradslam/geometry/se3utils.py:77-115,
+ *          transform_pointcloud gradslam/geometry/geometryutils.py:737-794 and the per-element Python loops
+ *          of ICPOdometryProvider.provide / GradICPOdometryProvider.provide (odometry/icp.py:84-97,
+ *          odometry/gradicp.py:105-122).
+ *
+ * Clouds are padded (B, stride, 3) float32 with int32 (B) sizes.  mode 0 = LM accept/reject (ICP),
+ * mode 1 = gradLM (gradICP; lambda_max, B, B2, nu as in the reference).  use_dist_thresh = 0 means
+ * dist_thresh=None; otherwise the SQUARED nn distance is compared with dist_thresh exactly as the
+ * reference does (icputils.py:206).  Exact 1-NN ties resolve to the lowest target index.            */
+
+/* exact nearest neighbour of every source point: idx_out int64 (B, ns_stride) (-1 for rows >= size or an
+ * empty target), d2_out squared distance (may be NULL).  scratch: B*ceil(ns_stride/256)*112 bytes. */
+int gsx_knn1(const float *src_points, const int32_t *src_count, int ns_stride, const float *tgt_points,
+             const int32_t *tgt_count, int nt_stride, int B, int64_t *idx_out, float *d2_out, void *scratch,
+             int64_t scratch_bytes, void *stream);
+
+/* full ICP / gradICP on given clouds.  initial_transform (B,16) or NULL (identity).  transform_out (B,16).
+ * nn_idx_out optional int64 (B, ns_stride): association of the last iteration (-1 = filtered out).
+ * scratch: gsx_icp_align_scratch_bytes(B, ns_stride) bytes. */
+int64_t gsx_icp_align_scratch_bytes(int B, int ns_stride);
+int gsx_icp_align(const float *src_points, const int32_t *src_count, int ns_stride, const float *tgt_points,
+                  const float *tgt_normals, const int32_t *tgt_count, int nt_stride, int B,
+                  const float *initial_transform, int mode, int numiters, float damp, int use_dist_thresh,
+                  float dist_thresh, float lambda_max, float Bp, float B2p, float nu, float *transform_out,
+                  int64_t *nn_idx_out, void *scratch, int64_t scratch_bytes, void *stream);
+
+/* ICPSLAM._localize for odom in {icp, gradicp} (gradslam/slam/icpslam.py:238-247) as one call:
+ * source cloud = live depth on the ds-lattice placed at the previous pose (downsample_rgbdimages,
+ * icputils.py:623-669); target cloud = map points inside the previous frame's frustum that land on the
+ * ds-lattice (find_active_map_points + downsample_pointclouds, fusionutils.py:198-287,
+ * icputils.py:548-620); ICP loop; poses_out[b] = T_icp[b] * prev_poses[b].
+ * tgt_scratch: 2*B*tgt_capacity*3 floats (target points, normals); workspace:
+ * gsx_icp_workspace_bytes(B,H,W,ds,map capacity) bytes zero-filled once; `epoch` increases by one per
+ * call on the same workspace, starting at 1. */
+int64_t gsx_icp_workspace_bytes(int B, int H, int W, int ds, int64_t map_capacity);
+int gsx_icp_localize(const float *map_points, const float *map_normals, const int32_t *counts, int64_t capacity,
+                     int64_t max_count, const float *depth, int64_t depth_bstride, const float *intrinsics,
+                     int64_t K_bstride, const float *prev_poses, int64_t prev_pose_bstride, int B, int H, int W,
+                     int ds, int mode, int numiters, float damp, int use_dist_thresh, float dist_thresh,
+                     float lambda_max, float Bp, float B2p, float nu, float *tgt_scratch, int64_t tgt_capacity,
+                     float *poses_out, int64_t poses_out_bstride, void *workspace, uint32_t epoch, void *stream);
 
 #ifdef __cplusplus
 }

@@ -106,3 +106,48 @@ def test_cpu_tensors_are_refused():
     fr = gs.RGBDImages(rgb, depth, K, poses)
     with pytest.raises(RuntimeError, match="CUDA"):
         fr.vertex_map
+
+
+def test_materialised_maps_path_equals_fused_path():
+    """update_map_fusion with frame maps already cached on the RGBDImages (K1 output gathered by K2/K4) gives the
+    same bits as the default path where K2/K4 sample the depth image on the fly."""
+    import gradslam_b200 as gs
+    from gradslam_b200.slam import fusionutils
+
+    B, L, H, W = 2, 3, 40, 56
+    rgb, depth, K, poses = make_sequence(B, L, H, W, seed=9)
+    dev = _dev()
+    frames = _frames(gs, rgb, depth, K, poses, dev)
+    slam = gs.PointFusion(odom="gt", device=dev)
+    pc_a, pc_b = gs.Pointclouds(device=dev), gs.Pointclouds(device=dev)
+    for s in range(L):
+        fa, fb = frames[:, s], frames[:, s]
+        fb.global_vertex_map, fb.global_normal_map  # materialise (K1) -> non-fused kernels
+        pc_a = fusionutils.update_map_fusion(pc_a, fa, slam.dist_th, slam.dot_th, slam.sigma, inplace=True)
+        pc_b = fusionutils.update_map_fusion(pc_b, fb, slam.dist_th, slam.dot_th, slam.sigma, inplace=True)
+    assert pc_a.num_points_per_pointcloud.tolist() == pc_b.num_points_per_pointcloud.tolist()
+    for b in range(B):
+        for attr in ("points_list", "normals_list", "colors_list", "features_list"):
+            assert torch.equal(getattr(pc_a, attr)[b], getattr(pc_b, attr)[b]), attr
+
+
+def test_update_map_aggregate_matches_oracle():
+    """ICPSLAM mapping step (append every valid pixel) == oracle.update_map_aggregate, bit for bit."""
+    import gradslam_b200 as gs
+    from gradslam_b200.slam import fusionutils
+
+    B, L, H, W = 2, 3, 32, 48
+    rgb, depth, K, poses = make_sequence(B, L, H, W, seed=12)
+    dev = _dev()
+    frames = _frames(gs, rgb, depth, K, poses, dev)
+    pc = gs.Pointclouds(device=dev)
+    smap = oracle.SurfelMap()
+    for s in range(L):
+        pc = fusionutils.update_map_aggregate(pc, frames[:, s], inplace=True)
+        smap = oracle.update_map_aggregate(smap, oracle.frame_maps(depth[:, s:s + 1], K, poses[:, s:s + 1]), rgb[:, s:s + 1])
+    assert pc.num_points_per_pointcloud.tolist() == smap.counts()
+    assert not pc.has_features
+    for b in range(B):
+        assert torch.equal(pc.points_list[b].cpu(), smap.points[b])
+        assert torch.equal(pc.normals_list[b].cpu(), smap.normals[b])
+        assert torch.equal(pc.colors_list[b].cpu(), smap.colors[b])
