@@ -39,6 +39,14 @@ SIGNATURES = {
     "gsx_pointfusion_sequence_gt": (
         c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_int,
                 c_int, c_float, c_float, c_double, c_vp, c_vp, c_u32, c_vp, c_vp]),
+    "gsx_compact_scratch_bytes": (c_i64, [c_i64]),
+    "gsx_compact_indices": (c_int, [c_vp, c_i64, c_vp, c_vp, c_vp, c_u32, c_vp]),
+    "gsx_active_eval": (c_int, [c_vp, c_vp, c_i64, c_i64, c_vp, c_i64, c_vp, c_i64, c_int, c_int, c_int, c_vp, c_vp,
+                                c_vp]),
+    "gsx_similar_eval": (c_int, [c_vp, c_i64, c_vp, c_vp, c_i64, c_vp, c_vp, c_int, c_int, c_int, c_float, c_float,
+                                 c_vp, c_vp]),
+    "gsx_unique_select": (c_int, [c_vp, c_i64, c_vp, c_vp, c_i64, c_vp, c_int, c_int, c_int, c_vp, c_vp, c_vp, c_vp]),
+    "gsx_records_from_table": (c_int, [c_vp, c_i64, c_i64, c_int, c_int, c_int, c_vp, c_vp]),
     "gsx_knn1": (c_int, [c_vp, c_vp, c_int, c_vp, c_vp, c_int, c_int, c_vp, c_vp, c_vp, c_i64, c_vp]),
     "gsx_icp_align_scratch_bytes": (c_i64, [c_int, c_int]),
     "gsx_icp_align": (

@@ -286,7 +286,9 @@ __global__ void __launch_bounds__(kBlock, GSX_K4_MINB) k_merge_append(MergeArgs 
   __shared__ int s_warp_sums[kPix][kBlock / 32];
   __shared__ int s_excl;
   __shared__ KInv s_k;
-  const int b = blockIdx.y;
+  // batch element varies fastest in the grid: CTAs resident at the same time belong to different elements, so
+  // each element's look-back chain only sees ~1/B of the in-flight tiles
+  const int b = blockIdx.x % a.B;
   const int T = a.ws.tiles;
   if (threadIdx.x == 0) {
     // dynamic tile id: tiles start in ticket order, so every predecessor of a running tile is running or done
@@ -470,9 +472,9 @@ int launch_project_select(const ProjectArgs &a, int64_t max_count, cudaStream_t 
 int launch_merge_append(const MergeArgs &a, cudaStream_t stream) {
   if (a.B == 0) return 0;
   if (a.gv)
-    k_merge_append<false><<<dim3((unsigned)a.ws.tiles, (unsigned)a.B), kBlock, 0, stream>>>(a);
+    k_merge_append<false><<<dim3((unsigned)(a.ws.tiles * a.B)), kBlock, 0, stream>>>(a);
   else
-    k_merge_append<true><<<dim3((unsigned)a.ws.tiles, (unsigned)a.B), kBlock, 0, stream>>>(a);
+    k_merge_append<true><<<dim3((unsigned)(a.ws.tiles * a.B)), kBlock, 0, stream>>>(a);
   GSX_CHECK_LAUNCH("gsx_fusion_merge_append");
   return 0;
 }

@@ -130,7 +130,7 @@ __global__ void __launch_bounds__(kIcpBlock) k_icp_gather_tgt(GatherTgtArgs a) {
   __shared__ float s_k[12];
   __shared__ int s_tile, s_excl;
   __shared__ int s_warp[4][kIcpBlock / 32];
-  const int b = blockIdx.y;
+  const int b = blockIdx.x % a.B;  // elements interleaved in the grid (short look-back chains)
   if (threadIdx.x == 0) {
     // dynamic tile id.  The block that draws the last ticket re-arms the counter for the next launch (nobody
     // else will touch it any more in this one), so the number of tiles may differ from launch to launch.
@@ -695,7 +695,7 @@ extern "C" int gsx_icp_localize(const float *map_points, const float *map_normal
     GatherTgtArgs gt{map_points, map_normals, counts, capacity, prev_poses, prev_pose_bstride, intrinsics, K_bstride,
                      B, H, W, ds, (float)(W - 0.999), (float)(H - 0.999), tgt_p, tgt_n, w.tgt_count,
                      (int)tgt_capacity, w.tile_state, w.ticket, tiles, epoch};
-    k_icp_gather_tgt<<<dim3((unsigned)tiles, (unsigned)B), kIcpBlock, 0, s>>>(gt);
+    k_icp_gather_tgt<<<dim3((unsigned)(tiles * B)), kIcpBlock, 0, s>>>(gt);
   }
   GSX_CHECK_LAUNCH("gsx_icp_localize(gather)");
   const int rc = run_icp_loop(w.src, w.src_count, w.ns_cap, tgt_p, tgt_n, w.tgt_count, (int)tgt_capacity, B, nullptr,

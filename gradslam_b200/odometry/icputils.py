@@ -78,10 +78,10 @@ def knn1(src: torch.Tensor, tgt: torch.Tensor):
     idx = torch.empty((B, Ns), dtype=torch.int64, device=src.device)
     d2 = torch.empty((B, Ns), dtype=torch.float32, device=src.device)
     scratch = torch.empty(B * ((Ns + 255) // 256) * 112, dtype=torch.uint8, device=src.device)
+    ns_t, nt_t = _counts(Ns, B, src.device), _counts(Nt, B, src.device)  # keep alive across the call
     with torch.cuda.device(src.device):
-        rc = _C.lib().gsx_knn1(_C.ptr(src), _C.ptr(_counts(Ns, B, src.device)), Ns, _C.ptr(tgt),
-                               _C.ptr(_counts(Nt, B, src.device)), Nt, B, _C.ptr(idx), _C.ptr(d2), _C.ptr(scratch),
-                               scratch.numel(), _C.stream_ptr(src.device))
+        rc = _C.lib().gsx_knn1(_C.ptr(src), _C.ptr(ns_t), Ns, _C.ptr(tgt), _C.ptr(nt_t), Nt, B, _C.ptr(idx),
+                               _C.ptr(d2), _C.ptr(scratch), scratch.numel(), _C.stream_ptr(src.device))
     _C.check(rc, "gsx_knn1")
     return d2, idx
 

@@ -202,6 +202,196 @@ def _fused_update(pointclouds, frames, dist_th, dot_th, sigma):
     return pointclouds
 
 
+# --------------------------------------------------------------------------------------------- table API
+def _compact(flags: torch.Tensor) -> torch.Tensor:
+    """Ascending indices of the non-zero entries of a flat uint8 CUDA tensor (stable compaction kernel)."""
+    n = flags.numel()
+    dev = flags.device
+    lib = _C.lib()
+    scratch = torch.zeros(lib.gsx_compact_scratch_bytes(n), dtype=torch.uint8, device=dev)
+    idx = torch.empty(max(n, 1), dtype=torch.int64, device=dev)
+    cnt = torch.zeros(1, dtype=torch.int64, device=dev)
+    with torch.cuda.device(dev):
+        rc = lib.gsx_compact_indices(_C.ptr(flags), n, _C.ptr(idx), _C.ptr(cnt), _C.ptr(scratch), 1,
+                                     _C.stream_ptr(dev))
+    _C.check(rc, "gsx_compact_indices")
+    return idx[: int(cnt.item())]  # the table's length is data dependent: this is the API's one host sync
+
+
+def _check_table(pc2im_bnhw):
+    if not torch.is_tensor(pc2im_bnhw):
+        raise TypeError("Expected input pc2im_bnhw to be of type torch.Tensor. Got {0} instead.".format(
+            type(pc2im_bnhw)))
+    if pc2im_bnhw.dtype != torch.int64:
+        raise TypeError("Expected input pc2im_bnhw to have dtype of torch.int64 (torch.long), not {0}.".format(
+            pc2im_bnhw.dtype))
+
+
+def _check_table_shape(pc2im_bnhw):
+    if pc2im_bnhw.ndim != 2:
+        raise ValueError("Expected pc2im_bnhw.ndim of 2. Got {0}.".format(pc2im_bnhw.ndim))
+    if pc2im_bnhw.shape[1] != 4:
+        raise ValueError("Expected pc2im_bnhw.shape[1] to be 4. Got {0}.".format(pc2im_bnhw.shape[1]))
+
+
+def _check_pc(pointclouds):
+    if not isinstance(pointclouds, Pointclouds):
+        raise TypeError("Expected pointclouds to be of type gradslam.Pointclouds. Got {0}.".format(type(pointclouds)))
+
+
+def _check_batch(pointclouds, rgbdimages):
+    if len(rgbdimages) != len(pointclouds):
+        raise ValueError("Expected equal batch sizes for pointclouds and rgbdimages. Got {0} and {1} "
+                         "respectively.".format(len(pointclouds), len(rgbdimages)))
+
+
+def find_active_map_points(pointclouds: Pointclouds, rgbdimages: RGBDImages) -> torch.Tensor:
+    """int64 (A,4) rows [b, n, h, w] of the map points that project inside the live frame, in (b, n) order
+    (fusionutils.py:198-287)."""
+    _check_pc(pointclouds)
+    _check_frame(rgbdimages)
+    device = pointclouds.device
+    if not pointclouds.has_points:
+        return torch.empty((0, 4), dtype=torch.int64, device=device)
+    _check_batch(pointclouds, rgbdimages)
+    frames = rgbdimages.to_channels_last()
+    B, _, H, W = frames.shape
+    st = pointclouds._store
+    _C.require_cuda(st["points"], "pointclouds.points")
+    width = min(max(pointclouds._bound, 1), pointclouds.capacity)
+    flags = torch.empty((B, width), dtype=torch.uint8, device=device)
+    hw = torch.empty((B, width), dtype=torch.int32, device=device)
+    poses, K = frames.poses.contiguous(), frames.intrinsics.contiguous()
+    with torch.cuda.device(device):
+        rc = _C.lib().gsx_active_eval(_C.ptr(st["points"]), _C.ptr(pointclouds._counts_dev[pointclouds._cur]),
+                                      pointclouds.capacity, width, _C.ptr(poses), 16, _C.ptr(K), 16, B, H, W,
+                                      _C.ptr(flags), _C.ptr(hw), _C.stream_ptr(device))
+    _C.check(rc, "gsx_active_eval")
+    idx = _compact(flags.view(-1))
+    pix = hw.view(-1)[idx].to(torch.int64)
+    table = torch.stack([idx // width, idx % width, pix // W, pix % W], dim=1)
+    if table.shape[0] == 0:
+        warnings.warn("No active map points were found")
+    return table
+
+
+def find_similar_map_points(pointclouds: Pointclouds, rgbdimages: RGBDImages, pc2im_bnhw: torch.Tensor,
+                            dist_th: Union[float, int], dot_th: Union[float, int]):
+    """Rows of the active table whose map point is close to, and has a normal similar to, the frame point of the
+    pixel it lands on.  Returns (int64 (S,4), bool (A,)) (fusionutils.py:290-411)."""
+    _check_pc(pointclouds)
+    if not isinstance(rgbdimages, RGBDImages):
+        raise TypeError("Expected rgbdimages to be of type gradslam.RGBDImages. Got {0}.".format(type(rgbdimages)))
+    _check_table(pc2im_bnhw)
+    if rgbdimages.shape[1] != 1:
+        raise ValueError("Expected rgbdimages to have sequence length of 1. Got {0}.".format(rgbdimages.shape[1]))
+    _check_table_shape(pc2im_bnhw)
+    device = pointclouds.device
+    if not pointclouds.has_points or pc2im_bnhw.shape[0] == 0:
+        return torch.empty((0, 4), dtype=torch.int64, device=device), torch.empty(0, dtype=torch.bool, device=device)
+    _check_batch(pointclouds, rgbdimages)
+    if not pointclouds.has_normals:
+        raise ValueError("Pointclouds must have normals for finding similar map points, but did not.")
+    frames = rgbdimages.to_channels_last()
+    B, _, H, W = frames.shape
+    table = pc2im_bnhw.contiguous()
+    rows = table.shape[0]
+    gv, gn = frames.global_vertex_map.contiguous(), frames.global_normal_map.contiguous()
+    st = pointclouds._store
+    flags = torch.empty(rows, dtype=torch.uint8, device=device)
+    with torch.cuda.device(device):
+        rc = _C.lib().gsx_similar_eval(_C.ptr(table), rows, _C.ptr(st["points"]), _C.ptr(st["normals"]),
+                                       pointclouds.capacity, _C.ptr(gv), _C.ptr(gn), B, H, W, float(dist_th),
+                                       float(dot_th), _C.ptr(flags), _C.stream_ptr(device))
+    _C.check(rc, "gsx_similar_eval")
+    keep = _compact(flags)
+    similar = table[keep]
+    if similar.shape[0] == 0:
+        warnings.warn("No similar map points were found (despite total {0} active points across the batch)".format(
+            rows), RuntimeWarning)
+    return similar, flags.bool()
+
+
+def find_best_unique_correspondences(pointclouds: Pointclouds, rgbdimages: RGBDImages,
+                                     pc2im_bnhw: torch.Tensor) -> torch.Tensor:
+    """One row per live pixel: among the candidates of a pixel keep the largest confidence count, then the
+    smallest ray distance, then the smallest index.  Output sorted by (b, h, w) (fusionutils.py:414-546); the
+    reference's torch.unique(dim=0) row sort becomes a per-pixel 128-bit atomic arg-min."""
+    _check_pc(pointclouds)
+    _check_table(pc2im_bnhw)
+    if rgbdimages.shape[1] != 1:
+        raise ValueError("Expected rgbdimages to have sequence length of 1. Got {0}.".format(rgbdimages.shape[1]))
+    _check_table_shape(pc2im_bnhw)
+    device = pointclouds.device
+    if not pointclouds.has_points or pc2im_bnhw.shape[0] == 0:
+        return torch.empty((0, 4), dtype=torch.int64, device=device)
+    _check_batch(pointclouds, rgbdimages)
+    if not pointclouds.has_features:
+        raise ValueError("Pointclouds must have features for finding best unique correspondences, but did not.")
+    frames = rgbdimages.to_channels_last()
+    B, _, H, W = frames.shape
+    table = pc2im_bnhw.contiguous()
+    gv = frames.global_vertex_map.contiguous()
+    st = pointclouds._store
+    ws = _Workspace.get(device, B, H, W)
+    pflags = torch.empty(B * H * W, dtype=torch.uint8, device=device)
+    pn = torch.empty(B * H * W, dtype=torch.int64, device=device)
+    with torch.cuda.device(device):
+        rc = _C.lib().gsx_unique_select(_C.ptr(table), table.shape[0], _C.ptr(st["points"]), _C.ptr(st["features"]),
+                                        pointclouds.capacity, _C.ptr(gv), B, H, W, _C.ptr(ws.buf), _C.ptr(pflags),
+                                        _C.ptr(pn), _C.stream_ptr(device))
+    _C.check(rc, "gsx_unique_select")
+    pix = _compact(pflags)
+    rem = pix % (H * W)
+    return torch.stack([pix // (H * W), pn[pix], rem // W, rem % W], dim=1)
+
+
+def find_correspondences(pointclouds: Pointclouds, rgbdimages: RGBDImages, dist_th: Union[float, int],
+                         dot_th: Union[float, int]) -> torch.Tensor:
+    """active -> similar -> best unique (fusionutils.py:549-577)."""
+    pc2im_bnhw = find_active_map_points(pointclouds, rgbdimages)
+    pc2im_bnhw, _ = find_similar_map_points(pointclouds, rgbdimages, pc2im_bnhw, dist_th, dot_th)
+    return find_best_unique_correspondences(pointclouds, rgbdimages, pc2im_bnhw)
+
+
+def fuse_with_map(pointclouds: Pointclouds, rgbdimages: RGBDImages, pc2im_bnhw: torch.Tensor,
+                  sigma: Union[torch.Tensor, float, int], inplace: bool = False) -> Pointclouds:
+    """Merges the corresponding points of `pc2im_bnhw` (unique rows) and appends the unmatched valid pixels
+    (fusionutils.py:580-722)."""
+    _check_pc(pointclouds)
+    if not isinstance(rgbdimages, RGBDImages):
+        raise TypeError("Expected rgbdimages to be of type gradslam.RGBDImages. Got {0}.".format(type(rgbdimages)))
+    _check_table(pc2im_bnhw)
+    _check_table_shape(pc2im_bnhw)
+    if pointclouds.has_points:
+        for what in ("normals", "colors"):
+            if not getattr(pointclouds, "has_" + what):
+                raise ValueError("Pointclouds must have {} for map fusion, but did not.".format(what))
+        if not pointclouds.has_features:
+            raise ValueError("Pointclouds must have features (ccounts) for map fusion, but did not.")
+    _check_frame(rgbdimages)
+    if not inplace:
+        pointclouds = pointclouds.clone()
+    frames = rgbdimages.to_channels_last()
+    _C.require_cuda(frames.depth_image, "depth_image")
+    B, _, H, W = frames.shape
+    _prepare_map(pointclouds, frames, True)
+    device = pointclouds.device
+    if pointclouds._bound > 0 and pc2im_bnhw.shape[0] != 0:
+        table = pc2im_bnhw.to(device).contiguous()
+        ws = _Workspace.get(device, B, H, W)
+        with torch.cuda.device(device):
+            rc = _C.lib().gsx_records_from_table(_C.ptr(table), table.shape[0], pointclouds.capacity, B, H, W,
+                                                 _C.ptr(ws.buf), _C.stream_ptr(device))
+        _C.check(rc, "gsx_records_from_table")
+    if frames.poses is not None:
+        vmap = nmap = None
+    else:
+        vmap, nmap = frames.global_vertex_map, frames.global_normal_map
+    _launch_merge_append(pointclouds, frames, vmap, nmap, sigma)
+    return pointclouds
+
+
 # --------------------------------------------------------------------------------------------- public ops
 def update_map_aggregate(pointclouds: Pointclouds, rgbdimages: RGBDImages, inplace: bool = False) -> Pointclouds:
     """Appends every valid live-frame pixel to the maps (fusionutils.py:725-758)."""

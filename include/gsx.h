@@ -114,6 +114,43 @@ int gsx_pointfusion_sequence_gt(float *map_points, float *map_normals, float *ma
                                 void *workspace, uint32_t epoch0, int32_t *overflow_flag, void *stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Table-returning association steps (API parity with gradslam's module-level helpers; the fused path
+ * above never materialises these tables).  Tables are int64 (rows,4) with rows [b, n, h, w].
+ * replaces find_active_map_points gradslam/slam/fusionutils.py:198-287 (gsx_active_eval + compaction),
+ *          find_similar_map_points :290-411 (gsx_similar_eval + compaction),
+ *          find_best_unique_correspondences :414-546 (gsx_unique_select + compaction, replacing the
+ *          torch.unique(dim=0) row sort), and the scatter of fuse_with_map :659-676, 702-704
+ *          (gsx_records_from_table, followed by gsx_fusion_merge_append).                              */
+
+/* stable compaction: ascending indices i with flags[i] != 0 -> out_idx, their number -> *out_count (int64,
+ * device).  scratch: gsx_compact_scratch_bytes(n) bytes, zero-filled by the caller; epoch >= 1, unique per
+ * call on the same scratch. */
+int64_t gsx_compact_scratch_bytes(int64_t n);
+int gsx_compact_indices(const uint8_t *flags, int64_t n, int64_t *out_idx, int64_t *out_count, void *scratch,
+                        uint32_t epoch, void *stream);
+
+/* per map slot (b, n < width): 1 if the point is a valid map point inside the live frustum; hw = h*W + w
+ * of the pixel it rounds to.  flags, hw: (B, width). */
+int gsx_active_eval(const float *map_points, const int32_t *counts, int64_t capacity, int64_t width,
+                    const float *poses, int64_t pose_bstride, const float *intrinsics, int64_t K_bstride, int B,
+                    int H, int W, uint8_t *flags, int32_t *hw, void *stream);
+
+/* per table row: 1 if ||frame vertex - map point|| < dist_th and <frame normal, map normal> > dot_th. */
+int gsx_similar_eval(const int64_t *table, int64_t rows, const float *map_points, const float *map_normals,
+                     int64_t capacity, const float *gvertex, const float *gnormal, int B, int H, int W,
+                     float dist_th, float dot_th, uint8_t *flags, void *stream);
+
+/* per pixel winner among the table rows (largest ccount, then smallest ray distance, then smallest n):
+ * pixel_flags (B*H*W) and pixel_n (B*H*W, -1 if none).  workspace = the fusion workspace (left clean). */
+int gsx_unique_select(const int64_t *table, int64_t rows, const float *map_points, const float *map_ccounts,
+                      int64_t capacity, const float *gvertex, int B, int H, int W, void *workspace,
+                      uint8_t *pixel_flags, int64_t *pixel_n, void *stream);
+
+/* stores every table row as its pixel's winner in the fusion workspace (then call gsx_fusion_merge_append). */
+int gsx_records_from_table(const int64_t *table, int64_t rows, int64_t capacity, int B, int H, int W,
+                           void *workspace, void *stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Point-to-plane ICP / gradICP odometry (K5 exact 1-NN, K6 residual+Jacobian rows and the 6x6 normal
  * equations, K7 damped solve + se3_exp + LM / gradLM update), batched over B, no host synchronisation.
  * replaces chamferdist.chamfer.knn_points (third party, call site gradslam/odometry/icputils.py:200),
