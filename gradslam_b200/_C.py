@@ -28,6 +28,10 @@ SIGNATURES = {
     "gsx_last_error": (ctypes.c_char_p, []),
     "gsx_backproject_normals_fwd": (
         c_int, [c_vp, c_i64, c_vp, c_i64, c_vp, c_i64, c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "gsx_backproject_normals_bwd_scratch_bytes": (c_i64, [c_int, c_int, c_int, c_int]),
+    "gsx_backproject_normals_bwd": (
+        c_int, [c_vp, c_i64, c_vp, c_i64, c_vp, c_i64, c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp,
+                c_vp, c_i64, c_vp]),
     "gsx_fusion_workspace_bytes": (c_i64, [c_int, c_int, c_int]),
     "gsx_fusion_workspace_stats_offset": (c_i64, [c_int, c_int, c_int]),
     "gsx_fusion_project_select": (

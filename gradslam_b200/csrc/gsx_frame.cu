@@ -93,3 +93,226 @@ extern "C" int gsx_backproject_normals_fwd(const float *depth, int64_t depth_bst
                    {vertex, normal, gvertex, gnormal}};
   return gsx::launch_backproject(a, (cudaStream_t)stream);
 }
+
+// =============================================================================================================
+// K1 backward: d(loss)/d(depth) and d(loss)/d(pose) from the upstream gradients of the four maps.
+// Autograd counterpart of gradslam/structures/rgbdimages.py:643-762 (the reference gets it from PyTorch's tape).
+// Gather formulation, no atomics: every pixel q re-evaluates the normal-branch terms of the (at most five)
+// pixels whose finite-difference stencil touches q.  Pose gradients are reduced per CTA and summed in tile
+// order by a second kernel (deterministic).
+// =============================================================================================================
+namespace gsx {
+
+struct FrameBwdArgs {
+  const float *depth;
+  int64_t depth_bstride;
+  const float *K;
+  int64_t K_bstride;
+  const float *poses;
+  int64_t pose_bstride;
+  int B, L, H, W;
+  const float *g[4];  // upstream: vertex, normal, gvertex, gnormal (dense (B,L,H,W,3)), any may be null
+  float *g_depth;     // (B,L,H,W)
+  float *pose_partials;  // (B*L, tiles, 12) or null
+  int tiles;
+};
+
+__device__ __forceinline__ float3 ld3(const float *p) { return make_float3(__ldg(p), __ldg(p + 1), __ldg(p + 2)); }
+__device__ __forceinline__ float3 cross3(const float3 &a, const float3 &b) {
+  return make_float3(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x);
+}
+// R^T g
+__device__ __forceinline__ float3 rot_t(const Rigid &r, const float3 &g) {
+  return make_float3(r.r[0] * g.x + r.r[3] * g.y + r.r[6] * g.z, r.r[1] * g.x + r.r[4] * g.y + r.r[7] * g.z,
+                     r.r[2] * g.x + r.r[5] * g.y + r.r[8] * g.z);
+}
+
+// gradient of the loss w.r.t. the two finite differences dh, dv of pixel p (through its normal)
+__device__ __forceinline__ void normal_terms(const FrameBwdArgs &a, const float *dimg, const KInv &k, const Rigid *pose,
+                                             const float *gn_img, const float *ggn_img, int h, int w, float3 &g_dh,
+                                             float3 &g_dv, float3 *n_out) {
+  const int W = a.W, H = a.H;
+  const int wa = (w < W - 1) ? w : w - 1;
+  const int ha = (h < H - 1) ? h : h - 1;
+  const float dc = __ldg(dimg + h * W + w);
+  const float vf = dc > 0.0f ? 1.0f : 0.0f;
+  const float3 a0 = backproject(k, (float)wa, (float)h, __ldg(dimg + h * W + wa));
+  const float3 a1 = backproject(k, (float)(wa + 1), (float)h, __ldg(dimg + h * W + wa + 1));
+  const float3 b0 = backproject(k, (float)w, (float)ha, __ldg(dimg + ha * W + w));
+  const float3 b1 = backproject(k, (float)w, (float)(ha + 1), __ldg(dimg + (ha + 1) * W + w));
+  const float3 dh = make_float3(a1.x - a0.x, a1.y - a0.y, a1.z - a0.z);
+  const float3 dv = make_float3(b1.x - b0.x, b1.y - b0.y, b1.z - b0.z);
+  const float3 c = cross3(dh, dv);
+  const float nrm = sqrtf((c.x * c.x + c.y * c.y) + c.z * c.z);
+  const float den = (nrm == 0.0f) ? 1.0f : nrm;
+  const float3 nh = make_float3(c.x / den, c.y / den, c.z / den);
+  if (n_out) *n_out = make_float3(nh.x * vf, nh.y * vf, nh.z * vf);
+  // upstream gradient w.r.t. the local normal of p
+  float3 G = make_float3(0.f, 0.f, 0.f);
+  const int64_t o = ((int64_t)h * W + w) * 3;
+  if (gn_img) G = ld3(gn_img + o);
+  if (ggn_img) {
+    float3 t = ld3(ggn_img + o);
+    if (pose) t = rot_t(*pose, t);
+    G.x += t.x; G.y += t.y; G.z += t.z;
+  }
+  // n = (c / |c|) * vf  ->  dL/dc = vf * (G - nh (nh.G)) / |c|   (|c| == 0: den is the constant 1)
+  float3 gc;
+  if (nrm == 0.0f) {
+    gc = make_float3(G.x * vf, G.y * vf, G.z * vf);
+  } else {
+    const float d = nh.x * G.x + nh.y * G.y + nh.z * G.z;
+    const float s = vf / den;
+    gc = make_float3((G.x - nh.x * d) * s, (G.y - nh.y * d) * s, (G.z - nh.z * d) * s);
+  }
+  g_dh = cross3(dv, gc);  // c = dh x dv
+  g_dv = cross3(gc, dh);
+}
+
+__global__ void __launch_bounds__(kTile) k_backproject_normals_bwd(FrameBwdArgs a) {
+  __shared__ KInv s_k;
+  __shared__ Rigid s_pose;
+  __shared__ float s_red[kTile / 32][12];
+  const int img = blockIdx.y;
+  const int b = img / a.L, l = img - b * a.L;
+  const int P = a.H * a.W;
+  if (threadIdx.x == 0) s_k = load_kinv(a.K + b * a.K_bstride);
+  if (threadIdx.x == 32 && a.poses) s_pose = load_rigid(a.poses + b * a.pose_bstride + (int64_t)l * 16);
+  __syncthreads();
+  const KInv k = s_k;
+  const Rigid *pose = a.poses ? &s_pose : nullptr;
+  const int pix = blockIdx.x * kTile + threadIdx.x;
+  const float *dimg = a.depth + b * a.depth_bstride + (int64_t)l * P;
+  const int64_t ibase = (int64_t)img * P * 3;
+  const float *gv_img = a.g[0] ? a.g[0] + ibase : nullptr;
+  const float *gn_img = a.g[1] ? a.g[1] + ibase : nullptr;
+  const float *ggv_img = a.g[2] ? a.g[2] + ibase : nullptr;
+  const float *ggn_img = a.g[3] ? a.g[3] + ibase : nullptr;
+  float acc[12];
+#pragma unroll
+  for (int i = 0; i < 12; ++i) acc[i] = 0.0f;
+  if (pix < P) {
+    const int h = pix / a.W, w = pix - h * a.W;
+    const int W = a.W, H = a.H;
+    const float d = __ldg(dimg + pix);
+    const float vf = d > 0.0f ? 1.0f : 0.0f;
+    const float3 ray = make_float3(k.k00 * (float)w + k.k02, k.k11 * (float)h + k.k12, 1.0f);
+    const float3 v = backproject(k, (float)w, (float)h, d);
+    // direct vertex gradient
+    float3 GV = make_float3(0.f, 0.f, 0.f);
+    const int64_t o = (int64_t)pix * 3;
+    if (gv_img) GV = ld3(gv_img + o);
+    float3 ggv = make_float3(0.f, 0.f, 0.f);
+    if (ggv_img) {
+      ggv = ld3(ggv_img + o);
+      ggv.x *= vf; ggv.y *= vf; ggv.z *= vf;  // gv = (R v + t) * valid
+      const float3 t = pose ? rot_t(*pose, ggv) : ggv;
+      GV.x += t.x; GV.y += t.y; GV.z += t.z;
+    }
+    // normal branch: stencil contributions
+    const bool any_n = gn_img || ggn_img;
+    float3 n_q = make_float3(0.f, 0.f, 0.f);
+    if (any_n) {
+      float3 gdh, gdv;
+      normal_terms(a, dimg, k, pose, gn_img, ggn_img, h, w, gdh, gdv, &n_q);
+      const float sh = (w < W - 1) ? -1.0f : 1.0f;  // q is its own a0 (interior) or a1 (last column)
+      const float sv = (h < H - 1) ? -1.0f : 1.0f;
+      GV.x += sh * gdh.x + sv * gdv.x; GV.y += sh * gdh.y + sv * gdv.y; GV.z += sh * gdh.z + sv * gdv.z;
+      if (w >= 1) {  // left neighbour uses q as a1 (for w-1 < W-1, always true here)
+        float3 e, f;
+        normal_terms(a, dimg, k, pose, gn_img, ggn_img, h, w - 1, e, f, nullptr);
+        GV.x += e.x; GV.y += e.y; GV.z += e.z;
+      }
+      if (w == W - 2) {  // the last column's difference re-uses (W-2, W-1): q is its a0
+        float3 e, f;
+        normal_terms(a, dimg, k, pose, gn_img, ggn_img, h, W - 1, e, f, nullptr);
+        GV.x -= e.x; GV.y -= e.y; GV.z -= e.z;
+      }
+      if (h >= 1) {
+        float3 e, f;
+        normal_terms(a, dimg, k, pose, gn_img, ggn_img, h - 1, w, e, f, nullptr);
+        GV.x += f.x; GV.y += f.y; GV.z += f.z;
+      }
+      if (h == H - 2) {
+        float3 e, f;
+        normal_terms(a, dimg, k, pose, gn_img, ggn_img, H - 1, w, e, f, nullptr);
+        GV.x -= f.x; GV.y -= f.y; GV.z -= f.z;
+      }
+    }
+    a.g_depth[(int64_t)img * P + pix] = vf * (ray.x * GV.x + ray.y * GV.y + ray.z * GV.z);
+    if (a.pose_partials && pose) {
+      // dL/dR = ggv (x) v + ggn (x) n ;  dL/dt = ggv
+      float3 ggn = make_float3(0.f, 0.f, 0.f);
+      if (ggn_img) ggn = ld3(ggn_img + o);
+      const float gg[3] = {ggv.x, ggv.y, ggv.z}, gn3[3] = {ggn.x, ggn.y, ggn.z};
+      const float vv[3] = {v.x, v.y, v.z}, nn[3] = {n_q.x, n_q.y, n_q.z};
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+#pragma unroll
+        for (int j = 0; j < 3; ++j) acc[i * 4 + j] = gg[i] * vv[j] + gn3[i] * nn[j];
+        acc[i * 4 + 3] = gg[i];
+      }
+    }
+  }
+  if (a.pose_partials) {
+#pragma unroll
+    for (int i = 0; i < 12; ++i) {
+      float x = acc[i];
+#pragma unroll
+      for (int s = 16; s > 0; s >>= 1) x += __shfl_xor_sync(0xffffffffu, x, s);
+      acc[i] = x;
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0)
+#pragma unroll
+      for (int i = 0; i < 12; ++i) s_red[warp][i] = acc[i];
+    __syncthreads();
+    if (threadIdx.x < 12) {
+      float x = 0.0f;
+      for (int wv = 0; wv < kTile / 32; ++wv) x += s_red[wv][threadIdx.x];
+      a.pose_partials[((int64_t)img * a.tiles + blockIdx.x) * 12 + threadIdx.x] = x;
+    }
+  }
+}
+
+__global__ void k_pose_grad_reduce(const float *partials, int tiles, float *g_poses, int n_img) {
+  const int img = blockIdx.x;
+  const int i = threadIdx.x;  // 0..15
+  if (img >= n_img || i >= 16) return;
+  float x = 0.0f;
+  if (i < 12)
+    for (int t = 0; t < tiles; ++t) x += partials[((int64_t)img * tiles + t) * 12 + i];
+  g_poses[(int64_t)img * 16 + i] = x;  // bottom row gets zeros
+}
+
+}  // namespace gsx
+
+extern "C" int64_t gsx_backproject_normals_bwd_scratch_bytes(int B, int L, int H, int W) {
+  if (B < 0 || L < 0 || H < 2 || W < 2) return -1;
+  const int64_t tiles = ((int64_t)H * W + gsx::kTile - 1) / gsx::kTile;
+  return (int64_t)B * L * tiles * 12 * 4 + 256;
+}
+
+extern "C" int gsx_backproject_normals_bwd(const float *depth, int64_t depth_bstride, const float *intrinsics,
+                                           int64_t K_bstride, const float *poses, int64_t pose_bstride, int B,
+                                           int L, int H, int W, const float *g_vertex, const float *g_normal,
+                                           const float *g_gvertex, const float *g_gnormal, float *g_depth,
+                                           float *g_poses, void *scratch, int64_t scratch_bytes, void *stream) {
+  GSX_CHECK_ARG(depth && intrinsics && g_depth, "gsx_backproject_normals_bwd: null pointer");
+  GSX_CHECK_ARG(B >= 0 && L >= 0 && H >= 2 && W >= 2, "gsx_backproject_normals_bwd: need H,W >= 2");
+  GSX_CHECK_ARG((int64_t)B * L <= 65535, "gsx_backproject_normals_bwd: extents too large");
+  if ((int64_t)B * L == 0) return 0;
+  const int tiles = (int)(((int64_t)H * W + gsx::kTile - 1) / gsx::kTile);
+  const bool want_pose = g_poses && poses;
+  if (want_pose)
+    GSX_CHECK_ARG(scratch && scratch_bytes >= gsx_backproject_normals_bwd_scratch_bytes(B, L, H, W),
+                  "gsx_backproject_normals_bwd: scratch too small");
+  gsx::FrameBwdArgs a{depth, depth_bstride, intrinsics, K_bstride, poses, pose_bstride, B, L, H, W,
+                      {g_vertex, g_normal, g_gvertex, g_gnormal}, g_depth, want_pose ? (float *)scratch : nullptr,
+                      tiles};
+  cudaStream_t s = (cudaStream_t)stream;
+  gsx::k_backproject_normals_bwd<<<dim3((unsigned)tiles, (unsigned)(B * L)), gsx::kTile, 0, s>>>(a);
+  if (want_pose) gsx::k_pose_grad_reduce<<<B * L, 16, 0, s>>>((const float *)scratch, tiles, g_poses, B * L);
+  GSX_CHECK_LAUNCH("gsx_backproject_normals_bwd");
+  return 0;
+}

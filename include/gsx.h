@@ -49,6 +49,19 @@ int gsx_backproject_normals_fwd(const float *depth, int64_t depth_bstride, const
                                 int H, int W, float *vertex, float *normal, float *gvertex, float *gnormal,
                                 void *stream);
 
+/* backward of K1: from the upstream gradients of any of the four maps (dense (B,L,H,W,3), NULL = zero)
+ * computes d(loss)/d(depth) (B,L,H,W) and, if g_poses != NULL and poses != NULL, d(loss)/d(poses)
+ * (B*L,4,4) (top 3x4 block; bottom row zero).  Autograd counterpart of the op chain above (the reference
+ * obtains it from PyTorch's tape).  Gradients w.r.t. the intrinsics are not produced.  Deterministic: no
+ * atomics; pose gradients are reduced per tile then summed in tile order.
+ * scratch: gsx_backproject_normals_bwd_scratch_bytes(B,L,H,W) bytes (only needed for g_poses). */
+int64_t gsx_backproject_normals_bwd_scratch_bytes(int B, int L, int H, int W);
+int gsx_backproject_normals_bwd(const float *depth, int64_t depth_bstride, const float *intrinsics,
+                                int64_t K_bstride, const float *poses, int64_t pose_bstride, int B, int L,
+                                int H, int W, const float *g_vertex, const float *g_normal,
+                                const float *g_gvertex, const float *g_gnormal, float *g_depth,
+                                float *g_poses, void *scratch, int64_t scratch_bytes, void *stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Fused PointFusion map update (K2+K3 and K4), one live frame for all B elements.
  * replaces update_map_fusion = find_active_map_points + find_similar_map_points +
