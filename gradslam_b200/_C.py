@@ -51,8 +51,10 @@ SIGNATURES = {
                                  c_vp, c_vp]),
     "gsx_unique_select": (c_int, [c_vp, c_i64, c_vp, c_vp, c_i64, c_vp, c_int, c_int, c_int, c_vp, c_vp, c_vp, c_vp]),
     "gsx_records_from_table": (c_int, [c_vp, c_i64, c_i64, c_int, c_int, c_int, c_vp, c_vp]),
+    "gsx_knn1_scratch_bytes": (c_i64, [c_int, c_int, c_int]),
+    "gsx_icp_tgt_scratch_bytes": (c_i64, [c_int, c_i64]),
     "gsx_knn1": (c_int, [c_vp, c_vp, c_int, c_vp, c_vp, c_int, c_int, c_vp, c_vp, c_vp, c_i64, c_vp]),
-    "gsx_icp_align_scratch_bytes": (c_i64, [c_int, c_int]),
+    "gsx_icp_align_scratch_bytes": (c_i64, [c_int, c_int, c_int]),
     "gsx_icp_align": (
         c_int, [c_vp, c_vp, c_int, c_vp, c_vp, c_vp, c_int, c_int, c_vp, c_int, c_int, c_float, c_int, c_float,
                 c_float, c_float, c_float, c_float, c_vp, c_vp, c_vp, c_i64, c_vp]),
@@ -60,7 +62,7 @@ SIGNATURES = {
     "gsx_icp_localize": (
         c_int, [c_vp, c_vp, c_vp, c_i64, c_i64, c_vp, c_i64, c_vp, c_i64, c_vp, c_i64, c_int, c_int, c_int, c_int,
                 c_int, c_int, c_float, c_int, c_float, c_float, c_float, c_float, c_float, c_vp, c_i64, c_vp, c_i64,
-                c_vp, c_u32, c_vp]),
+                c_vp, c_i64, c_u32, c_vp, c_vp]),
 }
 
 _lib = None

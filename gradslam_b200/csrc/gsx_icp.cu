@@ -110,6 +110,7 @@ struct GatherTgtArgs {
   unsigned int *ticket;            // (B)
   int tiles;                       // tiles per element (= ceil(max_count / 1024))
   unsigned int epoch;
+  int32_t *overflow;  // set to 1 if the target cloud did not fit nt_cap (may be null)
 };
 
 constexpr unsigned long long kAgg = 1ull, kPrefix = 2ull;
@@ -226,10 +227,232 @@ __global__ void __launch_bounds__(kIcpBlock) k_icp_gather_tgt(GatherTgtArgs a) {
         on[(int64_t)pos * 3 + 0] = __ldg(nrm + (int64_t)n[j] * 3);
         on[(int64_t)pos * 3 + 1] = __ldg(nrm + (int64_t)n[j] * 3 + 1);
         on[(int64_t)pos * 3 + 2] = __ldg(nrm + (int64_t)n[j] * 3 + 2);
+      } else if (a.overflow) {
+        *a.overflow = 1;
       }
     }
   }
   if (tile == a.tiles - 1 && threadIdx.x == 0) a.tgt_count[b] = min(s_excl + total, a.nt_cap);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// uniform grid over the target cloud (built once per ICP call: the target does not move during the loop)
+// ---------------------------------------------------------------------------------------------------------
+constexpr int kGridMaxDim = 64;                                                          // cells per axis
+constexpr int kGridMaxCells = (kGridMaxDim + 1) * (kGridMaxDim + 1) * (kGridMaxDim + 1);  // 274 625
+constexpr int kGridMaxRing = 3;  // rings searched before a query falls back to the full scan
+
+struct GridParams {  // per element
+  float ox, oy, oz;  // origin (bbox min)
+  float inv_c, c;    // cells are cubes of edge c
+  int nx, ny, nz;
+};
+
+struct TargetGrid {
+  GridParams *params;   // (B)
+  int *cell_start;      // (B, kGridMaxCells + 1) exclusive prefix of the per-cell counts
+  int *cursor;          // (B, kGridMaxCells)     counts, then scatter cursors
+  float4 *sorted;       // (B, nt_stride)         (x, y, z, original index as int bits), grouped by cell
+};
+
+__device__ __forceinline__ int cell_coord(float p, float o, float inv_c, int n) {
+  const int i = (int)floorf((p - o) * inv_c);
+  return min(max(i, 0), n - 1);
+}
+
+__global__ void __launch_bounds__(256) k_grid_bbox(const float *tgt_p, const int32_t *tgt_count, int nt_stride,
+                                                   TargetGrid g) {
+  __shared__ float s_lo[3][8], s_hi[3][8];
+  const int b = blockIdx.x;
+  const int nt = tgt_count[b];
+  const float *p = tgt_p + (int64_t)b * nt_stride * 3;
+  float lo[3] = {3.0e38f, 3.0e38f, 3.0e38f}, hi[3] = {-3.0e38f, -3.0e38f, -3.0e38f};
+  for (int i = threadIdx.x; i < nt; i += 256)
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      const float v = __ldg(p + (int64_t)i * 3 + a);
+      lo[a] = fminf(lo[a], v);
+      hi[a] = fmaxf(hi[a], v);
+    }
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      lo[a] = fminf(lo[a], __shfl_xor_sync(0xffffffffu, lo[a], o));
+      hi[a] = fmaxf(hi[a], __shfl_xor_sync(0xffffffffu, hi[a], o));
+    }
+    if ((threadIdx.x & 31) == 0) {
+      s_lo[a][threadIdx.x >> 5] = lo[a];
+      s_hi[a][threadIdx.x >> 5] = hi[a];
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float l[3], h[3];
+    for (int a = 0; a < 3; ++a) {
+      l[a] = s_lo[a][0];
+      h[a] = s_hi[a][0];
+      for (int w = 1; w < 8; ++w) {
+        l[a] = fminf(l[a], s_lo[a][w]);
+        h[a] = fmaxf(h[a], s_hi[a][w]);
+      }
+    }
+    GridParams gp;
+    if (nt <= 0) {
+      gp = GridParams{0.f, 0.f, 0.f, 1.f, 1.f, 1, 1, 1};
+    } else {
+      const float ext = fmaxf(fmaxf(h[0] - l[0], h[1] - l[1]), fmaxf(h[2] - l[2], 1e-6f));
+      const float c = ext / (float)kGridMaxDim;
+      gp.ox = l[0]; gp.oy = l[1]; gp.oz = l[2];
+      gp.c = c;
+      gp.inv_c = 1.0f / c;
+      gp.nx = min(kGridMaxDim + 1, (int)floorf((h[0] - l[0]) * gp.inv_c) + 1);
+      gp.ny = min(kGridMaxDim + 1, (int)floorf((h[1] - l[1]) * gp.inv_c) + 1);
+      gp.nz = min(kGridMaxDim + 1, (int)floorf((h[2] - l[2]) * gp.inv_c) + 1);
+    }
+    g.params[b] = gp;
+  }
+}
+
+__global__ void __launch_bounds__(256) k_grid_clear(TargetGrid g, int B) {
+  const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  if (i < (int64_t)B * kGridMaxCells) g.cursor[i] = 0;
+}
+
+__global__ void __launch_bounds__(256) k_grid_count(const float *tgt_p, const int32_t *tgt_count, int nt_stride,
+                                                    TargetGrid g) {
+  const int b = blockIdx.y;
+  const int i = blockIdx.x * 256 + threadIdx.x;
+  if (i >= tgt_count[b]) return;
+  const GridParams gp = g.params[b];
+  const float *p = tgt_p + ((int64_t)b * nt_stride + i) * 3;
+  const int cx = cell_coord(__ldg(p), gp.ox, gp.inv_c, gp.nx), cy = cell_coord(__ldg(p + 1), gp.oy, gp.inv_c, gp.ny),
+            cz = cell_coord(__ldg(p + 2), gp.oz, gp.inv_c, gp.nz);
+  atomicAdd(g.cursor + (int64_t)b * kGridMaxCells + (cz * gp.ny + cy) * gp.nx + cx, 1);
+}
+
+__global__ void __launch_bounds__(1024) k_grid_scan(TargetGrid g) {
+  __shared__ int s_warp[32];
+  __shared__ int s_base;
+  const int b = blockIdx.x;
+  const GridParams gp = g.params[b];
+  const int ncell = gp.nx * gp.ny * gp.nz;
+  int *cnt = g.cursor + (int64_t)b * kGridMaxCells;
+  int *start = g.cell_start + (int64_t)b * (kGridMaxCells + 1);
+  if (threadIdx.x == 0) s_base = 0;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int base = 0; base < ncell; base += 1024) {
+    const int i = base + threadIdx.x;
+    const int v = (i < ncell) ? cnt[i] : 0;
+    int x = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int y = __shfl_up_sync(0xffffffffu, x, o);
+      if (lane >= o) x += y;
+    }
+    if (lane == 31) s_warp[warp] = x;
+    __syncthreads();
+    int off = s_base;
+    for (int w = 0; w < warp; ++w) off += s_warp[w];
+    if (i < ncell) {
+      start[i] = off + x - v;
+      cnt[i] = off + x - v;  // becomes the scatter cursor
+    }
+    __syncthreads();
+    if (threadIdx.x == 1023) s_base = off + x;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) start[ncell] = s_base;
+}
+
+__global__ void __launch_bounds__(256) k_grid_scatter(const float *tgt_p, const int32_t *tgt_count, int nt_stride,
+                                                      TargetGrid g) {
+  const int b = blockIdx.y;
+  const int i = blockIdx.x * 256 + threadIdx.x;
+  if (i >= tgt_count[b]) return;
+  const GridParams gp = g.params[b];
+  const float *p = tgt_p + ((int64_t)b * nt_stride + i) * 3;
+  const float x = __ldg(p), y = __ldg(p + 1), z = __ldg(p + 2);
+  const int cx = cell_coord(x, gp.ox, gp.inv_c, gp.nx), cy = cell_coord(y, gp.oy, gp.inv_c, gp.ny),
+            cz = cell_coord(z, gp.oz, gp.inv_c, gp.nz);
+  const int pos = atomicAdd(g.cursor + (int64_t)b * kGridMaxCells + (cz * gp.ny + cy) * gp.nx + cx, 1);
+  g.sorted[(int64_t)b * nt_stride + pos] = make_float4(x, y, z, __int_as_float(i));
+}
+
+// Exact nearest neighbour of (sx,sy,sz) through the grid.  Candidates are compared on (squared distance, original
+// index) so the result is identical to an ascending brute-force scan with a strict '<' (lowest index on ties),
+// whatever the order of the points inside a cell.  Rings of cells are visited outwards; the search stops as soon
+// as the best distance is provably not larger than the distance to anything not yet visited; queries that do not
+// terminate within kGridMaxRing rings fall back to scanning every target point.
+__device__ __forceinline__ void nn_update(float d, int idx, float &best, int &bi) {
+  if (bi < 0 || d < best || (d == best && idx < bi)) {
+    best = d;
+    bi = idx;
+  }
+}
+
+__device__ void search_grid(const TargetGrid &g, int b, int nt, int nt_stride, float sx, float sy, float sz, float &best,
+                            int &bi) {
+  const GridParams gp = g.params[b];
+  const int *start = g.cell_start + (int64_t)b * (kGridMaxCells + 1);
+  const float4 *pts = g.sorted + (int64_t)b * nt_stride;
+  const float gx = (sx - gp.ox) * gp.inv_c, gy = (sy - gp.oy) * gp.inv_c, gz = (sz - gp.oz) * gp.inv_c;
+  const int cx = min(max((int)floorf(gx), 0), gp.nx - 1), cy = min(max((int)floorf(gy), 0), gp.ny - 1),
+            cz = min(max((int)floorf(gz), 0), gp.nz - 1);
+  bool done = false;
+  for (int r = 0; r <= kGridMaxRing && !done; ++r) {
+    const int z0 = max(cz - r, 0), z1 = min(cz + r, gp.nz - 1);
+    const int y0 = max(cy - r, 0), y1 = min(cy + r, gp.ny - 1);
+    const int x0 = max(cx - r, 0), x1 = min(cx + r, gp.nx - 1);
+    for (int z = z0; z <= z1; ++z)
+      for (int y = y0; y <= y1; ++y) {
+        const bool shell_row = (abs(z - cz) == r) || (abs(y - cy) == r);
+        const int row = (z * gp.ny + y) * gp.nx;
+        if (shell_row) {  // the whole x-run belongs to the shell: cells are contiguous in the sorted array
+          const int e0 = start[row + x0], e1 = start[row + x1 + 1];
+          for (int e = e0; e < e1; ++e) {
+            const float4 p = pts[e];
+            const float dx = sx - p.x, dy = sy - p.y, dz = sz - p.z;
+            nn_update((dx * dx + dy * dy) + dz * dz, __float_as_int(p.w), best, bi);
+          }
+        } else {  // only the two end cells of the run are new
+          for (int side = 0; side < 2; ++side) {
+            const int x = side ? cx + r : cx - r;
+            if (x < 0 || x >= gp.nx || (side && r == 0)) continue;
+            const int e0 = start[row + x], e1 = start[row + x + 1];
+            for (int e = e0; e < e1; ++e) {
+              const float4 p = pts[e];
+              const float dx = sx - p.x, dy = sy - p.y, dz = sz - p.z;
+              nn_update((dx * dx + dy * dy) + dz * dz, __float_as_int(p.w), best, bi);
+            }
+          }
+        }
+      }
+    // distance (in cells) from the query to the nearest face of the visited cube that still has cells behind it
+    float m = 3.0e38f;
+    bool open = false;
+    if (cx - r > 0) { m = fminf(m, gx - (float)(cx - r)); open = true; }
+    if (cx + r < gp.nx - 1) { m = fminf(m, (float)(cx + r + 1) - gx); open = true; }
+    if (cy - r > 0) { m = fminf(m, gy - (float)(cy - r)); open = true; }
+    if (cy + r < gp.ny - 1) { m = fminf(m, (float)(cy + r + 1) - gy); open = true; }
+    if (cz - r > 0) { m = fminf(m, gz - (float)(cz - r)); open = true; }
+    if (cz + r < gp.nz - 1) { m = fminf(m, (float)(cz + r + 1) - gz); open = true; }
+    if (!open) {
+      done = true;  // the cube covers the whole grid
+    } else if (bi >= 0 && m > 1e-3f) {
+      // 1e-3 cells of slack covers the rounding of the cell assignment (|error| < 2e-5 cells for <= 65 cells)
+      const float lim = (m - 1e-3f) * gp.c;
+      if (best <= lim * lim) done = true;
+    }
+  }
+  if (!done) {  // rare: a query far from every target point -> exact full scan
+    for (int e = 0; e < nt; ++e) {
+      const float4 p = pts[e];
+      const float dx = sx - p.x, dy = sy - p.y, dz = sz - p.z;
+      nn_update((dx * dx + dy * dy) + dz * dz, __float_as_int(p.w), best, bi);
+    }
+  }
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -249,10 +472,12 @@ struct KnnArgs {
   float *partials;  // (B, gridDim.x, 28)
   int64_t *nn_idx;  // optional (B, ns_stride): nn index per source point (-1 = filtered / invalid)
   float *nn_d2;     // optional (B, ns_stride)
+  TargetGrid grid;  // used by the kGrid variant
 };
 
+template <bool kGrid>
 __global__ void __launch_bounds__(kIcpBlock) k_icp_knn_linearize(KnnArgs a) {
-  __shared__ float4 s_t[kTgtTile];
+  __shared__ float4 s_t[kGrid ? 1 : kTgtTile];
   __shared__ float s_red[kIcpBlock / 32][kNumSums];
   __shared__ Rigid s_pre;
   const int b = blockIdx.y;
@@ -281,7 +506,9 @@ __global__ void __launch_bounds__(kIcpBlock) k_icp_knn_linearize(KnnArgs a) {
   }
   float best = 0.0f;
   int bi = -1;
-  if (blockIdx.x * kIcpBlock < ns) {  // whole block idle otherwise (uniform)
+  if (kGrid) {
+    if (valid && nt > 0) search_grid(a.grid, b, nt, a.nt_stride, sx, sy, sz, best, bi);
+  } else if (blockIdx.x * kIcpBlock < ns) {  // whole block idle otherwise (uniform)
     for (int base = 0; base < nt; base += kTgtTile) {
       const int m = min(kTgtTile, nt - base);
       __syncthreads();
@@ -586,10 +813,28 @@ inline IcpWorkspace icp_carve(void *ws, int B, int H, int W, int ds, int64_t map
 }
 
 // runs the LM / gradLM loop on clouds that are already in place
+constexpr int kGridThreshold = 4096;  // target clouds up to this size use the shared-memory brute force
+
+inline int64_t grid_bytes(int B, int nt_stride) {
+  if (nt_stride <= kGridThreshold) return 0;
+  return up256((int64_t)B * sizeof(GridParams)) + up256((int64_t)B * (kGridMaxCells + 1) * 4) +
+         up256((int64_t)B * kGridMaxCells * 4) + up256((int64_t)B * nt_stride * 16);
+}
+
+inline TargetGrid grid_carve(void *mem, int B, int nt_stride) {
+  TargetGrid g;
+  char *p = (char *)mem;
+  g.params = (GridParams *)p;  p += up256((int64_t)B * sizeof(GridParams));
+  g.cell_start = (int *)p;     p += up256((int64_t)B * (kGridMaxCells + 1) * 4);
+  g.cursor = (int *)p;         p += up256((int64_t)B * kGridMaxCells * 4);
+  g.sorted = (float4 *)p;
+  return g;
+}
+
 int run_icp_loop(float *src, const int32_t *src_count, int ns_stride, const float *tgt_p, const float *tgt_n,
                  const int32_t *tgt_count, int nt_stride, int B, const float *T0, int mode, int numiters, float damp,
                  int use_thresh, float dist_thresh, float lambda_max, float Bp, float B2p, float nu, float *partials,
-                 int nblk_cap, IcpState st, int64_t *nn_idx, cudaStream_t stream) {
+                 int nblk_cap, IcpState st, int64_t *nn_idx, void *grid_mem, cudaStream_t stream) {
   const int nblk = (ns_stride + kIcpBlock - 1) / kIcpBlock;
   if (nblk > nblk_cap) {
     set_error("icp: source cloud larger than workspace");
@@ -598,18 +843,30 @@ int run_icp_loop(float *src, const int32_t *src_count, int ns_stride, const floa
   k_icp_init<<<(B + 63) / 64, 64, 0, stream>>>(st, T0, damp, B);
   UpdateArgs u{mode, 1.0f / lambda_max, lambda_max, Bp, B2p, 1.0f / nu};
   KnnArgs ka{src, src_count, ns_stride, tgt_p, tgt_n, tgt_count, nt_stride, nullptr, 0, dist_thresh, use_thresh,
-             partials, nullptr, nullptr};
+             partials, nullptr, nullptr, TargetGrid{}};
+  const bool use_grid = grid_mem != nullptr && nt_stride > kGridThreshold;
+  if (use_grid) {  // the target is fixed for the whole loop: bin it once
+    ka.grid = grid_carve(grid_mem, B, nt_stride);
+    const unsigned nb = (unsigned)((nt_stride + 255) / 256);
+    k_grid_bbox<<<B, 256, 0, stream>>>(tgt_p, tgt_count, nt_stride, ka.grid);
+    k_grid_clear<<<(unsigned)(((int64_t)B * kGridMaxCells + 255) / 256), 256, 0, stream>>>(ka.grid, B);
+    k_grid_count<<<dim3(nb, (unsigned)B), 256, 0, stream>>>(tgt_p, tgt_count, nt_stride, ka.grid);
+    k_grid_scan<<<B, 1024, 0, stream>>>(ka.grid);
+    k_grid_scatter<<<dim3(nb, (unsigned)B), 256, 0, stream>>>(tgt_p, tgt_count, nt_stride, ka.grid);
+  }
   const dim3 grid((unsigned)nblk, (unsigned)B);
   for (int it = 0; it < numiters; ++it) {
     ka.pre = st.T_pend;
     ka.write_back = 1;
     ka.nn_idx = (it == numiters - 1) ? nn_idx : nullptr;
-    k_icp_knn_linearize<<<grid, kIcpBlock, 0, stream>>>(ka);
+    if (use_grid) k_icp_knn_linearize<true><<<grid, kIcpBlock, 0, stream>>>(ka);
+    else k_icp_knn_linearize<false><<<grid, kIcpBlock, 0, stream>>>(ka);
     k_icp_solve<<<B, 32, 0, stream>>>(partials, nblk, st);
     ka.pre = st.dT;
     ka.write_back = 0;
     ka.nn_idx = nullptr;
-    k_icp_knn_linearize<<<grid, kIcpBlock, 0, stream>>>(ka);
+    if (use_grid) k_icp_knn_linearize<true><<<grid, kIcpBlock, 0, stream>>>(ka);
+    else k_icp_knn_linearize<false><<<grid, kIcpBlock, 0, stream>>>(ka);
     k_icp_update<<<B, 32, 0, stream>>>(partials, nblk, st, u);
   }
   GSX_CHECK_LAUNCH("gsx_icp");
@@ -637,7 +894,7 @@ extern "C" int gsx_icp_align(const float *src_points, const int32_t *src_count, 
   // scratch: working copy of src (B,ns,3) + partials + state
   const int nblk = (ns_stride + kIcpBlock - 1) / kIcpBlock;
   const int64_t need = up256((int64_t)B * ns_stride * 12) + up256((int64_t)B * nblk * kNumSums * 4) +
-                       3 * up256((int64_t)B * 64) + 3 * up256((int64_t)B * 24);
+                       3 * up256((int64_t)B * 64) + 3 * up256((int64_t)B * 24) + grid_bytes(B, nt_stride);
   GSX_CHECK_ARG(scratch_bytes >= need, "gsx_icp_align: scratch too small (%lld < %lld)", (long long)scratch_bytes,
                 (long long)need);
   char *p = (char *)scratch;
@@ -649,22 +906,28 @@ extern "C" int gsx_icp_align(const float *src_points, const int32_t *src_count, 
   st.dT = (float *)p;            p += up256((int64_t)B * 64);
   st.xi = (float *)p;            p += up256((int64_t)B * 24);
   st.err = (float *)p;           p += up256((int64_t)B * 24);
-  st.damp = (float *)p;
+  st.damp = (float *)p;        p += up256((int64_t)B * 24);
+  void *grid_mem = grid_bytes(B, nt_stride) ? (void *)p : nullptr;
   cudaStream_t s = (cudaStream_t)stream;
   cudaMemcpyAsync(src, src_points, (size_t)B * ns_stride * 12, cudaMemcpyDeviceToDevice, s);
   const int rc = run_icp_loop(src, src_count, ns_stride, tgt_points, tgt_normals, tgt_count, nt_stride, B,
                               initial_transform, mode, numiters, damp, use_dist_thresh, dist_thresh, lambda_max, Bp,
-                              B2p, nu, partials, nblk, st, nn_idx_out, s);
+                              B2p, nu, partials, nblk, st, nn_idx_out, grid_mem, s);
   if (rc) return rc;
   cudaMemcpyAsync(transform_out, st.T_total, (size_t)B * 64, cudaMemcpyDeviceToDevice, s);
   return 0;
 }
 
-extern "C" int64_t gsx_icp_align_scratch_bytes(int B, int ns_stride) {
-  if (B < 1 || ns_stride < 1) return -1;
+extern "C" int64_t gsx_icp_align_scratch_bytes(int B, int ns_stride, int nt_stride) {
+  if (B < 1 || ns_stride < 1 || nt_stride < 1) return -1;
   const int nblk = (ns_stride + kIcpBlock - 1) / kIcpBlock;
   return up256((int64_t)B * ns_stride * 12) + up256((int64_t)B * nblk * kNumSums * 4) + 3 * up256((int64_t)B * 64) +
-         3 * up256((int64_t)B * 24);
+         3 * up256((int64_t)B * 24) + grid_bytes(B, nt_stride);
+}
+
+extern "C" int64_t gsx_icp_tgt_scratch_bytes(int B, int64_t tgt_capacity) {
+  if (B < 1 || tgt_capacity < 1 || tgt_capacity > (1ll << 30)) return -1;
+  return 2 * up256((int64_t)B * tgt_capacity * 12) + grid_bytes(B, (int)tgt_capacity);
 }
 
 extern "C" int gsx_icp_localize(const float *map_points, const float *map_normals, const int32_t *counts,
@@ -672,8 +935,9 @@ extern "C" int gsx_icp_localize(const float *map_points, const float *map_normal
                                 const float *intrinsics, int64_t K_bstride, const float *prev_poses,
                                 int64_t prev_pose_bstride, int B, int H, int W, int ds, int mode, int numiters,
                                 float damp, int use_dist_thresh, float dist_thresh, float lambda_max, float Bp,
-                                float B2p, float nu, float *tgt_scratch, int64_t tgt_capacity, float *poses_out,
-                                int64_t poses_out_bstride, void *workspace, uint32_t epoch, void *stream) {
+                                float B2p, float nu, void *tgt_scratch, int64_t tgt_capacity, float *poses_out,
+                                int64_t poses_out_bstride, void *workspace, int64_t workspace_map_capacity,
+                                uint32_t epoch, int32_t *overflow_flag, void *stream) {
   GSX_CHECK_ARG(map_points && map_normals && counts && depth && intrinsics && prev_poses && poses_out && workspace &&
                     tgt_scratch,
                 "gsx_icp_localize: null pointer");
@@ -682,9 +946,15 @@ extern "C" int gsx_icp_localize(const float *map_points, const float *map_normal
   GSX_CHECK_ARG(max_count <= capacity && tgt_capacity >= 1, "gsx_icp_localize: bad capacities");
   GSX_CHECK_ARG(epoch >= 1 && epoch < (1u << 30), "gsx_icp_localize: epoch out of range");
   cudaStream_t s = (cudaStream_t)stream;
-  IcpWorkspace w = icp_carve(workspace, B, H, W, ds, capacity);
-  float *tgt_p = tgt_scratch;
-  float *tgt_n = tgt_scratch + (int64_t)B * tgt_capacity * 3;
+  GSX_CHECK_ARG(workspace_map_capacity >= max_count, "gsx_icp_localize: workspace sized for a smaller map");
+  // the layout of the workspace is fixed by the capacity it was created for, not by today's map capacity
+  IcpWorkspace w = icp_carve(workspace, B, H, W, ds, workspace_map_capacity);
+  GSX_CHECK_ARG(tgt_capacity < (1ll << 30), "gsx_icp_localize: tgt_capacity too large");
+  float *tgt_p = (float *)tgt_scratch;
+  float *tgt_n = (float *)((char *)tgt_scratch + up256((int64_t)B * tgt_capacity * 12));
+  void *grid_mem = grid_bytes(B, (int)tgt_capacity)
+                       ? (void *)((char *)tgt_scratch + 2 * up256((int64_t)B * tgt_capacity * 12))
+                       : nullptr;
   GatherSrcArgs gs{depth, depth_bstride, intrinsics, K_bstride, prev_poses, prev_pose_bstride, B, H, W, ds,
                    w.src, w.src_count, w.ns_cap};
   k_icp_gather_src<<<B, 1024, 0, s>>>(gs);
@@ -694,18 +964,24 @@ extern "C" int gsx_icp_localize(const float *map_points, const float *map_normal
   if (tiles > 0) {
     GatherTgtArgs gt{map_points, map_normals, counts, capacity, prev_poses, prev_pose_bstride, intrinsics, K_bstride,
                      B, H, W, ds, (float)(W - 0.999), (float)(H - 0.999), tgt_p, tgt_n, w.tgt_count,
-                     (int)tgt_capacity, w.tile_state, w.ticket, tiles, epoch};
+                     (int)tgt_capacity, w.tile_state, w.ticket, tiles, epoch, overflow_flag};
     k_icp_gather_tgt<<<dim3((unsigned)(tiles * B)), kIcpBlock, 0, s>>>(gt);
   }
   GSX_CHECK_LAUNCH("gsx_icp_localize(gather)");
   const int rc = run_icp_loop(w.src, w.src_count, w.ns_cap, tgt_p, tgt_n, w.tgt_count, (int)tgt_capacity, B, nullptr,
                               mode, numiters, damp, use_dist_thresh, dist_thresh, lambda_max, Bp, B2p, nu, w.partials,
-                              w.nblk, w.st, nullptr, s);
+                              w.nblk, w.st, nullptr, grid_mem, s);
   if (rc) return rc;
   k_pose_compose<<<(B + 63) / 64, 64, 0, s>>>(w.st.T_total, prev_poses, prev_pose_bstride, poses_out,
                                               poses_out_bstride, B);
   GSX_CHECK_LAUNCH("gsx_icp_localize(compose)");
   return 0;
+}
+
+extern "C" int64_t gsx_knn1_scratch_bytes(int B, int ns_stride, int nt_stride) {
+  if (B < 1 || ns_stride < 1 || nt_stride < 1) return -1;
+  const int nblk = (ns_stride + kIcpBlock - 1) / kIcpBlock;
+  return up256((int64_t)B * nblk * kNumSums * 4) + grid_bytes(B, nt_stride);
 }
 
 extern "C" int gsx_knn1(const float *src_points, const int32_t *src_count, int ns_stride, const float *tgt_points,
@@ -714,11 +990,25 @@ extern "C" int gsx_knn1(const float *src_points, const int32_t *src_count, int n
   GSX_CHECK_ARG(src_points && src_count && tgt_points && tgt_count && idx_out && scratch, "gsx_knn1: null pointer");
   GSX_CHECK_ARG(B >= 1 && ns_stride >= 1 && nt_stride >= 1, "gsx_knn1: bad extents");
   const int nblk = (ns_stride + kIcpBlock - 1) / kIcpBlock;
-  GSX_CHECK_ARG(scratch_bytes >= (int64_t)B * nblk * kNumSums * 4, "gsx_knn1: scratch too small");
+  const int64_t part = up256((int64_t)B * nblk * kNumSums * 4);
+  GSX_CHECK_ARG(scratch_bytes >= part + grid_bytes(B, nt_stride), "gsx_knn1: scratch too small");
   // the target normals are not needed for the association itself: reuse the points as a placeholder
   KnnArgs ka{const_cast<float *>(src_points), src_count, ns_stride, tgt_points, tgt_points, tgt_count, nt_stride,
-             nullptr, 0, 0.0f, 0, (float *)scratch, idx_out, d2_out};
-  k_icp_knn_linearize<<<dim3((unsigned)nblk, (unsigned)B), kIcpBlock, 0, (cudaStream_t)stream>>>(ka);
+             nullptr, 0, 0.0f, 0, (float *)scratch, idx_out, d2_out, TargetGrid{}};
+  cudaStream_t s = (cudaStream_t)stream;
+  const dim3 grid((unsigned)nblk, (unsigned)B);
+  if (nt_stride > kGridThreshold) {
+    ka.grid = grid_carve((char *)scratch + part, B, nt_stride);
+    const unsigned nb = (unsigned)((nt_stride + 255) / 256);
+    k_grid_bbox<<<B, 256, 0, s>>>(tgt_points, tgt_count, nt_stride, ka.grid);
+    k_grid_clear<<<(unsigned)(((int64_t)B * kGridMaxCells + 255) / 256), 256, 0, s>>>(ka.grid, B);
+    k_grid_count<<<dim3(nb, (unsigned)B), 256, 0, s>>>(tgt_points, tgt_count, nt_stride, ka.grid);
+    k_grid_scan<<<B, 1024, 0, s>>>(ka.grid);
+    k_grid_scatter<<<dim3(nb, (unsigned)B), 256, 0, s>>>(tgt_points, tgt_count, nt_stride, ka.grid);
+    k_icp_knn_linearize<true><<<grid, kIcpBlock, 0, s>>>(ka);
+  } else {
+    k_icp_knn_linearize<false><<<grid, kIcpBlock, 0, s>>>(ka);
+  }
   GSX_CHECK_LAUNCH("gsx_knn1");
   return 0;
 }

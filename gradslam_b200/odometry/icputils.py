@@ -77,7 +77,7 @@ def knn1(src: torch.Tensor, tgt: torch.Tensor):
     Nt = tgt.shape[1]
     idx = torch.empty((B, Ns), dtype=torch.int64, device=src.device)
     d2 = torch.empty((B, Ns), dtype=torch.float32, device=src.device)
-    scratch = torch.empty(B * ((Ns + 255) // 256) * 112, dtype=torch.uint8, device=src.device)
+    scratch = torch.empty(_C.lib().gsx_knn1_scratch_bytes(B, Ns, Nt), dtype=torch.uint8, device=src.device)
     ns_t, nt_t = _counts(Ns, B, src.device), _counts(Nt, B, src.device)  # keep alive across the call
     with torch.cuda.device(src.device):
         rc = _C.lib().gsx_knn1(_C.ptr(src), _C.ptr(ns_t), Ns, _C.ptr(tgt), _C.ptr(nt_t), Nt, B, _C.ptr(idx),
@@ -132,7 +132,7 @@ def icp_align(src, src_counts, tgt, tgt_normals, tgt_counts, T0, mode, numiters,
     out = torch.empty((Bn, 4, 4), dtype=torch.float32, device=dev)
     idx = torch.empty((Bn, Ns), dtype=torch.int64, device=dev) if want_idx else None
     lib = _C.lib()
-    nbytes = lib.gsx_icp_align_scratch_bytes(Bn, Ns)
+    nbytes = lib.gsx_icp_align_scratch_bytes(Bn, Ns, Nt)
     scratch = torch.empty(nbytes, dtype=torch.uint8, device=dev)
     T0c = None if T0 is None else T0.to(dev).float().contiguous()
     with torch.cuda.device(dev):
@@ -251,8 +251,11 @@ def localize_against_map(pointclouds, live_frame, prev_frame, dsratio, odomprov)
     prev = prev_frame.poses.contiguous()
     st = pointclouds._store
     ws = _IcpWorkspace.get(dev, B, H, W, dsratio, pointclouds.capacity)
-    bound = max(1, pointclouds._bound)
-    tgt = torch.empty((2, B, bound, 3), dtype=torch.float32, device=dev)
+    # target capacity: lattice-active map points.  32 map points per lattice pixel on average is far beyond
+    # anything a surfel map produces; if it is ever exceeded the kernel raises the map's overflow flag.
+    ns_cap = ((H + dsratio - 1) // dsratio) * ((W + dsratio - 1) // dsratio)
+    bound = max(1, min(pointclouds._bound, 32 * ns_cap))
+    tgt = torch.empty(_C.lib().gsx_icp_tgt_scratch_bytes(B, bound), dtype=torch.uint8, device=dev)
     out = torch.empty((B, 1, 4, 4), dtype=torch.float32, device=dev)
     mode = 1 if hasattr(odomprov, "lambda_max") else 0
     dth = odomprov.dist_thresh
@@ -264,6 +267,6 @@ def localize_against_map(pointclouds, live_frame, prev_frame, dsratio, odomprov)
             0.0 if dth is None else float(dth), float(getattr(odomprov, "lambda_max", 2.0)),
             float(getattr(odomprov, "B", 1.0)), float(getattr(odomprov, "B2", 1.0)),
             float(getattr(odomprov, "nu", 200.0)), _C.ptr(tgt), bound, _C.ptr(out), 16, _C.ptr(ws.buf),
-            ws.next_epoch(), _C.stream_ptr(dev))
+            ws.capacity, ws.next_epoch(), _C.ptr(pointclouds._overflow_flag()), _C.stream_ptr(dev))
     _C.check(rc, "gsx_icp_localize")
     return out

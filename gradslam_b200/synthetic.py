@@ -23,9 +23,9 @@ def intrinsics(H, W):
     return K
 
 
-def _room_from_cam(s, b, motion_scale=1.0):
-    """Camera-to-room transform of frame s, element b: yaw 0.01*s rad, t = (0.01 s + 0.002 b, 0.005 s, 0.008 s)."""
-    a = 0.01 * s * motion_scale
+def _room_from_cam(s, b, motion_scale=1.0, yaw0=0.0):
+    """Camera-to-room transform of frame s, element b: yaw yaw0 + 0.01*s rad, t = (0.01 s + 0.002 b, 0.005 s, 0.008 s)."""
+    a = yaw0 + 0.01 * s * motion_scale
     T = np.eye(4, dtype=np.float64)
     T[0, 0], T[0, 2] = math.cos(a), math.sin(a)
     T[2, 0], T[2, 2] = -math.sin(a), math.cos(a)
@@ -34,7 +34,7 @@ def _room_from_cam(s, b, motion_scale=1.0):
 
 
 def make_sequence(B, L, H, W, seed=0, hole_fraction=0.02, motion_scale=1.0, pin_memory=False,
-                  isolated_holes=False):
+                  isolated_holes=False, yaw0=0.0):
     """Returns (rgb (B,L,H,W,3), depth (B,L,H,W,1), intrinsics (B,1,4,4), poses (B,L,4,4)), all float32 CPU.
 
     poses are camera-to-world with frame 0 of every element at identity (world = camera 0).
@@ -43,7 +43,12 @@ def make_sequence(B, L, H, W, seed=0, hole_fraction=0.02, motion_scale=1.0, pin_
     right and its lower neighbour missing.  At such pixels the normal is the normalised cross product
     of two identical vectors: exactly zero in IEEE arithmetic without FMA, but normalised rounding
     garbage wherever `a*b - b*a` is contracted to an FMA (as the reference's torch.cross does on
-    AVX2 CPUs).  Fixtures that pin the oracle against the reference use isolated holes."""
+    AVX2 CPUs).  Fixtures that pin the oracle against the reference use isolated holes.
+
+    yaw0 turns the first camera about the vertical axis.  With yaw0 = 0 (SURVEY.md's scene) the 62-degree
+    horizontal field of view only sees the far wall, so point-to-plane ICP observes 3 of the 6 degrees of
+    freedom and drifts (the reference drifts identically); yaw0 ~ 0.6 looks into a corner (two walls + floor /
+    ceiling) and makes ICP well conditioned."""
     gen = torch.Generator().manual_seed(int(seed))
     K = intrinsics(H, W)
     fx, fy, cx, cy = K[0, 0], K[1, 1], K[0, 2], K[1, 2]
@@ -54,9 +59,9 @@ def make_sequence(B, L, H, W, seed=0, hole_fraction=0.02, motion_scale=1.0, pin_
     depth = torch.empty((B, L, H, W, 1), dtype=torch.float32, pin_memory=pin_memory)
     poses = torch.empty((B, L, 4, 4), dtype=torch.float32)
     for b in range(B):
-        T0_inv = np.linalg.inv(_room_from_cam(0, b, motion_scale))
+        T0_inv = np.linalg.inv(_room_from_cam(0, b, motion_scale, yaw0))
         for s in range(L):
-            T = _room_from_cam(s, b, motion_scale)
+            T = _room_from_cam(s, b, motion_scale, yaw0)
             d_room = dirs @ T[:3, :3].T
             o = T[:3, 3]
             with np.errstate(divide="ignore", invalid="ignore"):

@@ -179,15 +179,19 @@ int gsx_records_from_table(const int64_t *table, int64_t rows, int64_t capacity,
  * reference does (icputils.py:206).  Exact 1-NN ties resolve to the lowest target index.            */
 
 /* exact nearest neighbour of every source point: idx_out int64 (B, ns_stride) (-1 for rows >= size or an
- * empty target), d2_out squared distance (may be NULL).  scratch: B*ceil(ns_stride/256)*112 bytes. */
+ * empty target), d2_out squared distance (may be NULL).  scratch: gsx_knn1_scratch_bytes bytes.
+ * Target clouds with nt_stride > 4096 are binned into a uniform grid and searched ring by ring with an exact
+ * termination bound (full scan as the fallback); smaller ones are scanned from shared memory.  Both return
+ * the same (distance, index): candidates are ordered by (squared distance, index). */
+int64_t gsx_knn1_scratch_bytes(int B, int ns_stride, int nt_stride);
 int gsx_knn1(const float *src_points, const int32_t *src_count, int ns_stride, const float *tgt_points,
              const int32_t *tgt_count, int nt_stride, int B, int64_t *idx_out, float *d2_out, void *scratch,
              int64_t scratch_bytes, void *stream);
 
 /* full ICP / gradICP on given clouds.  initial_transform (B,16) or NULL (identity).  transform_out (B,16).
  * nn_idx_out optional int64 (B, ns_stride): association of the last iteration (-1 = filtered out).
- * scratch: gsx_icp_align_scratch_bytes(B, ns_stride) bytes. */
-int64_t gsx_icp_align_scratch_bytes(int B, int ns_stride);
+ * scratch: gsx_icp_align_scratch_bytes(B, ns_stride, nt_stride) bytes. */
+int64_t gsx_icp_align_scratch_bytes(int B, int ns_stride, int nt_stride);
 int gsx_icp_align(const float *src_points, const int32_t *src_count, int ns_stride, const float *tgt_points,
                   const float *tgt_normals, const int32_t *tgt_count, int nt_stride, int B,
                   const float *initial_transform, int mode, int numiters, float damp, int use_dist_thresh,
@@ -199,16 +203,20 @@ int gsx_icp_align(const float *src_points, const int32_t *src_count, int ns_stri
  * icputils.py:623-669); target cloud = map points inside the previous frame's frustum that land on the
  * ds-lattice (find_active_map_points + downsample_pointclouds, fusionutils.py:198-287,
  * icputils.py:548-620); ICP loop; poses_out[b] = T_icp[b] * prev_poses[b].
- * tgt_scratch: 2*B*tgt_capacity*3 floats (target points, normals); workspace:
- * gsx_icp_workspace_bytes(B,H,W,ds,map capacity) bytes zero-filled once; `epoch` increases by one per
+ * tgt_scratch: gsx_icp_tgt_scratch_bytes(B, tgt_capacity) bytes (target points, normals, search grid);
+ * *overflow_flag is set to 1 if a target cloud did not fit tgt_capacity (surplus dropped).  workspace:
+ * gsx_icp_workspace_bytes(B,H,W,ds,workspace_map_capacity) bytes zero-filled once (pass the same
+ * workspace_map_capacity >= max_count on every call: it fixes the layout); `epoch` increases by one per
  * call on the same workspace, starting at 1. */
 int64_t gsx_icp_workspace_bytes(int B, int H, int W, int ds, int64_t map_capacity);
+int64_t gsx_icp_tgt_scratch_bytes(int B, int64_t tgt_capacity);
 int gsx_icp_localize(const float *map_points, const float *map_normals, const int32_t *counts, int64_t capacity,
                      int64_t max_count, const float *depth, int64_t depth_bstride, const float *intrinsics,
                      int64_t K_bstride, const float *prev_poses, int64_t prev_pose_bstride, int B, int H, int W,
                      int ds, int mode, int numiters, float damp, int use_dist_thresh, float dist_thresh,
-                     float lambda_max, float Bp, float B2p, float nu, float *tgt_scratch, int64_t tgt_capacity,
-                     float *poses_out, int64_t poses_out_bstride, void *workspace, uint32_t epoch, void *stream);
+                     float lambda_max, float Bp, float B2p, float nu, void *tgt_scratch, int64_t tgt_capacity,
+                     float *poses_out, int64_t poses_out_bstride, void *workspace,
+                     int64_t workspace_map_capacity, uint32_t epoch, int32_t *overflow_flag, void *stream);
 
 #ifdef __cplusplus
 }

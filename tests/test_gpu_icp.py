@@ -135,3 +135,41 @@ def test_slam_with_icp_odometry_matches_oracle(cls, odom):
         else:  # set comparison: every point has a counterpart within 1e-3
             assert _nn_dist(mine, ref.map.points[b]).quantile(0.999) < 1e-3
             assert _nn_dist(ref.map.points[b], mine).quantile(0.999) < 1e-3
+
+
+@pytest.mark.parametrize("nt", [5000, 60000])
+def test_knn1_grid_path_is_exact(nt):
+    """Targets larger than 4096 points go through the uniform-grid search: identical (distance, index) to the
+    brute-force oracle, including duplicated targets, far-away queries (full-scan fallback) and queries outside the
+    target bounding box."""
+    from gradslam_b200.odometry import icputils
+
+    g = torch.Generator().manual_seed(1)
+    # targets on three planes of a box (surface-like), plus duplicates
+    a = torch.rand(nt, 3, generator=g)
+    face = torch.randint(0, 3, (nt,), generator=g)
+    a[torch.arange(nt), face] = 0.0
+    tgt = a * torch.tensor([4.0, 3.0, 6.0])
+    tgt[nt // 2: nt // 2 + 200] = tgt[:200]
+    src = tgt[torch.randint(0, nt, (3000,), generator=g)] + 0.01 * torch.randn(3000, 3, generator=g)
+    src[:100] = tgt[nt // 2: nt // 2 + 100]                      # exact hits on duplicated points -> lower index
+    src[100:150] += 50.0                                          # far outside the grid
+    src[150:200] = torch.rand(50, 3, generator=g) * torch.tensor([4.0, 3.0, 6.0]) + 1.0  # inside the box, off-surface
+    d2, idx = icputils.knn1(src[None].to(DEV), tgt[None].to(DEV))
+    rd2, ridx = oracle.knn1(src, tgt)
+    assert torch.equal(idx[0].cpu(), ridx)
+    assert torch.equal(d2[0].cpu(), rd2)
+    assert (idx[0, :100].cpu() == torch.arange(100)).all()
+
+
+def test_slam_with_dense_icp_uses_grid_and_matches_oracle():
+    """dsratio=1 makes the ICP clouds larger than 4096 points, so the localisation runs on the grid search."""
+    import gradslam_b200 as gs
+
+    B, L, H, W = 1, 3, 64, 80
+    rgb, depth, K, poses = make_sequence(B, L, H, W, seed=13)
+    slam = gs.PointFusion(odom="gradicp", numiters=6, dsratio=1, device=DEV)
+    pc, rec = slam(gs.RGBDImages(rgb.to(DEV), depth.to(DEV), K.to(DEV), poses.to(DEV)))
+    ref = oracle.run_slam(rgb, depth, K, poses, odom="gradicp", numiters=6, dsratio=1)
+    torch.testing.assert_close(rec.cpu(), ref.poses, rtol=0, atol=1e-4)
+    assert abs(pc.num_points_per_pointcloud.tolist()[0] - ref.map.counts()[0]) <= 12
