@@ -182,7 +182,7 @@ def main():
     import torch.distributed as dist
 
     import gradslam_b200 as gs
-    from gradslam_b200 import profiling
+    from gradslam_b200 import parallel, profiling
     from gradslam_b200.parallel import gather_maps
     from gradslam_b200.synthetic import make_sequence
 
@@ -202,9 +202,10 @@ def main():
     slam = gs.PointFusion(odom="gt", device=dev)
 
     def step(frames):
+        """Un-pipelined step (warm-up): fuse the batch, then all-gather the fused maps of every rank."""
         pc, poses = slam(frames)
         if world > 1:
-            pc = gather_maps(pc)  # final fused maps of every rank (variable-length NCCL all-gather)
+            pc = gather_maps(pc)
         return pc, poses
 
     def barrier():
@@ -217,10 +218,22 @@ def main():
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         res = None
+        pending = None  # (gather handle, poses) of the previous step
         for _ in range(steps):
-            pc, poses = step(frames)
-            if d2h:  # result read-back: recovered poses + per-map sizes
+            # N>1: the final-map all-gather of step k (NCCL, side stream) overlaps the fusion of step k+1
+            pc, poses = slam(frames)
+            if pending is not None:  # step k-1's maps travel while step k (just enqueued) computes
+                pc_done, poses_done = parallel.gather_maps_end(pending[0], wait=False), pending[1]
+                if d2h:
+                    res = (poses_done.cpu(), pc_done.num_points_per_pointcloud.cpu())
+            if world > 1:
+                pending = (parallel.gather_maps_begin(pc), poses)
+            elif d2h:  # result read-back: recovered poses + per-map sizes
                 res = (poses.cpu(), pc.num_points_per_pointcloud.cpu())
+        if pending is not None:
+            pc_done = parallel.gather_maps_end(pending[0], wait=True)
+            if d2h:
+                res = (pending[1].cpu(), pc_done.num_points_per_pointcloud.cpu())
         e1.record()
         torch.cuda.synchronize(dev)
         ms = e0.elapsed_time(e1)

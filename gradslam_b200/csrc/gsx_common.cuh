@@ -109,36 +109,37 @@ struct FrameSample {
   float3 v, n, gv, gn;
   float d;
 };
+
+// local normal of pixel (h,w) given its own local vertex v and validity vf (1 or 0)
+__device__ __forceinline__ float3 frame_normal(const float *__restrict__ dimg, const KInv &k, int h, int w, int H, int W,
+                                               const float3 &v, float vf) {
+  const int wa = (w < W - 1) ? w : w - 1;
+  const int ha = (h < H - 1) ? h : h - 1;
+  const float dr = __ldg(dimg + h * W + wa + 1);
+  const float db = __ldg(dimg + (ha + 1) * W + w);
+  const float3 a1 = backproject(k, (float)(wa + 1), (float)h, dr);
+  const float3 b1 = backproject(k, (float)w, (float)(ha + 1), db);
+  const float3 a0 = (wa == w) ? v : backproject(k, (float)wa, (float)h, __ldg(dimg + h * W + wa));
+  const float3 b0 = (ha == h) ? v : backproject(k, (float)w, (float)ha, __ldg(dimg + ha * W + w));
+  const float dhx = a1.x - a0.x, dhy = a1.y - a0.y, dhz = a1.z - a0.z;
+  const float dvx = b1.x - b0.x, dvy = b1.y - b0.y, dvz = b1.z - b0.z;
+  const float cx = dhy * dvz - dhz * dvy;
+  const float cy = dhz * dvx - dhx * dvz;
+  const float cz = dhx * dvy - dhy * dvx;
+  const float nrm = sqrtf((cx * cx + cy * cy) + cz * cz);
+  const float den = (nrm == 0.0f) ? 1.0f : nrm;
+  return make_float3((cx / den) * vf, (cy / den) * vf, (cz / den) * vf);
+}
+
 template <bool kWantNormal>
 __device__ __forceinline__ FrameSample frame_sample(const float *__restrict__ dimg, const KInv &k, const Rigid *pose,
                                                     int h, int w, int H, int W) {
   FrameSample s;
-  const int wa = (w < W - 1) ? w : w - 1;
-  const int ha = (h < H - 1) ? h : h - 1;
   const float dc = __ldg(dimg + h * W + w);
   s.d = dc;
   const float vf = dc > 0.0f ? 1.0f : 0.0f;
   s.v = backproject(k, (float)w, (float)h, dc);
-  if (kWantNormal) {
-    const float dr = __ldg(dimg + h * W + wa + 1);
-    const float db = __ldg(dimg + (ha + 1) * W + w);
-    const float3 a1 = backproject(k, (float)(wa + 1), (float)h, dr);
-    const float3 b1 = backproject(k, (float)w, (float)(ha + 1), db);
-    const float3 a0 = (wa == w) ? s.v : backproject(k, (float)wa, (float)h, __ldg(dimg + h * W + wa));
-    const float3 b0 = (ha == h) ? s.v : backproject(k, (float)w, (float)ha, __ldg(dimg + ha * W + w));
-    const float dhx = a1.x - a0.x, dhy = a1.y - a0.y, dhz = a1.z - a0.z;
-    const float dvx = b1.x - b0.x, dvy = b1.y - b0.y, dvz = b1.z - b0.z;
-    const float cx = dhy * dvz - dhz * dvy;
-    const float cy = dhz * dvx - dhx * dvz;
-    const float cz = dhx * dvy - dhy * dvx;
-    const float nrm = sqrtf((cx * cx + cy * cy) + cz * cz);
-    const float den = (nrm == 0.0f) ? 1.0f : nrm;
-    s.n.x = (cx / den) * vf;
-    s.n.y = (cy / den) * vf;
-    s.n.z = (cz / den) * vf;
-  } else {
-    s.n = make_float3(0.f, 0.f, 0.f);
-  }
+  s.n = kWantNormal ? frame_normal(dimg, k, h, w, H, W, s.v, vf) : make_float3(0.f, 0.f, 0.f);
   if (pose) {
     s.gv = rigid_apply(*pose, s.v.x, s.v.y, s.v.z);
     s.gv.x *= vf; s.gv.y *= vf; s.gv.z *= vf;

@@ -149,29 +149,44 @@ __global__ void __launch_bounds__(kBlock, GSX_K2_MINB) k_project_select(ProjectA
       pix[j] = live[j] ? h * a.W + w : 0;
       n_active += live[j] ? 1u : 0u;
     }
-    // stage 2: the frame sample under each projection (vertex + normal in the world frame) and the map normal
-    float3 fv[kPts], fnm[kPts];
-    float mx[kPts], my[kPts], mz[kPts], c0[kPts];
+    // stage 2: world-frame vertex of the pixel under each projection; are_points_close (fusionutils.py:130)
+    // first: ||frame - map|| < dist_th.  Points that fail never touch the normal branch (2 more depth gathers,
+    // the cross product / normalisation, the map normal and the confidence count).
+    float3 fnm[kPts];
+    float d2[kPts], mx[kPts], my[kPts], mz[kPts], c0[kPts];
 #pragma unroll
     for (int j = 0; j < kPts; ++j) {
       if (live[j]) {
+        float3 fv;
         if (kFused) {
           const int h = pix[j] / a.W, w = pix[j] - h * a.W;
-          const FrameSample f = frame_sample<true>(dimg, s_kinv, &s_pose, h, w, a.H, a.W);
-          fv[j] = f.gv;
-          fnm[j] = f.gn;
+          const FrameSample f = frame_sample<false>(dimg, s_kinv, &s_pose, h, w, a.H, a.W);
+          fv = f.gv;
+          const float dx = fv.x - px[j], dy = fv.y - py[j], dz = fv.z - pz[j];
+          d2[j] = (dx * dx + dy * dy) + dz * dz;
+          live[j] = sqrtf(d2[j]) < a.dist_th;
+          if (live[j]) {
+            const float vf = f.d > 0.0f ? 1.0f : 0.0f;
+            const float3 n = frame_normal(dimg, s_kinv, h, w, a.H, a.W, f.v, vf);
+            fnm[j] = rotate(s_pose, n.x, n.y, n.z);
+          }
         } else {
           const float *g = gv + (int64_t)pix[j] * 3, *q = gn + (int64_t)pix[j] * 3;
-          fv[j] = make_float3(__ldg(g), __ldg(g + 1), __ldg(g + 2));
-          fnm[j] = make_float3(__ldg(q), __ldg(q + 1), __ldg(q + 2));
+          fv = make_float3(__ldg(g), __ldg(g + 1), __ldg(g + 2));
+          const float dx = fv.x - px[j], dy = fv.y - py[j], dz = fv.z - pz[j];
+          d2[j] = (dx * dx + dy * dy) + dz * dz;
+          live[j] = sqrtf(d2[j]) < a.dist_th;
+          if (live[j]) fnm[j] = make_float3(__ldg(q), __ldg(q + 1), __ldg(q + 2));
         }
-        mx[j] = __ldg(nrm + (int64_t)n[j] * 3);
-        my[j] = __ldg(nrm + (int64_t)n[j] * 3 + 1);
-        mz[j] = __ldg(nrm + (int64_t)n[j] * 3 + 2);
-        c0[j] = __ldg(cc + n[j]);
+        if (live[j]) {
+          mx[j] = __ldg(nrm + (int64_t)n[j] * 3);
+          my[j] = __ldg(nrm + (int64_t)n[j] * 3 + 1);
+          mz[j] = __ldg(nrm + (int64_t)n[j] * 3 + 2);
+          c0[j] = __ldg(cc + n[j]);
+        }
       }
     }
-    // stage 3: tests + first (optimistic) CAS of every surviving candidate; nothing is awaited here
+    // stage 3: normal test + first (optimistic) CAS of every surviving candidate; nothing is awaited here
 #pragma unroll
     for (int j = 0; j < kPts; ++j) {
       if (pend_pix[j] >= 0) {  // settle the previous iteration's CAS before re-using its slot
@@ -179,12 +194,9 @@ __global__ void __launch_bounds__(kBlock, GSX_K2_MINB) k_project_select(ProjectA
         pend_pix[j] = -1;
       }
       if (live[j]) {
-        // are_points_close (fusionutils.py:130): ||frame - map|| < dist_th
-        const float dx = fv[j].x - px[j], dy = fv[j].y - py[j], dz = fv[j].z - pz[j];
-        const float d2 = (dx * dx + dy * dy) + dz * dz;
         // are_normals_similar (fusionutils.py:187-195): n_frame . n_map > dot_th
         const float dot = (fnm[j].x * mx[j] + fnm[j].y * my[j]) + fnm[j].z * mz[j];
-        live[j] = (sqrtf(d2) < a.dist_th) && (dot > a.dot_th);
+        live[j] = dot > a.dot_th;
         if (live[j]) {
           // sort key of find_best_unique_correspondences (fusionutils.py:491-517): 1/(cc+1e-20), then the
           // squared distance (map - frame)^2 (== d2: squares are sign-independent), then n.
@@ -192,7 +204,7 @@ __global__ void __launch_bounds__(kBlock, GSX_K2_MINB) k_project_select(ProjectA
           // positive floats order like their bit patterns; flip negatives so the order stays total.
           unsigned int kb = __float_as_uint(inv_cc);
           kb = (kb & 0x80000000u) ? ~kb : (kb | 0x80000000u);
-          const unsigned int rb = __float_as_uint(d2) | 0x80000000u;  // d2 >= 0
+          const unsigned int rb = __float_as_uint(d2[j]) | 0x80000000u;  // d2 >= 0
           const unsigned long long hi = ((unsigned long long)kb << 32) | rb;
           mine[j] = U128{~(unsigned long long)n[j], ~hi};
           old[j] = cas128(best + pix[j], U128{0ull, 0ull}, mine[j]);

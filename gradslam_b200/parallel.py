@@ -13,7 +13,7 @@ import torch.distributed as dist
 
 from .structures.pointclouds import Pointclouds, _ATTRS
 
-__all__ = ["shard_batch", "gather_maps"]
+__all__ = ["shard_batch", "gather_maps", "gather_maps_begin", "gather_maps_end", "comm_stream"]
 
 
 def shard_batch(total: int, rank: Optional[int] = None, world: Optional[int] = None):
@@ -25,34 +25,110 @@ def shard_batch(total: int, rank: Optional[int] = None, world: Optional[int] = N
     return lo, lo + base + (1 if rank < extra else 0)
 
 
-def gather_maps(pointclouds: Pointclouds, group=None) -> Pointclouds:
-    """All-gathers the maps of every rank (equal local batch size).  Returns a Pointclouds with world*B maps,
-    ordered by rank.  Works on NCCL (CUDA tensors) and on gloo (CPU tensors, used by the CPU tests)."""
-    world = dist.get_world_size(group)
-    if world == 1:
-        return pointclouds
+_COMM_STREAMS = {}
+
+
+def _comm_stream(device):
+    if device.type != "cuda":
+        return None
+    key = str(device)
+    if key not in _COMM_STREAMS:
+        _COMM_STREAMS[key] = torch.cuda.Stream(device=device)
+    return _COMM_STREAMS[key]
+
+
+class _GatherHandle:
+    __slots__ = ("pc", "group", "world", "counts_host", "ready", "stream")
+
+
+def gather_maps_begin(pointclouds: Pointclouds, group=None) -> "_GatherHandle":
+    """First half of the map all-gather: exchanges the per-sequence sizes on a side (communication) stream and
+    starts their copy to pinned host memory.  Does NOT block the host, so the caller can enqueue the next batch of
+    sequences before calling `gather_maps_end` — the exchange then overlaps that compute."""
+    h = _GatherHandle()
+    h.pc, h.group, h.world = pointclouds, group, dist.get_world_size(group)
     dev = pointclouds.device
     B = len(pointclouds)
-    local = pointclouds._counts_dev[pointclouds._cur].to(torch.int64)
-    all_counts = torch.empty(world * B, dtype=torch.int64, device=dev)
-    _all_gather(all_counts, local.contiguous(), group)
-    counts = [int(c) for c in all_counts.tolist()]  # the one host sync of the whole job
+    h.stream = _comm_stream(dev)
+    local = pointclouds._counts_dev[pointclouds._cur]
+    if h.stream is not None:
+        h.stream.wait_stream(torch.cuda.current_stream(dev))
+        ctx = torch.cuda.stream(h.stream)
+    else:
+        import contextlib
+
+        ctx = contextlib.nullcontext()
+    with ctx:
+        all_counts = torch.empty(h.world * B, dtype=torch.int64, device=dev)
+        _all_gather(all_counts, local.to(torch.int64).contiguous(), group)
+        if h.stream is not None:
+            h.counts_host = torch.empty(h.world * B, dtype=torch.int64, pin_memory=True)
+            h.counts_host.copy_(all_counts, non_blocking=True)
+            h.ready = torch.cuda.Event()
+            h.ready.record(h.stream)
+            for st in pointclouds._store.values():
+                if st is not None:
+                    st.record_stream(h.stream)
+            local.record_stream(h.stream)
+            all_counts.record_stream(h.stream)
+        else:
+            h.counts_host, h.ready = all_counts, None
+    return h
+
+
+def gather_maps_end(h: "_GatherHandle", wait: bool = True) -> Pointclouds:
+    """Second half: waits (host) for the sizes only, then enqueues the variable-length all-gather of the four map
+    attributes on the communication stream.  With wait=True the caller's current stream is made to wait for the
+    result; with wait=False the caller must synchronise with `parallel.comm_stream(device)` before using it."""
+    pc, group, world = h.pc, h.group, h.world
+    dev = pc.device
+    B = len(pc)
+    if h.ready is not None:
+        h.ready.synchronize()
+    counts = [int(c) for c in h.counts_host.tolist()]
     nmax = max(max(counts), 1)
-    pointclouds._counts_host = counts[dist.get_rank(group) * B: (dist.get_rank(group) + 1) * B]
-    pointclouds.reserve(nmax)
-    pointclouds._zero_rows_upto(nmax)
+    rank = dist.get_rank(group)
+    pc._counts_host = counts[rank * B: (rank + 1) * B]
     out = Pointclouds(device=dev)
     out._B = world * B
-    for key in _ATTRS:
-        st = pointclouds._store[key]
-        if st is None:
-            continue
-        send = st[:, :nmax].contiguous()
-        recv = torch.empty((world * B, nmax, st.shape[2]), dtype=st.dtype, device=dev)
-        _all_gather(recv, send, group)
-        out._store[key] = recv
-    out._set_counts(counts)
+    if h.stream is not None:
+        ctx = torch.cuda.stream(h.stream)
+    else:
+        import contextlib
+
+        ctx = contextlib.nullcontext()
+    with ctx:
+        pc.reserve(nmax)
+        pc._zero_rows_upto(nmax)
+        for key in _ATTRS:
+            st = pc._store[key]
+            if st is None:
+                continue
+            send = st[:, :nmax].contiguous()
+            recv = torch.empty((world * B, nmax, st.shape[2]), dtype=st.dtype, device=dev)
+            _all_gather(recv, send, group)
+            out._store[key] = recv
+            if h.stream is not None:
+                send.record_stream(h.stream)
+                recv.record_stream(torch.cuda.current_stream(dev))
+        out._set_counts(counts)
+    if h.stream is not None and wait:
+        torch.cuda.current_stream(dev).wait_stream(h.stream)
     return out
+
+
+def comm_stream(device):
+    """The side stream the map all-gathers run on (None on CPU)."""
+    return _comm_stream(torch.device(device))
+
+
+def gather_maps(pointclouds: Pointclouds, group=None) -> Pointclouds:
+    """All-gathers the maps of every rank (equal local batch size).  Returns a Pointclouds with world*B maps,
+    ordered by rank.  Works on NCCL (CUDA tensors) and on gloo (CPU tensors, used by the CPU tests).
+    Blocking convenience wrapper around gather_maps_begin / gather_maps_end."""
+    if dist.get_world_size(group) == 1:
+        return pointclouds
+    return gather_maps_end(gather_maps_begin(pointclouds, group), wait=True)
 
 
 def _all_gather(recv, send, group):
