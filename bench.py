@@ -20,6 +20,7 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # NCCL's version banner must not land on stdout (ONE JSON line)
 
 METRIC = "PointFusion frames/sec (640x480, B=8)"
 UNIT = "frames/s"
@@ -183,7 +184,6 @@ def main():
 
     import gradslam_b200 as gs
     from gradslam_b200 import parallel, profiling
-    from gradslam_b200.parallel import gather_maps
     from gradslam_b200.synthetic import make_sequence
 
     assert torch.cuda.is_available(), "bench.py (impl gsx) needs a GPU; there is no CPU fallback"
@@ -201,26 +201,17 @@ def main():
     frames_host = gs.RGBDImages(rgb_h, depth_h, K_h, poses_h)
     slam = gs.PointFusion(odom="gt", device=dev)
 
-    def step(frames):
-        """Un-pipelined step (warm-up): fuse the batch, then all-gather the fused maps of every rank."""
-        pc, poses = slam(frames)
-        if world > 1:
-            pc = gather_maps(pc)
-        return pc, poses
-
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize(dev)
 
-    def timed(frames, steps, d2h):
-        barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
+    def run_steps(frames, steps, d2h):
+        """`steps` whole-batch PointFusion calls.  N>1: the final-map all-gather of step k (NCCL, communication
+        stream) overlaps the fusion of step k+1; the last gather is awaited before returning."""
         res = None
         pending = None  # (gather handle, poses) of the previous step
         for _ in range(steps):
-            # N>1: the final-map all-gather of step k (NCCL, side stream) overlaps the fusion of step k+1
             pc, poses = slam(frames)
             if pending is not None:  # step k-1's maps travel while step k (just enqueued) computes
                 pc_done, poses_done = parallel.gather_maps_end(pending[0], wait=False), pending[1]
@@ -234,6 +225,13 @@ def main():
             pc_done = parallel.gather_maps_end(pending[0], wait=True)
             if d2h:
                 res = (pending[1].cpu(), pc_done.num_points_per_pointcloud.cpu())
+        return res
+
+    def timed(frames, steps, d2h):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        res = run_steps(frames, steps, d2h)
         e1.record()
         torch.cuda.synchronize(dev)
         ms = e0.elapsed_time(e1)
@@ -244,15 +242,13 @@ def main():
         barrier()
         return ms, res
 
-    for _ in range(max(args.warmup, 3)):
-        step(frames_dev)
+    run_steps(frames_dev, max(args.warmup, 3), d2h=False)  # same (pipelined) code path as the timed region
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
     ms_dev, _ = timed(frames_dev, args.steps, d2h=False)
     clocks = sampler.stop() if rank == 0 else None
-    for _ in range(2):
-        step(frames_host)
+    run_steps(frames_host, 3, d2h=True)
     ms_e2e, res = timed(frames_host, args.steps, d2h=True)
 
     frames_per_step = B * L * world
