@@ -191,7 +191,19 @@ def main():
     dev = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=dev)
+        # NCCL prints its version banner on stdout when the communicator is created; stdout must carry exactly
+        # one JSON line, so point fd 1 at stderr until the first collective has gone through.
+        sys.stdout.flush()
+        saved_stdout = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=dev)
+            dist.barrier()
+            torch.cuda.synchronize(dev)
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_stdout, 1)
+            os.close(saved_stdout)
 
     B, L, H, W = args.batch, args.seqlen, args.height, args.width
     rgb_h, depth_h, K_h, poses_h = make_sequence(B, L, H, W, seed=rank, pin_memory=True)

@@ -78,14 +78,32 @@ struct ProjectArgs {
   unsigned long long *stats;
 };
 
-#ifndef GSX_KPTS
-#define GSX_KPTS 1
-#endif
-constexpr int kPts = GSX_KPTS;  // map points per thread (independent chains -> 4x memory-level parallelism)
-
 #ifndef GSX_K2_MINB
-#define GSX_K2_MINB 5
+#define GSX_K2_MINB 4
 #endif
+
+struct MapPoint {  // everything K2 needs from one map row
+  float px, py, pz, mx, my, mz, cc;
+};
+__device__ __forceinline__ MapPoint load_map_point(const float *pts, const float *nrm, const float *cc, int64_t n) {
+  MapPoint m;
+  m.px = __ldg(pts + n * 3);
+  m.py = __ldg(pts + n * 3 + 1);
+  m.pz = __ldg(pts + n * 3 + 2);
+  m.mx = __ldg(nrm + n * 3);
+  m.my = __ldg(nrm + n * 3 + 1);
+  m.mz = __ldg(nrm + n * 3 + 2);
+  m.cc = __ldg(cc + n);
+  return m;
+}
+
+// The kernel is bound by (threads in flight) / (length of the dependent memory chain), not by bytes: ncu shows
+// ~50 % issue utilisation and ~1.5 TB/s of DRAM traffic.  So the chain is kept as short as possible:
+//   * the map row of the NEXT grid-stride iteration (position, normal, confidence) is fetched while the current
+//     point is processed (software pipelining) - normal / confidence are read for every point, also the ~35 %
+//     outside the frustum, which costs bytes but removes a round trip;
+//   * the depth values under the projection (centre, right, below) are requested together;
+//   * the result of the 128-bit CAS is only looked at one iteration later.
 template <bool kFused>
 __global__ void __launch_bounds__(kBlock, GSX_K2_MINB) k_project_select(ProjectArgs a) {
   __shared__ Rigid s_pose, s_tinv;
@@ -93,8 +111,7 @@ __global__ void __launch_bounds__(kBlock, GSX_K2_MINB) k_project_select(ProjectA
   __shared__ KInv s_kinv;
   const int b = blockIdx.y;
   const int count = a.counts[b];
-  const int chunk = kBlock * kPts;
-  if ((int64_t)blockIdx.x * chunk >= count) return;
+  if ((int64_t)blockIdx.x * kBlock >= count) return;
   if (threadIdx.x == 0) {
     s_pose = load_rigid(a.poses + b * a.pose_bstride);
     s_tinv = rigid_inverse(s_pose);
@@ -111,111 +128,68 @@ __global__ void __launch_bounds__(kBlock, GSX_K2_MINB) k_project_select(ProjectA
   const float *dimg = a.depth + b * a.depth_bstride;
   U128 *best = a.best + (int64_t)b * P;
   unsigned int n_active = 0;
-  // CAS results are consumed one iteration late, so the ~L2 round trip of the atomic overlaps the next points
-  U128 mine[kPts], old[kPts];
-  int pend_pix[kPts];
-#pragma unroll
-  for (int j = 0; j < kPts; ++j) pend_pix[j] = -1;
-  for (int64_t base = (int64_t)blockIdx.x * chunk; base < count; base += (int64_t)gridDim.x * chunk) {
-    int n[kPts], pix[kPts];
-    float px[kPts], py[kPts], pz[kPts];
-    bool live[kPts];
-    // stage 1: positions (independent coalesced loads), projection, frustum test
-#pragma unroll
-    for (int j = 0; j < kPts; ++j) {
-      n[j] = (int)(base + j * kBlock + threadIdx.x);
-      live[j] = n[j] < count;
-      const int nn = live[j] ? n[j] : 0;
-      px[j] = __ldg(pts + (int64_t)nn * 3);
-      py[j] = __ldg(pts + (int64_t)nn * 3 + 1);
-      pz[j] = __ldg(pts + (int64_t)nn * 3 + 2);
-    }
-#pragma unroll
-    for (int j = 0; j < kPts; ++j) {
-      // world -> camera (pointclouds.py:526-573), then pinhole projection with the 4x4 K on the homogeneous
-      // point (projutils.py:92-238): z == 0 divides by 1.
-      const float3 q = rigid_apply(s_tinv, px[j], py[j], pz[j]);
-      const float hx = ((s_k[0] * q.x + s_k[1] * q.y) + s_k[2] * q.z) + s_k[3];
-      const float hy = ((s_k[4] * q.x + s_k[5] * q.y) + s_k[6] * q.z) + s_k[7];
-      const float hz = ((s_k[8] * q.x + s_k[9] * q.y) + s_k[10] * q.z) + s_k[11];
-      const float den = (hz != 0.0f) ? hz : 1.0f;
-      const float u = hx / den, v = hy / den;
-      // fusionutils.py:259-266
-      live[j] = live[j] && (u > -1e-3f) && (u < a.u_hi) && (v > -1e-3f) && (v < a.v_hi) && (q.z > 0.0f);
+  const int64_t stride = (int64_t)gridDim.x * kBlock;
+  int64_t n = (int64_t)blockIdx.x * kBlock + threadIdx.x;
+  U128 mine{0ull, 0ull}, old{0ull, 0ull};
+  int pend_pix = -1;
+  MapPoint cur = load_map_point(pts, nrm, cc, n < count ? n : 0);
+  for (; n < count; n += stride) {
+    const MapPoint m = cur;
+    const int64_t nn = n + stride;
+    if (nn < count) cur = load_map_point(pts, nrm, cc, nn);  // in flight while this point is processed
+    // world -> camera (pointclouds.py:526-573), then pinhole projection with the 4x4 K on the homogeneous
+    // point (projutils.py:92-238): z == 0 divides by 1.
+    const float3 q = rigid_apply(s_tinv, m.px, m.py, m.pz);
+    const float hx = ((s_k[0] * q.x + s_k[1] * q.y) + s_k[2] * q.z) + s_k[3];
+    const float hy = ((s_k[4] * q.x + s_k[5] * q.y) + s_k[6] * q.z) + s_k[7];
+    const float hz = ((s_k[8] * q.x + s_k[9] * q.y) + s_k[10] * q.z) + s_k[11];
+    const float den = (hz != 0.0f) ? hz : 1.0f;
+    const float u = hx / den, v = hy / den;
+    // fusionutils.py:259-266
+    bool live = (u > -1e-3f) && (u < a.u_hi) && (v > -1e-3f) && (v < a.v_hi) && (q.z > 0.0f);
+    if (live) {
+      ++n_active;
       // round-half-even like torch.round, then clamp (fusionutils.py:267-274)
       int w = (int)rintf(u), h = (int)rintf(v);
       w = min(max(w, 0), a.W - 1);
       h = min(max(h, 0), a.H - 1);
-      pix[j] = live[j] ? h * a.W + w : 0;
-      n_active += live[j] ? 1u : 0u;
-    }
-    // stage 2: world-frame vertex of the pixel under each projection; are_points_close (fusionutils.py:130)
-    // first: ||frame - map|| < dist_th.  Points that fail never touch the normal branch (2 more depth gathers,
-    // the cross product / normalisation, the map normal and the confidence count).
-    float3 fnm[kPts];
-    float d2[kPts], mx[kPts], my[kPts], mz[kPts], c0[kPts];
-#pragma unroll
-    for (int j = 0; j < kPts; ++j) {
-      if (live[j]) {
-        float3 fv;
-        if (kFused) {
-          const int h = pix[j] / a.W, w = pix[j] - h * a.W;
-          const FrameSample f = frame_sample<false>(dimg, s_kinv, &s_pose, h, w, a.H, a.W);
-          fv = f.gv;
-          const float dx = fv.x - px[j], dy = fv.y - py[j], dz = fv.z - pz[j];
-          d2[j] = (dx * dx + dy * dy) + dz * dz;
-          live[j] = sqrtf(d2[j]) < a.dist_th;
-          if (live[j]) {
-            const float vf = f.d > 0.0f ? 1.0f : 0.0f;
-            const float3 n = frame_normal(dimg, s_kinv, h, w, a.H, a.W, f.v, vf);
-            fnm[j] = rotate(s_pose, n.x, n.y, n.z);
-          }
-        } else {
-          const float *g = gv + (int64_t)pix[j] * 3, *q = gn + (int64_t)pix[j] * 3;
-          fv = make_float3(__ldg(g), __ldg(g + 1), __ldg(g + 2));
-          const float dx = fv.x - px[j], dy = fv.y - py[j], dz = fv.z - pz[j];
-          d2[j] = (dx * dx + dy * dy) + dz * dz;
-          live[j] = sqrtf(d2[j]) < a.dist_th;
-          if (live[j]) fnm[j] = make_float3(__ldg(q), __ldg(q + 1), __ldg(q + 2));
-        }
-        if (live[j]) {
-          mx[j] = __ldg(nrm + (int64_t)n[j] * 3);
-          my[j] = __ldg(nrm + (int64_t)n[j] * 3 + 1);
-          mz[j] = __ldg(nrm + (int64_t)n[j] * 3 + 2);
-          c0[j] = __ldg(cc + n[j]);
-        }
+      const int pix = h * a.W + w;
+      float3 fv, fnm;
+      if (kFused) {
+        const FrameSample f = frame_sample<true>(dimg, s_kinv, &s_pose, h, w, a.H, a.W);
+        fv = f.gv;
+        fnm = f.gn;
+      } else {
+        const float *g = gv + (int64_t)pix * 3, *t = gn + (int64_t)pix * 3;
+        fv = make_float3(__ldg(g), __ldg(g + 1), __ldg(g + 2));
+        fnm = make_float3(__ldg(t), __ldg(t + 1), __ldg(t + 2));
       }
-    }
-    // stage 3: normal test + first (optimistic) CAS of every surviving candidate; nothing is awaited here
-#pragma unroll
-    for (int j = 0; j < kPts; ++j) {
-      if (pend_pix[j] >= 0) {  // settle the previous iteration's CAS before re-using its slot
-        atomic_max_rec128_finish(best + pend_pix[j], mine[j], old[j]);
-        pend_pix[j] = -1;
+      // are_points_close (fusionutils.py:130): ||frame - map|| < dist_th
+      const float dx = fv.x - m.px, dy = fv.y - m.py, dz = fv.z - m.pz;
+      const float d2 = (dx * dx + dy * dy) + dz * dz;
+      // are_normals_similar (fusionutils.py:187-195): n_frame . n_map > dot_th
+      const float dot = (fnm.x * m.mx + fnm.y * m.my) + fnm.z * m.mz;
+      live = (sqrtf(d2) < a.dist_th) && (dot > a.dot_th);
+      if (pend_pix >= 0) {  // settle the previous candidate's CAS before re-using the slot
+        atomic_max_rec128_finish(best + pend_pix, mine, old);
+        pend_pix = -1;
       }
-      if (live[j]) {
-        // are_normals_similar (fusionutils.py:187-195): n_frame . n_map > dot_th
-        const float dot = (fnm[j].x * mx[j] + fnm[j].y * my[j]) + fnm[j].z * mz[j];
-        live[j] = dot > a.dot_th;
-        if (live[j]) {
-          // sort key of find_best_unique_correspondences (fusionutils.py:491-517): 1/(cc+1e-20), then the
-          // squared distance (map - frame)^2 (== d2: squares are sign-independent), then n.
-          const float inv_cc = 1.0f / (c0[j] + 1e-20f);
-          // positive floats order like their bit patterns; flip negatives so the order stays total.
-          unsigned int kb = __float_as_uint(inv_cc);
-          kb = (kb & 0x80000000u) ? ~kb : (kb | 0x80000000u);
-          const unsigned int rb = __float_as_uint(d2[j]) | 0x80000000u;  // d2 >= 0
-          const unsigned long long hi = ((unsigned long long)kb << 32) | rb;
-          mine[j] = U128{~(unsigned long long)n[j], ~hi};
-          old[j] = cas128(best + pix[j], U128{0ull, 0ull}, mine[j]);
-          pend_pix[j] = pix[j];
-        }
+      if (live) {
+        // sort key of find_best_unique_correspondences (fusionutils.py:491-517): 1/(cc+1e-20), then the squared
+        // distance (map - frame)^2 (== d2: squares are sign-independent), then n.
+        const float inv_cc = 1.0f / (m.cc + 1e-20f);
+        // positive floats order like their bit patterns; flip negatives so the order stays total.
+        unsigned int kb = __float_as_uint(inv_cc);
+        kb = (kb & 0x80000000u) ? ~kb : (kb | 0x80000000u);
+        const unsigned int rb = __float_as_uint(d2) | 0x80000000u;  // d2 >= 0
+        const unsigned long long hi = ((unsigned long long)kb << 32) | rb;
+        mine = U128{~(unsigned long long)n, ~hi};
+        old = cas128(best + pix, U128{0ull, 0ull}, mine);  // optimistic: most pixels see a single candidate
+        pend_pix = pix;
       }
     }
   }
-#pragma unroll
-  for (int j = 0; j < kPts; ++j)
-    if (pend_pix[j] >= 0) atomic_max_rec128_finish(best + pend_pix[j], mine[j], old[j]);
+  if (pend_pix >= 0) atomic_max_rec128_finish(best + pend_pix, mine, old);
   // bookkeeping for the roofline's algorithmic-byte count: one atomic per warp
   n_active = __reduce_add_sync(0xffffffffu, n_active);
   if ((threadIdx.x & 31) == 0 && n_active) atomicAdd(a.stats + 2 * b, (unsigned long long)n_active);
@@ -291,7 +265,78 @@ __device__ __forceinline__ unsigned int lookback_warp(const unsigned long long *
 #ifndef GSX_K4_MINB
 #define GSX_K4_MINB 4
 #endif
+#ifndef GSX_K4_SPLIT
+#define GSX_K4_SPLIT 0  // 1: k_merge_only (no barriers) then k_merge_append<.., false> (append + scan only); measured slower
+#endif
+#ifndef GSX_K4A_MINB
+#define GSX_K4A_MINB 4
+#endif
+
+// K4a: confidence-weighted merge of every matched pixel into its map row.  One thread per pixel, no barriers, no
+// ordering: exactly one pixel owns a map row.  The records are left in place for the append pass.
 template <bool kFused>
+__global__ void __launch_bounds__(kBlock, GSX_K4A_MINB) k_merge_only(MergeArgs a) {
+  __shared__ Rigid s_pose;
+  __shared__ KInv s_k;
+  const int b = blockIdx.y;
+  if (threadIdx.x == 32) s_k = load_kinv(a.K + b * a.K_bstride);
+  if (kFused && threadIdx.x == 64) s_pose = load_rigid(a.poses + b * a.pose_bstride);
+  __syncthreads();
+  const int P = a.H * a.W;
+  const int pix = blockIdx.x * kBlock + threadIdx.x;
+  if (pix >= P) return;
+  const U128 rec = a.ws.best[(int64_t)b * P + pix];
+  if ((rec.lo | rec.hi) == 0ull) return;
+  const int64_t n = (int64_t)(~rec.lo);
+  float *pts = a.pts + ((int64_t)b * a.cap + n) * 3;
+  float *nrm = a.nrm + ((int64_t)b * a.cap + n) * 3;
+  float *col = a.col + ((int64_t)b * a.cap + n) * 3;
+  float *cc = a.cc + (int64_t)b * a.cap + n;
+  // the map row and the frame sample are independent: all loads go out together
+  float mp[10];
+#pragma unroll
+  for (int q = 0; q < 3; ++q) {
+    mp[q] = pts[q];
+    mp[3 + q] = nrm[q];
+    mp[6 + q] = col[q];
+  }
+  mp[9] = *cc;
+  const float *c = a.rgb + b * a.rgb_bstride + (int64_t)pix * 3;
+  const float3 fc = make_float3(__ldg(c), __ldg(c + 1), __ldg(c + 2));
+  const int h = pix / a.W, w = pix - h * a.W;
+  const float *depth = a.depth + b * a.depth_bstride;
+  float3 fp, fn, v;
+  if (kFused) {
+    const FrameSample f = frame_sample<true>(depth, s_k, &s_pose, h, w, a.H, a.W);
+    fp = f.gv;
+    fn = f.gn;
+    v = f.v;
+  } else {
+    const float *g = a.gv + ((int64_t)b * P + pix) * 3, *t = a.gn + ((int64_t)b * P + pix) * 3;
+    fp = make_float3(__ldg(g), __ldg(g + 1), __ldg(g + 2));
+    fn = make_float3(__ldg(t), __ldg(t + 1), __ldg(t + 2));
+    v = backproject(s_k, (float)w, (float)h, __ldg(depth + pix));
+  }
+  // alpha from the LOCAL vertex (fusionutils.py:657, 69-72)
+  const float sq = (v.x * v.x + v.y * v.y) + v.z * v.z;
+  const float alpha = fminf(fmaxf(expf((-sq) / a.two_sigma_sq), 1e-7f), 1.01f);
+  // confidence-weighted running mean (fusionutils.py:678-699)
+  const float c0 = mp[9];
+  const float tot = c0 + alpha;
+  const float inv = 1.0f / ((tot == 0.0f) ? 1.0f : tot);
+  pts[0] = ((c0 * mp[0]) + (alpha * fp.x)) * inv;
+  pts[1] = ((c0 * mp[1]) + (alpha * fp.y)) * inv;
+  pts[2] = ((c0 * mp[2]) + (alpha * fp.z)) * inv;
+  nrm[0] = ((c0 * mp[3]) + (alpha * fn.x)) * inv;
+  nrm[1] = ((c0 * mp[4]) + (alpha * fn.y)) * inv;
+  nrm[2] = ((c0 * mp[5]) + (alpha * fn.z)) * inv;
+  col[0] = ((c0 * mp[6]) + (alpha * fc.x)) * inv;
+  col[1] = ((c0 * mp[7]) + (alpha * fc.y)) * inv;
+  col[2] = ((c0 * mp[8]) + (alpha * fc.z)) * inv;
+  *cc = tot;
+}
+
+template <bool kFused, bool kDoMerge>
 __global__ void __launch_bounds__(kBlock, GSX_K4_MINB) k_merge_append(MergeArgs a) {
   __shared__ Rigid s_pose;
   __shared__ int s_tile;
@@ -376,7 +421,7 @@ __global__ void __launch_bounds__(kBlock, GSX_K4_MINB) k_merge_append(MergeArgs 
   float3 fp[kPix], fn[kPix], fc[kPix];
 #pragma unroll
   for (int j = 0; j < kPix; ++j) {
-    if (matched[j] || is_new[j]) {
+    if ((kDoMerge && matched[j]) || is_new[j]) {
       const float *c = rgb + (int64_t)pix[j] * 3;
       fc[j] = make_float3(__ldg(c), __ldg(c + 1), __ldg(c + 2));
       if (kFused) {
@@ -403,7 +448,7 @@ __global__ void __launch_bounds__(kBlock, GSX_K4_MINB) k_merge_append(MergeArgs 
   float mp[kPix][10];
 #pragma unroll
   for (int j = 0; j < kPix; ++j) {
-    if (matched[j] && cc) {
+    if (kDoMerge && matched[j] && cc) {
       const int64_t n = (int64_t)(~rec[j].lo);
 #pragma unroll
       for (int q = 0; q < 3; ++q) {
@@ -416,7 +461,7 @@ __global__ void __launch_bounds__(kBlock, GSX_K4_MINB) k_merge_append(MergeArgs 
   }
 #pragma unroll
   for (int j = 0; j < kPix; ++j) {
-    if (matched[j] && cc) {
+    if (kDoMerge && matched[j] && cc) {
       // confidence-weighted running mean (fusionutils.py:678-699); exactly one pixel owns this map row
       const int64_t n = (int64_t)(~rec[j].lo);
       const float c0 = mp[j][9];
@@ -468,9 +513,12 @@ __global__ void __launch_bounds__(kBlock, GSX_K4_MINB) k_merge_append(MergeArgs 
 
 int launch_project_select(const ProjectArgs &a, int64_t max_count, cudaStream_t stream) {
   if (a.B == 0 || max_count <= 0) return 0;
-  const int64_t chunk = (int64_t)kBlock * kPts;
+  const int64_t chunk = (int64_t)kBlock;
   int64_t bx = (max_count + chunk - 1) / chunk;
-  const int64_t cap_blocks = (int64_t)kNumSMs * 16;  // grid-stride beyond 16 CTAs per SM
+#ifndef GSX_K2_CTAS_PER_SM
+#define GSX_K2_CTAS_PER_SM 16
+#endif
+  const int64_t cap_blocks = (int64_t)kNumSMs * GSX_K2_CTAS_PER_SM;  // grid-stride beyond this many CTAs per SM
   if (bx * a.B > cap_blocks) bx = (cap_blocks + a.B - 1) / a.B;
   if (bx < 1) bx = 1;
   if (a.gv)
@@ -483,10 +531,19 @@ int launch_project_select(const ProjectArgs &a, int64_t max_count, cudaStream_t 
 
 int launch_merge_append(const MergeArgs &a, cudaStream_t stream) {
   if (a.B == 0) return 0;
-  if (a.gv)
-    k_merge_append<false><<<dim3((unsigned)(a.ws.tiles * a.B)), kBlock, 0, stream>>>(a);
-  else
-    k_merge_append<true><<<dim3((unsigned)(a.ws.tiles * a.B)), kBlock, 0, stream>>>(a);
+  const dim3 grid((unsigned)(a.ws.tiles * a.B));
+#if GSX_K4_SPLIT
+  if (a.cc) {  // maps without confidence counts are never merged (aggregation only)
+    const dim3 mgrid((unsigned)(((int64_t)a.H * a.W + kBlock - 1) / kBlock), (unsigned)a.B);
+    if (a.gv) k_merge_only<false><<<mgrid, kBlock, 0, stream>>>(a);
+    else k_merge_only<true><<<mgrid, kBlock, 0, stream>>>(a);
+  }
+  if (a.gv) k_merge_append<false, false><<<grid, kBlock, 0, stream>>>(a);
+  else k_merge_append<true, false><<<grid, kBlock, 0, stream>>>(a);
+#else
+  if (a.gv) k_merge_append<false, true><<<grid, kBlock, 0, stream>>>(a);
+  else k_merge_append<true, true><<<grid, kBlock, 0, stream>>>(a);
+#endif
   GSX_CHECK_LAUNCH("gsx_fusion_merge_append");
   return 0;
 }
