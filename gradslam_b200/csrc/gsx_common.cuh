@@ -131,6 +131,54 @@ __device__ __forceinline__ float3 frame_normal(const float *__restrict__ dimg, c
   return make_float3((cx / den) * vf, (cy / den) * vf, (cz / den) * vf);
 }
 
+// The five depth values the sample of pixel (h,w) depends on: centre, the two ends of its horizontal difference
+// (w_a, w_a+1) and of its vertical difference (h_a, h_a+1), where w_a = min(w, W-2), h_a = min(h, H-2).
+struct DepthStencil {
+  float c, l, r, u, d;
+};
+__device__ __forceinline__ DepthStencil load_stencil(const float *__restrict__ dimg, int h, int w, int H, int W) {
+  const int wa = (w < W - 1) ? w : w - 1;
+  const int ha = (h < H - 1) ? h : h - 1;
+  DepthStencil s;
+  s.c = __ldg(dimg + h * W + w);
+  s.l = __ldg(dimg + h * W + wa);
+  s.r = __ldg(dimg + h * W + wa + 1);
+  s.u = __ldg(dimg + ha * W + w);
+  s.d = __ldg(dimg + (ha + 1) * W + w);
+  return s;
+}
+// frame_sample<true> evaluated from an already loaded stencil (bit-identical arithmetic)
+__device__ __forceinline__ FrameSample frame_sample_from(const DepthStencil &t, const KInv &k, const Rigid *pose, int h,
+                                                         int w, int H, int W) {
+  FrameSample s;
+  const int wa = (w < W - 1) ? w : w - 1;
+  const int ha = (h < H - 1) ? h : h - 1;
+  s.d = t.c;
+  const float vf = t.c > 0.0f ? 1.0f : 0.0f;
+  s.v = backproject(k, (float)w, (float)h, t.c);
+  const float3 a1 = backproject(k, (float)(wa + 1), (float)h, t.r);
+  const float3 b1 = backproject(k, (float)w, (float)(ha + 1), t.d);
+  const float3 a0 = (wa == w) ? s.v : backproject(k, (float)wa, (float)h, t.l);
+  const float3 b0 = (ha == h) ? s.v : backproject(k, (float)w, (float)ha, t.u);
+  const float dhx = a1.x - a0.x, dhy = a1.y - a0.y, dhz = a1.z - a0.z;
+  const float dvx = b1.x - b0.x, dvy = b1.y - b0.y, dvz = b1.z - b0.z;
+  const float cx = dhy * dvz - dhz * dvy;
+  const float cy = dhz * dvx - dhx * dvz;
+  const float cz = dhx * dvy - dhy * dvx;
+  const float nrm = sqrtf((cx * cx + cy * cy) + cz * cz);
+  const float den = (nrm == 0.0f) ? 1.0f : nrm;
+  s.n = make_float3((cx / den) * vf, (cy / den) * vf, (cz / den) * vf);
+  if (pose) {
+    s.gv = rigid_apply(*pose, s.v.x, s.v.y, s.v.z);
+    s.gv.x *= vf; s.gv.y *= vf; s.gv.z *= vf;
+    s.gn = rotate(*pose, s.n.x, s.n.y, s.n.z);
+  } else {
+    s.gv = s.v;
+    s.gn = s.n;
+  }
+  return s;
+}
+
 template <bool kWantNormal>
 __device__ __forceinline__ FrameSample frame_sample(const float *__restrict__ dimg, const KInv &k, const Rigid *pose,
                                                     int h, int w, int H, int W) {

@@ -81,6 +81,9 @@ struct ProjectArgs {
 #ifndef GSX_K2_MINB
 #define GSX_K2_MINB 4
 #endif
+#ifndef GSX_K2_DEEP
+#define GSX_K2_DEEP 0  // 1: two-stage software pipeline (depth stencil loads one iteration ahead); measured slower
+#endif
 
 struct MapPoint {  // everything K2 needs from one map row
   float px, py, pz, mx, my, mz, cc;
@@ -132,6 +135,70 @@ __global__ void __launch_bounds__(kBlock, GSX_K2_MINB) k_project_select(ProjectA
   int64_t n = (int64_t)blockIdx.x * kBlock + threadIdx.x;
   U128 mine{0ull, 0ull}, old{0ull, 0ull};
   int pend_pix = -1;
+#if GSX_K2_DEEP
+  // Two-stage software pipeline over the grid-stride loop (fused path):
+  //   iteration k:  fetch row k+1  |  stage A(k): project, frustum test, issue the depth stencil loads
+  //                                |  stage B(k-1): frame sample from the stencil loaded last iteration, tests, CAS
+  if (kFused) {
+    MapPoint row_next = load_map_point(pts, nrm, cc, n < count ? n : 0);
+    MapPoint mb{};  // stage-B item
+    DepthStencil tb{};
+    int hb = 0, wb = 0;
+    int64_t nb = -1;
+    for (;; n += stride) {
+      const bool have_a = n < count;
+      MapPoint ma{};
+      DepthStencil ta{};
+      int ha_ = 0, wa_ = 0;
+      bool live_a = false;
+      if (have_a) {
+        ma = row_next;
+        if (n + stride < count) row_next = load_map_point(pts, nrm, cc, n + stride);
+        const float3 q = rigid_apply(s_tinv, ma.px, ma.py, ma.pz);
+        const float hx = ((s_k[0] * q.x + s_k[1] * q.y) + s_k[2] * q.z) + s_k[3];
+        const float hy = ((s_k[4] * q.x + s_k[5] * q.y) + s_k[6] * q.z) + s_k[7];
+        const float hz = ((s_k[8] * q.x + s_k[9] * q.y) + s_k[10] * q.z) + s_k[11];
+        const float den = (hz != 0.0f) ? hz : 1.0f;
+        const float u = hx / den, v = hy / den;
+        live_a = (u > -1e-3f) && (u < a.u_hi) && (v > -1e-3f) && (v < a.v_hi) && (q.z > 0.0f);
+        if (live_a) {
+          ++n_active;
+          wa_ = min(max((int)rintf(u), 0), a.W - 1);
+          ha_ = min(max((int)rintf(v), 0), a.H - 1);
+          ta = load_stencil(dimg, ha_, wa_, a.H, a.W);  // consumed next iteration
+        }
+      }
+      if (nb >= 0) {  // stage B for the previous item
+        const FrameSample f = frame_sample_from(tb, s_kinv, &s_pose, hb, wb, a.H, a.W);
+        const float dx = f.gv.x - mb.px, dy = f.gv.y - mb.py, dz = f.gv.z - mb.pz;
+        const float d2 = (dx * dx + dy * dy) + dz * dz;
+        const float dot = (f.gn.x * mb.mx + f.gn.y * mb.my) + f.gn.z * mb.mz;
+        if (pend_pix >= 0) {
+          atomic_max_rec128_finish(best + pend_pix, mine, old);
+          pend_pix = -1;
+        }
+        if ((sqrtf(d2) < a.dist_th) && (dot > a.dot_th)) {
+          const float inv_cc = 1.0f / (mb.cc + 1e-20f);
+          unsigned int kb = __float_as_uint(inv_cc);
+          kb = (kb & 0x80000000u) ? ~kb : (kb | 0x80000000u);
+          const unsigned int rb = __float_as_uint(d2) | 0x80000000u;
+          const unsigned long long hi = ((unsigned long long)kb << 32) | rb;
+          const int pix = hb * a.W + wb;
+          mine = U128{~(unsigned long long)nb, ~hi};
+          old = cas128(best + pix, U128{0ull, 0ull}, mine);
+          pend_pix = pix;
+        }
+      }
+      if (live_a) {
+        mb = ma; tb = ta; hb = ha_; wb = wa_; nb = n;
+      } else {
+        nb = -1;
+      }
+      if (!have_a) break;
+    }
+  } else
+#endif
+  {
   MapPoint cur = load_map_point(pts, nrm, cc, n < count ? n : 0);
   for (; n < count; n += stride) {
     const MapPoint m = cur;
@@ -188,6 +255,7 @@ __global__ void __launch_bounds__(kBlock, GSX_K2_MINB) k_project_select(ProjectA
         pend_pix = pix;
       }
     }
+  }
   }
   if (pend_pix >= 0) atomic_max_rec128_finish(best + pend_pix, mine, old);
   // bookkeeping for the roofline's algorithmic-byte count: one atomic per warp
@@ -516,7 +584,7 @@ int launch_project_select(const ProjectArgs &a, int64_t max_count, cudaStream_t 
   const int64_t chunk = (int64_t)kBlock;
   int64_t bx = (max_count + chunk - 1) / chunk;
 #ifndef GSX_K2_CTAS_PER_SM
-#define GSX_K2_CTAS_PER_SM 16
+#define GSX_K2_CTAS_PER_SM 8
 #endif
   const int64_t cap_blocks = (int64_t)kNumSMs * GSX_K2_CTAS_PER_SM;  // grid-stride beyond this many CTAs per SM
   if (bx * a.B > cap_blocks) bx = (cap_blocks + a.B - 1) / a.B;
