@@ -146,7 +146,50 @@ def icp_align(src, src_counts, tgt, tgt_normals, tgt_counts, T0, mode, numiters,
     return out, idx
 
 
+def _wants_grad(*tensors):
+    return torch.is_grad_enabled() and any(torch.is_tensor(t) and t.requires_grad for t in tensors)
+
+
+def _taped_icp(src_pc, tgt_pc, tgt_normals, initial_transform, mode, numiters, damp, dist_thresh, lambda_max=2.0,
+               B=1.0, B2=1.0, nu=200.0):
+    """Differentiable variant used when an input requires grad: the association is the CUDA exact 1-NN (no gradient,
+    as in the reference), the rest of the LM / gradLM iteration is torch ops so PyTorch's tape yields the same
+    gradients as the reference (icputils.py:235-545).  Slower than the fused loop; forward values agree with it."""
+    from ..geometry.geometryutils import transform_pointcloud
+    from ..geometry.se3utils import se3_exp
+
+    dtype, device = src_pc.dtype, src_pc.device
+    damp = torch.tensor(damp, dtype=dtype, device=device)
+    lambda_min = 1 / lambda_max
+    T = torch.eye(4, dtype=dtype, device=device) if initial_transform is None else initial_transform
+    src = transform_pointcloud(src_pc[0], T)
+    idx = None
+    for _ in range(numiters):
+        A, b, idx = gauss_newton_solve(src.unsqueeze(0), tgt_pc, tgt_normals, dist_thresh)
+        xi = solve_linear_system(A, b, damp)
+        dT = se3_exp(xi)
+        err = torch.dot(b[:, 0], b[:, 0])
+        one_step = transform_pointcloud(src, dT)
+        _, b1, _ = gauss_newton_solve(one_step.unsqueeze(0), tgt_pc, tgt_normals, dist_thresh)
+        new_err = torch.dot(b1[:, 0], b1[:, 0])
+        if mode == 0:
+            if new_err < err:
+                src, damp, T = one_step, damp / 2, torch.mm(dT, T)
+            else:
+                damp = damp * 2
+        else:
+            diff = (new_err - err).clamp(-70.0, 70.0)
+            damp = damp * (lambda_min + (lambda_max - lambda_min) / (1 + torch.exp(-B * diff)))
+            sig = 1 / ((1 + torch.exp(-B2 * diff)) ** (1 / nu))
+            dT = se3_exp(sig * xi)
+            src = transform_pointcloud(src, dT)
+            T = torch.mm(dT, T)
+    return T, idx
+
+
 def _single(src_pc, tgt_pc, tgt_normals, initial_transform, mode, numiters, damp, dist_thresh, **kw):
+    if _wants_grad(src_pc, tgt_pc, tgt_normals, initial_transform):
+        return _taped_icp(src_pc, tgt_pc, tgt_normals, initial_transform, mode, numiters, damp, dist_thresh, **kw)
     dev = src_pc.device
     T0 = None if initial_transform is None else initial_transform.view(1, 4, 4)
     T, idx = icp_align(src_pc.contiguous(), _counts(src_pc.shape[1], 1, dev), tgt_pc.contiguous(),

@@ -107,9 +107,21 @@ class ICPSLAM(nn.Module):
                 raise ValueError("`live_frame` must have poses when `prev_frame` is None or `odom='gt'`.")
             return live_frame.poses
 
-        from ..odometry.icputils import localize_against_map
+        from ..odometry.icputils import _wants_grad, downsample_pointclouds, downsample_rgbdimages, localize_against_map
 
         live_frame.poses = prev_frame.poses
+        if _wants_grad(live_frame.depth_image, prev_frame.poses, pointclouds._store["points"],
+                       pointclouds._store["normals"]):
+            # differentiable mode (reference op order, slam/icpslam.py:238-247): the K1 maps carry their hand-written
+            # backward, the association kernels are index-only, the ICP algebra is taped.
+            from ..geometry.geometryutils import compose_transformations
+            from .fusionutils import find_active_map_points
+
+            frames_pc = downsample_rgbdimages(live_frame, self.dsratio)
+            pc2im_bnhw = find_active_map_points(pointclouds, prev_frame)
+            maps_pc = downsample_pointclouds(pointclouds, pc2im_bnhw, self.dsratio)
+            transform = self.odomprov.provide(maps_pc, frames_pc)
+            return compose_transformations(transform.squeeze(1), prev_frame.poses.squeeze(1)).unsqueeze(1)
         # source / target gathering, the ICP loop and the final T_icp · prev_pose all happen in one C call
         return localize_against_map(pointclouds, live_frame, prev_frame, self.dsratio, self.odomprov)
 
