@@ -392,6 +392,58 @@ def fuse_with_map(pointclouds: Pointclouds, rgbdimages: RGBDImages, pc2im_bnhw: 
     return pointclouds
 
 
+# --------------------------------------------------------------------------------------------- differentiable mode
+def _wants_grad(pointclouds, frames):
+    if not torch.is_grad_enabled():
+        return False
+    ts = [frames.depth_image, frames.poses, frames.rgb_image, frames.intrinsics] + list(pointclouds._store.values())
+    return any(torch.is_tensor(t) and t.requires_grad for t in ts)
+
+
+def _append_differentiable(pointclouds, frames, with_features, sigma):
+    """Appends every valid pixel through differentiable torch indexing of the K1 maps (which carry their hand-written
+    backward).  Used only when a gradient is requested; values equal the kernel path."""
+    frames = frames.to_channels_last()
+    B = len(frames)
+    gv, gn, col = frames.global_vertex_map[:, 0], frames.global_normal_map[:, 0], frames.rgb_image[:, 0]
+    mask = frames.valid_depth_mask[:, 0, ..., 0]
+    feats = None
+    if with_features:
+        alpha = get_alpha(frames.vertex_map[:, 0], sigma, dim=-1, keepdim=True)
+        feats = [alpha[i][mask[i]] for i in range(B)]
+    fresh = Pointclouds([gv[i][mask[i]] for i in range(B)], [gn[i][mask[i]] for i in range(B)],
+                        [col[i][mask[i]] for i in range(B)], feats)
+    return pointclouds.append_points(fresh)
+
+
+def _fuse_differentiable(pointclouds, frames, table, sigma):
+    """fuse_with_map as out-of-place torch ops on the rows named by `table` (fusionutils.py:654-720), so PyTorch's
+    tape links the fused map to depth / poses / colours and to the previous map.  The association (`table`) comes
+    from the CUDA kernels and is index-only, as in the reference."""
+    frames = frames.to_channels_last()
+    B = len(frames)
+    gv, gn, col = frames.global_vertex_map[:, 0], frames.global_normal_map[:, 0], frames.rgb_image[:, 0]
+    alpha = get_alpha(frames.vertex_map[:, 0], sigma, dim=-1, keepdim=True)  # (B,H,W,1)
+    new_mask = frames.valid_depth_mask[:, 0, ..., 0].clone()
+    if not pointclouds.has_points:
+        pointclouds.device = frames.device
+    st = pointclouds._store
+    if pointclouds.has_points and table.shape[0] != 0:
+        b, n, h, w = table.unbind(1)
+        cc = st["features"][b, n]
+        a = alpha[b, h, w]
+        tot = cc + a
+        inv = 1 / torch.where(tot == 0, torch.ones_like(tot), tot)
+        for key, fmap in (("points", gv), ("normals", gn), ("colors", col)):
+            st[key] = st[key].index_put((b, n), ((cc * st[key][b, n]) + (a * fmap[b, h, w])) * inv)
+        st["features"] = st["features"].index_put((b, n), tot)
+        pointclouds._list_cache = {}
+        new_mask[b, h, w] = False
+    fresh = Pointclouds([gv[i][new_mask[i]] for i in range(B)], [gn[i][new_mask[i]] for i in range(B)],
+                        [col[i][new_mask[i]] for i in range(B)], [alpha[i][new_mask[i]] for i in range(B)])
+    return pointclouds.append_points(fresh)
+
+
 # --------------------------------------------------------------------------------------------- public ops
 def update_map_aggregate(pointclouds: Pointclouds, rgbdimages: RGBDImages, inplace: bool = False) -> Pointclouds:
     """Appends every valid live-frame pixel to the maps (fusionutils.py:725-758)."""
@@ -401,6 +453,9 @@ def update_map_aggregate(pointclouds: Pointclouds, rgbdimages: RGBDImages, inpla
         raise TypeError("Expected rgbdimages to be of type gradslam.RGBDImages. Got {0}.".format(type(rgbdimages)))
     if not inplace:
         pointclouds = pointclouds.clone()
+    if _wants_grad(pointclouds, rgbdimages):
+        _check_frame(rgbdimages)
+        return _append_differentiable(pointclouds, rgbdimages, pointclouds.has_features, 0.6)
     return _append_valid_pixels(pointclouds, rgbdimages, True)
 
 
@@ -413,4 +468,8 @@ def update_map_fusion(pointclouds: Pointclouds, rgbdimages: RGBDImages, dist_th:
     _check_frame(rgbdimages)
     if not inplace:
         pointclouds = pointclouds.clone()
+    if _wants_grad(pointclouds, rgbdimages):
+        with torch.no_grad():
+            table = find_correspondences(pointclouds, rgbdimages.detach(), dist_th, dot_th)
+        return _fuse_differentiable(pointclouds, rgbdimages, table, sigma)
     return _fused_update(pointclouds, rgbdimages, dist_th, dot_th, sigma)

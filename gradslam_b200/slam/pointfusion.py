@@ -49,6 +49,9 @@ class PointFusion(ICPSLAM):
         stream, so the copy of chunk i+1 overlaps the fusion of chunk i (pin the host tensors for this)."""
         if self.odom != "gt" or frames.poses is None or torch.is_tensor(self.sigma):
             return None
+        if torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in (
+                frames.depth_image, frames.rgb_image, frames.poses, frames.intrinsics)):
+            return None  # differentiable mode goes through the per-frame step loop
         if frames.channels_first:
             frames = frames.to_channels_last()
         dev = self.device

@@ -130,3 +130,36 @@ def test_icpslam_pose_gradient_wrt_live_depth():
     assert torch.isfinite(g_gpu).all() and g_ref.abs().max() > 0
     scale = g_ref.abs().max().item()
     torch.testing.assert_close(g_gpu, g_ref, rtol=5e-2, atol=5e-3 * scale)
+
+
+def test_pointfusion_map_gradients_match_oracle_autograd():
+    """PointFusion(odom='gt') in differentiable mode: d(fused map)/d(depth, colours) through the K1 backward kernel and
+    the taped merge, against PyTorch autograd of the oracle restatement (fusionutils.py:580-722)."""
+    import gradslam_b200 as gs
+    import gsx_oracle as oracle
+
+    B, L, H, W = 1, 2, 24, 32
+    rgb, depth, K, poses = make_sequence(B, L, H, W, seed=41, isolated_holes=True, yaw0=0.6)
+    d_ref, c_ref = depth.clone().requires_grad_(True), rgb.clone().requires_grad_(True)
+    ref = oracle.run_slam(c_ref, d_ref, K, poses, odom="gt")
+    g = torch.Generator().manual_seed(5)
+    n = ref.map.counts()[0]
+    wp, wc, wf = torch.randn(n, 3, generator=g), torch.randn(n, 3, generator=g), torch.randn(n, 1, generator=g)
+    ((ref.map.points[0] * wp).sum() + (ref.map.colors[0] * wc).sum() + (ref.map.ccounts[0] * wf).sum()).backward()
+
+    d_gpu, c_gpu = depth.clone().to(DEV).requires_grad_(True), rgb.clone().to(DEV).requires_grad_(True)
+    slam = gs.PointFusion(odom="gt", device=DEV)
+    pc, _ = slam(gs.RGBDImages(c_gpu, d_gpu, K.to(DEV), poses.to(DEV)))
+    assert pc.num_points_per_pointcloud.tolist() == [n]
+    torch.testing.assert_close(pc.points_list[0].detach().cpu(), ref.map.points[0].detach(), rtol=1e-5, atol=1e-6)
+    ((pc.points_list[0] * wp.to(DEV)).sum() + (pc.colors_list[0] * wc.to(DEV)).sum()
+     + (pc.features_list[0] * wf.to(DEV)).sum()).backward()
+    for got, want in ((d_gpu.grad.cpu(), d_ref.grad), (c_gpu.grad.cpu(), c_ref.grad)):
+        assert torch.isfinite(got).all()
+        scale = want.abs().max().item()
+        torch.testing.assert_close(got, want, rtol=1e-3, atol=1e-4 * scale)
+    # the same call without gradients takes the fused kernels and gives the same map
+    with torch.no_grad():
+        pc2, _ = slam(gs.RGBDImages(rgb.to(DEV), depth.to(DEV), K.to(DEV), poses.to(DEV)))
+    assert pc2.num_points_per_pointcloud.tolist() == [n]
+    torch.testing.assert_close(pc2.points_list[0], pc.points_list[0].detach(), rtol=1e-6, atol=1e-6)
