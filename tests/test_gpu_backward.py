@@ -126,10 +126,12 @@ def test_icpslam_pose_gradient_wrt_live_depth():
     pc, rec = slam(gs.RGBDImages(rgb.to(DEV), d_gpu, K.to(DEV), poses.to(DEV)))
     torch.testing.assert_close(rec.detach().cpu(), ref.poses.detach(), rtol=0, atol=1e-4)
     (rec[0, 1] * w.to(DEV)).sum().backward()
-    g_ref, g_gpu = d_ref.grad[:, 1], d_gpu.grad[:, 1].cpu()
-    assert torch.isfinite(g_gpu).all() and g_ref.abs().max() > 0
-    scale = g_ref.abs().max().item()
-    torch.testing.assert_close(g_gpu, g_ref, rtol=5e-2, atol=5e-3 * scale)
+    # frame 1 (the live frame) AND frame 0 (whose pixels became the map the ICP aligns to)
+    for s in (1, 0):
+        g_ref, g_gpu = d_ref.grad[:, s], d_gpu.grad[:, s].cpu()
+        assert torch.isfinite(g_gpu).all() and g_ref.abs().max() > 0
+        scale = g_ref.abs().max().item()
+        torch.testing.assert_close(g_gpu, g_ref, rtol=5e-2, atol=5e-3 * scale)
 
 
 def test_pointfusion_map_gradients_match_oracle_autograd():

@@ -151,3 +151,24 @@ def test_update_map_aggregate_matches_oracle():
         assert torch.equal(pc.points_list[b].cpu(), smap.points[b])
         assert torch.equal(pc.normals_list[b].cpu(), smap.normals[b])
         assert torch.equal(pc.colors_list[b].cpu(), smap.colors[b])
+
+
+def test_update_map_fusion_threshold_monotonicity():
+    """The reference's property test (tests/slam/test_fusionutils.py:1138-1176): looser thresholds merge more and
+    append less; with impossible thresholds every valid pixel is appended."""
+    import gradslam_b200 as gs
+    from gradslam_b200.slam import fusionutils as fu
+
+    rgb, depth, K, poses = make_sequence(2, 2, 40, 56, seed=17)
+    dev = _dev()
+    frames = _frames(gs, rgb, depth, K, poses, dev)
+    base = fu.update_map_fusion(gs.Pointclouds(device=dev), frames[:, 0], 0.05, 0.94, 0.6)
+    n0 = base.num_points_per_pointcloud
+    valid1 = (depth[:, 1, ..., 0] > 0).flatten(1).sum(1)
+    strict = fu.update_map_fusion(base, frames[:, 1], 0.0, 1.0, 0.6)       # nothing can match
+    loose = fu.update_map_fusion(base, frames[:, 1], 0.05, 0.94, 0.6)
+    looser = fu.update_map_fusion(base, frames[:, 1], 0.2, 0.5, 0.6)
+    assert (strict.num_points_per_pointcloud.cpu() == n0.cpu() + valid1).all()
+    assert (looser.num_points_per_pointcloud <= loose.num_points_per_pointcloud).all()
+    assert (loose.num_points_per_pointcloud <= strict.num_points_per_pointcloud).all()
+    assert (base.num_points_per_pointcloud == n0).all()  # inputs untouched
