@@ -14,8 +14,10 @@ from gradslam_b200.synthetic import make_sequence
 
 L = int(sys.argv[1]) if len(sys.argv) > 1 else 10
 B = int(sys.argv[2]) if len(sys.argv) > 2 else 8
+H = int(sys.argv[3]) if len(sys.argv) > 3 else 480
+W = int(sys.argv[4]) if len(sys.argv) > 4 else 640
 dev = torch.device("cuda:0")
-rgb, depth, K, poses = make_sequence(B, L, 480, 640, seed=0)
+rgb, depth, K, poses = make_sequence(B, L, H, W, seed=0)
 frames = gs.RGBDImages(rgb.to(dev), depth.to(dev), K.to(dev), poses.to(dev))
 slam = gs.PointFusion(odom="gt", device=dev)
 pc, _ = slam(frames)

@@ -17,15 +17,17 @@ from gradslam_b200.slam.fusionutils import _Workspace
 from gradslam_b200.synthetic import make_sequence
 
 args = [a for a in sys.argv[1:]]
-L = 32
-if "--L" in args:
-    i = args.index("--L")
-    L = int(args[i + 1])
-    del args[i:i + 2]
+opts = {"--L": 32, "--B": 8, "--H": 480, "--W": 640}
+for k in list(opts):
+    if k in args:
+        i = args.index(k)
+        opts[k] = int(args[i + 1])
+        del args[i:i + 2]
+L, B, H, W = opts["--L"], opts["--B"], opts["--H"], opts["--W"]
 libs = args or [_C.LIB_PATH] + sorted(glob.glob(os.path.join(ROOT, "gradslam_b200", "_lib", "variants", "*.so")))
 dev = torch.device("cuda:0")
 t0 = time.time()
-rgb, depth, K, poses = make_sequence(8, L, 480, 640, seed=0)
+rgb, depth, K, poses = make_sequence(B, L, H, W, seed=0)
 rgb, depth, K, poses = (t.to(dev) for t in (rgb, depth, K, poses))
 print("inputs ready in %.1f s" % (time.time() - t0), flush=True)
 frames = gs.RGBDImages(rgb, depth, K, poses)
@@ -53,7 +55,7 @@ for path in libs:
         ref_counts = counts
     prof, _ = profiling.profile_pointfusion_gt(depth, rgb, K, poses, slam.dist_th, slam.dot_th, slam.sigma)
     prof, finfo = profiling.profile_pointfusion_gt(depth, rgb, K, poses, slam.dist_th, slam.dot_th, slam.sigma)
-    line = "%-28s %.3f ms/step  %.0f frames/s  same_counts=%s |" % (os.path.basename(path), ms, 8 * L / ms * 1e3,
+    line = "%-28s %.3f ms/step  %.0f frames/s  same_counts=%s |" % (os.path.basename(path), ms, B * L / ms * 1e3,
                                                                    counts == ref_counts)
     for name, rows in prof.items():
         tot = sum(r[0] for r in rows)
