@@ -254,6 +254,8 @@ def main():
         barrier()
         return ms, res
 
+    if world > 1:  # setup, not warm-up: let the caching allocator reach its steady state (two map stores and two sets
+        run_steps(frames_dev, 3, d2h=False)  # of gather buffers are alive at once in the pipelined loop)
     run_steps(frames_dev, max(args.warmup, 3), d2h=False)  # same (pipelined) code path as the timed region
     sampler = ClockSampler(local_rank)
     if rank == 0:

@@ -50,7 +50,9 @@ def run(mode, steps=6):
             mode, t.item(), wall, torch.cuda.memory_allocated() / 1e9, torch.cuda.memory_reserved() / 1e9), flush=True)
 
 
-for mode in ("compute", "compute", "blocking", "blocking", "pipelined", "pipelined", "pipelined"):
+if rank == 0:
+    print("NCCL_MAX_CTAS =", os.environ.get("NCCL_MAX_CTAS"), flush=True)
+for mode in ("compute", "pipelined", "pipelined", "pipelined", "compute"):
     run(mode)
 # phases of one blocking gather
 pc, _p = slam(frames)
