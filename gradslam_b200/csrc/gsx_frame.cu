@@ -48,21 +48,36 @@ __global__ void __launch_bounds__(kTile) k_backproject_normals(FrameArgs a) {
       stage[3][t3] = f.gn.x; stage[3][t3 + 1] = f.gn.y; stage[3][t3 + 2] = f.gn.z;
     }
   }
+  // make the generic-proxy shared-memory writes visible to the async (bulk-copy) proxy, then sync the CTA
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   __syncthreads();
   const int remaining = P - tile0;
   const int nfloat = (remaining < kTile ? remaining : kTile) * 3;
   const int64_t obase = ((int64_t)img * P + tile0) * 3;
   // every image starts 16-byte aligned only if P*3 floats is a multiple of 4
   const bool vec_ok = (nfloat == kTile * 3) && ((obase & 3) == 0);
+  if (vec_ok) {
+    // full tile: ONE thread hands each 3072-byte map tile to the bulk-copy engine (cp.async.bulk, shared -> global;
+    // SASS: UBLKCP), instead of 192 threads issuing 16-byte stores
+    if (threadIdx.x == 0) {
 #pragma unroll
-  for (int m = 0; m < 4; ++m) {
-    float *out = a.out[m];
-    if (!out) continue;
-    float *dst = out + obase;
-    if (vec_ok) {
-      if (threadIdx.x < kTile * 3 / 4)
-        reinterpret_cast<float4 *>(dst)[threadIdx.x] = reinterpret_cast<const float4 *>(stage[m])[threadIdx.x];
-    } else {
+      for (int m = 0; m < 4; ++m) {
+        float *out = a.out[m];
+        if (!out) continue;
+        const unsigned int src = (unsigned int)__cvta_generic_to_shared(stage[m]);
+        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(out + obase), "r"(src),
+                     "n"(kTile * 3 * 4)
+                     : "memory");
+      }
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // smem must stay intact until it has been read
+    }
+  } else {
+#pragma unroll
+    for (int m = 0; m < 4; ++m) {
+      float *out = a.out[m];
+      if (!out) continue;
+      float *dst = out + obase;
       for (int j = threadIdx.x; j < nfloat; j += kTile) dst[j] = stage[m][j];
     }
   }
