@@ -333,6 +333,12 @@ __device__ __forceinline__ unsigned int lookback_warp(const unsigned long long *
 #ifndef GSX_K4_MINB
 #define GSX_K4_MINB 4
 #endif
+#ifndef GSX_K4_EARLY_EXIT
+#define GSX_K4_EARLY_EXIT 0  // measured: no gain
+#endif
+#ifndef GSX_K4_EARLY_LOOKBACK
+#define GSX_K4_EARLY_LOOKBACK 0  // measured: slower (125 us vs 116 us)
+#endif
 #ifndef GSX_K4_SPLIT
 #define GSX_K4_SPLIT 0  // 1: k_merge_only (no barriers) then k_merge_append<.., false> (append + scan only); measured slower
 #endif
@@ -474,6 +480,17 @@ __global__ void __launch_bounds__(kBlock, GSX_K4_MINB) k_merge_append(MergeArgs 
   }
   unsigned long long *state = a.ws.tile_state + (int64_t)b * T;
   if (threadIdx.x == 0 && tile + 1 < T) st_release_u64(state + tile, pack_state(a.epoch, kFlagAgg, (unsigned)block_total));
+#if GSX_K4_EARLY_LOOKBACK
+  // warp 0 resolves the tile's exclusive prefix right away (its successors stop walking back as soon as they see a
+  // PREFIX), the other warps go on with the merge meanwhile
+  if (warp == 0) {
+    const unsigned int excl = lookback_warp(state, tile, a.epoch, lane);
+    if (lane == 0) {
+      if (tile + 1 < T) st_release_u64(state + tile, pack_state(a.epoch, kFlagPrefix, excl + (unsigned)block_total));
+      s_excl = (int)excl;
+    }
+  }
+#endif
 
   float *pts = a.pts + (int64_t)b * a.cap * 3;
   float *nrm = a.nrm + (int64_t)b * a.cap * 3;
@@ -548,6 +565,7 @@ __global__ void __launch_bounds__(kBlock, GSX_K4_MINB) k_merge_append(MergeArgs 
     }
   }
 
+#if !GSX_K4_EARLY_LOOKBACK
   // decoupled look-back (warp 0): exclusive prefix of new-point counts over preceding tiles of this element
   if (warp == 0) {
     const unsigned int excl = lookback_warp(state, tile, a.epoch, lane);
@@ -556,6 +574,17 @@ __global__ void __launch_bounds__(kBlock, GSX_K4_MINB) k_merge_append(MergeArgs 
       s_excl = (int)excl;
     }
   }
+#endif
+#if GSX_K4_EARLY_EXIT
+  {
+    // only warps that have something to append need the prefix; the others retire now (exited warps count as
+    // arrived at the barrier) and free their slots for the next CTA.  Warp 0 stays: it owns s_excl / counts_out.
+    bool any_new = false;
+#pragma unroll
+    for (int j = 0; j < kPix; ++j) any_new = any_new || is_new[j];
+    if (warp != 0 && !__any_sync(0xffffffffu, any_new)) return;
+  }
+#endif
   __syncthreads();
   const int64_t base = (int64_t)count_in + s_excl;
 #pragma unroll
