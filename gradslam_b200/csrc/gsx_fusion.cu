@@ -285,6 +285,14 @@ struct MergeArgs {
   int32_t *overflow;
 };
 
+// alpha = clamp(exp(-|v|^2 / 2 sigma^2), 1e-7, 1.01) (fusionutils.py:69-72).  The exponential is evaluated in double and
+// rounded once: that is the correctly rounded float32 exp (up to 2^-29 odds), so the CUDA path and the CPU oracle agree
+// bit for bit and no later threshold / arg-min decision can flip because of a 1-ulp difference in a confidence weight.
+__device__ __forceinline__ float confidence_alpha(float sq_norm, float two_sigma_sq) {
+  const float e = (float)exp((double)((-sq_norm) / two_sigma_sq));
+  return fminf(fmaxf(e, 1e-7f), 1.01f);
+}
+
 constexpr unsigned long long kFlagAgg = 1ull, kFlagPrefix = 2ull;
 
 __device__ __forceinline__ unsigned long long pack_state(unsigned int epoch, unsigned long long flag, unsigned int value) {
@@ -393,7 +401,7 @@ __global__ void __launch_bounds__(kBlock, GSX_K4A_MINB) k_merge_only(MergeArgs a
   }
   // alpha from the LOCAL vertex (fusionutils.py:657, 69-72)
   const float sq = (v.x * v.x + v.y * v.y) + v.z * v.z;
-  const float alpha = fminf(fmaxf(expf((-sq) / a.two_sigma_sq), 1e-7f), 1.01f);
+  const float alpha = confidence_alpha(sq, a.two_sigma_sq);
   // confidence-weighted running mean (fusionutils.py:678-699)
   const float c0 = mp[9];
   const float tot = c0 + alpha;
@@ -516,7 +524,7 @@ __global__ void __launch_bounds__(kBlock, GSX_K4_MINB) k_merge_append(MergeArgs 
         fn[j] = f.gn;
         // alpha from the LOCAL vertex (fusionutils.py:657, 69-72)
         const float s = (f.v.x * f.v.x + f.v.y * f.v.y) + f.v.z * f.v.z;
-        alpha[j] = fminf(fmaxf(expf((-s) / a.two_sigma_sq), 1e-7f), 1.01f);
+        alpha[j] = confidence_alpha(s, a.two_sigma_sq);
       } else {
         const float *g = gvb + (int64_t)pix[j] * 3;
         const float *q = gnb + (int64_t)pix[j] * 3;
@@ -525,7 +533,7 @@ __global__ void __launch_bounds__(kBlock, GSX_K4_MINB) k_merge_append(MergeArgs 
         const int h = pix[j] / a.W, w = pix[j] - h * a.W;
         const float3 v = backproject(k, (float)w, (float)h, d[j]);
         const float s = (v.x * v.x + v.y * v.y) + v.z * v.z;
-        alpha[j] = fminf(fmaxf(expf((-s) / a.two_sigma_sq), 1e-7f), 1.01f);
+        alpha[j] = confidence_alpha(s, a.two_sigma_sq);
       }
     }
   }

@@ -27,8 +27,10 @@ einsum/bmm, whose rounding order is whatever the BLAS picks.  So that the CUDA
 kernels can be BIT-exact on every decision (thresholds, rounding to pixels,
 argmin keys) the oracle fixes one order:  every product and sum is rounded
 separately to float32 (no FMA) and 3-term sums associate left to right,
-`(a*x + b*y) + c*z`, then `+ t`.  Differences from the reference are at the
-1-ulp level and are covered by the tolerances in the golden tests.
+`(a*x + b*y) + c*z`, then `+ t`; square roots and the confidence weight's exp are
+taken in float64 and rounded once (correctly rounded float32 results).  Differences
+from the reference are at the 1-ulp level and are covered by the tolerances in
+the golden tests.
 
 One deliberate deviation: the reference's merge rewrites EVERY map point as
 `(c*p) * (1/c)` each frame (fusionutils.py:682-699 operates on the whole padded
@@ -335,7 +337,8 @@ def find_correspondences(smap, maps, pose, K, dist_th, dot_th):
 def get_alpha(vertex, sigma, eps=1e-7):
     """clamp(exp(-(x^2+y^2+z^2) / (2 sigma^2)), eps, 1.01) on the LOCAL vertex; (...,3)->(...,1)."""
     s = (vertex[..., 0] * vertex[..., 0] + vertex[..., 1] * vertex[..., 1]) + vertex[..., 2] * vertex[..., 2]
-    a = torch.exp(-s / torch.tensor(2 * (sigma ** 2), dtype=F32))
+    # exp in float64, rounded once to float32 (the correctly rounded result; see confidence_alpha in gsx_fusion.cu)
+    a = torch.exp((-s / torch.tensor(2 * (sigma ** 2), dtype=F32)).double()).float()
     return torch.clamp(a, min=eps, max=1.01).unsqueeze(-1)
 
 

@@ -38,12 +38,12 @@ def _compare_maps(pc, ref_map, exact_structure=True):
     got = [int(c) for c in pc.num_points_per_pointcloud.tolist()]
     assert got == ref_map.counts()
     for b in range(len(got)):
-        # positions / normals / colours of never-merged points are bit-exact; merged ones differ only through
-        # expf (CUDA) vs exp (CPU) in the confidence weight: <= a few ulp.  Tolerance: 1e-6 abs/rel.
-        torch.testing.assert_close(pc.points_list[b].cpu(), ref_map.points[b], rtol=1e-6, atol=1e-6)
-        torch.testing.assert_close(pc.normals_list[b].cpu(), ref_map.normals[b], rtol=1e-6, atol=1e-6)
-        torch.testing.assert_close(pc.colors_list[b].cpu(), ref_map.colors[b], rtol=1e-6, atol=1e-6)
-        torch.testing.assert_close(pc.features_list[b].cpu(), ref_map.ccounts[b], rtol=1e-6, atol=1e-7)
+        # every operation of the fusion step is canonical IEEE arithmetic on both sides (the exp of the confidence
+        # weight is taken in double and rounded once), so the maps are bit-identical
+        assert torch.equal(pc.points_list[b].cpu(), ref_map.points[b])
+        assert torch.equal(pc.normals_list[b].cpu(), ref_map.normals[b])
+        assert torch.equal(pc.colors_list[b].cpu(), ref_map.colors[b])
+        assert torch.equal(pc.features_list[b].cpu(), ref_map.ccounts[b])
 
 
 @pytest.mark.parametrize("shape", [(2, 4, 48, 64), (1, 5, 120, 160), (3, 3, 64, 64)])
