@@ -15,7 +15,11 @@ constexpr int kBlock = 256;
 #ifndef GSX_KPIX
 #define GSX_KPIX 2
 #endif
-constexpr int kTilePix = kBlock * GSX_KPIX;  // pixels per merge tile (must equal kMergeTile)
+#ifndef GSX_K4_BLOCK
+#define GSX_K4_BLOCK 256
+#endif
+constexpr int kMB = GSX_K4_BLOCK;         // threads per CTA of the merge/append kernel
+constexpr int kTilePix = kMB * GSX_KPIX;  // pixels per merge tile (must equal kMergeTile)
 
 // ---- workspace layout -----------------------------------------------------------------------------------
 //   [0, B*P*16)                       U128 best[B][P]     complemented arg-min records (0 = empty)
@@ -312,7 +316,7 @@ __device__ __forceinline__ void st_release_u64(unsigned long long *p, unsigned l
 #define GSX_KPIX 2
 #endif
 constexpr int kPix = GSX_KPIX;             // pixels per thread
-constexpr int kMergeTile = kBlock * kPix;  // pixels per CTA
+constexpr int kMergeTile = kMB * kPix;  // pixels per CTA
 static_assert(kMergeTile == kTilePix, "workspace tile size");
 
 // exclusive prefix of the new-point counts of all preceding tiles (decoupled look-back, one warp, 32
@@ -419,10 +423,10 @@ __global__ void __launch_bounds__(kBlock, GSX_K4A_MINB) k_merge_only(MergeArgs a
 }
 
 template <bool kFused, bool kDoMerge>
-__global__ void __launch_bounds__(kBlock, GSX_K4_MINB) k_merge_append(MergeArgs a) {
+__global__ void __launch_bounds__(kMB, GSX_K4_MINB) k_merge_append(MergeArgs a) {
   __shared__ Rigid s_pose;
   __shared__ int s_tile;
-  __shared__ int s_warp_sums[kPix][kBlock / 32];
+  __shared__ int s_warp_sums[kPix][kMB / 32];
   __shared__ int s_excl;
   __shared__ KInv s_k;
   // batch element varies fastest in the grid: CTAs resident at the same time belong to different elements, so
@@ -451,7 +455,7 @@ __global__ void __launch_bounds__(kBlock, GSX_K4_MINB) k_merge_append(MergeArgs 
   int warp_excl[kPix];
 #pragma unroll
   for (int j = 0; j < kPix; ++j) {
-    pix[j] = tile * kMergeTile + j * kBlock + threadIdx.x;
+    pix[j] = tile * kMergeTile + j * kMB + threadIdx.x;
     rec[j] = U128{0ull, 0ull};
     d[j] = 0.0f;
     if (pix[j] < P) {
@@ -480,7 +484,7 @@ __global__ void __launch_bounds__(kBlock, GSX_K4_MINB) k_merge_append(MergeArgs 
   for (int j = 0; j < kPix; ++j) {
     block_excl[j] = block_total;
 #pragma unroll
-    for (int i = 0; i < kBlock / 32; ++i) {
+    for (int i = 0; i < kMB / 32; ++i) {
       const int c = s_warp_sums[j][i];
       if (i < warp) block_excl[j] += c;
       block_total += c;
@@ -643,11 +647,11 @@ int launch_merge_append(const MergeArgs &a, cudaStream_t stream) {
     if (a.gv) k_merge_only<false><<<mgrid, kBlock, 0, stream>>>(a);
     else k_merge_only<true><<<mgrid, kBlock, 0, stream>>>(a);
   }
-  if (a.gv) k_merge_append<false, false><<<grid, kBlock, 0, stream>>>(a);
-  else k_merge_append<true, false><<<grid, kBlock, 0, stream>>>(a);
+  if (a.gv) k_merge_append<false, false><<<grid, kMB, 0, stream>>>(a);
+  else k_merge_append<true, false><<<grid, kMB, 0, stream>>>(a);
 #else
-  if (a.gv) k_merge_append<false, true><<<grid, kBlock, 0, stream>>>(a);
-  else k_merge_append<true, true><<<grid, kBlock, 0, stream>>>(a);
+  if (a.gv) k_merge_append<false, true><<<grid, kMB, 0, stream>>>(a);
+  else k_merge_append<true, true><<<grid, kMB, 0, stream>>>(a);
 #endif
   GSX_CHECK_LAUNCH("gsx_fusion_merge_append");
   return 0;
