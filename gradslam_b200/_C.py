@@ -54,6 +54,9 @@ SIGNATURES = {
     "gsx_knn1_scratch_bytes": (c_i64, [c_int, c_int, c_int]),
     "gsx_icp_tgt_scratch_bytes": (c_i64, [c_int, c_i64]),
     "gsx_knn1": (c_int, [c_vp, c_vp, c_int, c_vp, c_vp, c_int, c_int, c_vp, c_vp, c_vp, c_i64, c_vp]),
+    "gsx_icp_normal_eq_scratch_bytes": (c_i64, [c_int]),
+    "gsx_icp_normal_eq_fwd": (c_int, [c_vp, c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_vp]),
+    "gsx_icp_normal_eq_bwd": (c_int, [c_vp, c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "gsx_icp_align_scratch_bytes": (c_i64, [c_int, c_int, c_int]),
     "gsx_icp_align": (
         c_int, [c_vp, c_vp, c_int, c_vp, c_vp, c_vp, c_int, c_int, c_vp, c_int, c_int, c_float, c_int, c_float,

@@ -475,6 +475,50 @@ struct KnnArgs {
   TargetGrid grid;  // used by the kGrid variant
 };
 
+// point-to-plane row of one association and its 28 products (gauss_newton_solve, icputils.py:227-230)
+__device__ __forceinline__ void row_products(float sx, float sy, float sz, const float *__restrict__ tp,
+                                             const float *__restrict__ tn, int64_t bi, float *acc) {
+  const float dx = __ldg(tp + bi * 3), dy = __ldg(tp + bi * 3 + 1), dz = __ldg(tp + bi * 3 + 2);
+  const float nx = __ldg(tn + bi * 3), ny = __ldg(tn + bi * 3 + 1), nz = __ldg(tn + bi * 3 + 2);
+  float A[6];
+  A[0] = nx; A[1] = ny; A[2] = nz;
+  A[3] = nz * sy - ny * sz;
+  A[4] = nx * sz - nz * sx;
+  A[5] = ny * sx - nx * sy;
+  const float r = (nx * (dx - sx) + ny * (dy - sy)) + nz * (dz - sz);
+  int k = 0;
+#pragma unroll
+  for (int p = 0; p < 6; ++p)
+#pragma unroll
+    for (int q = p; q < 6; ++q) acc[k++] = A[p] * A[q];
+#pragma unroll
+  for (int p = 0; p < 6; ++p) acc[21 + p] = A[p] * r;
+  acc[27] = r * r;
+}
+
+// deterministic block reduction of the 28 sums: butterfly inside the warp, then warps in index order
+__device__ __forceinline__ void block_reduce_sums(float *acc, float (*s_red)[kNumSums], float *out) {
+#pragma unroll
+  for (int k = 0; k < kNumSums; ++k) {
+    float v = acc[k];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    acc[k] = v;
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane == 0) {
+#pragma unroll
+    for (int k = 0; k < kNumSums; ++k) s_red[warp][k] = acc[k];
+  }
+  __syncthreads();
+  if (threadIdx.x < kNumSums) {
+    float v = 0.0f;
+#pragma unroll
+    for (int w = 0; w < kIcpBlock / 32; ++w) v += s_red[w][threadIdx.x];
+    out[threadIdx.x] = v;
+  }
+}
+
 template <bool kGrid>
 __global__ void __launch_bounds__(kIcpBlock) k_icp_knn_linearize(KnnArgs a) {
   __shared__ float4 s_t[kGrid ? 1 : kTgtTile];
@@ -540,44 +584,84 @@ __global__ void __launch_bounds__(kIcpBlock) k_icp_knn_linearize(KnnArgs a) {
   float acc[kNumSums];
 #pragma unroll
   for (int k = 0; k < kNumSums; ++k) acc[k] = 0.0f;
-  if (use) {
-    const float dx = __ldg(tp + (int64_t)bi * 3), dy = __ldg(tp + (int64_t)bi * 3 + 1), dz = __ldg(tp + (int64_t)bi * 3 + 2);
-    const float nx = __ldg(tn + (int64_t)bi * 3), ny = __ldg(tn + (int64_t)bi * 3 + 1), nz = __ldg(tn + (int64_t)bi * 3 + 2);
-    // rows of gauss_newton_solve (icputils.py:227-230)
-    float A[6];
-    A[0] = nx; A[1] = ny; A[2] = nz;
-    A[3] = nz * sy - ny * sz;
-    A[4] = nx * sz - nz * sx;
-    A[5] = ny * sx - nx * sy;
-    const float r = (nx * (dx - sx) + ny * (dy - sy)) + nz * (dz - sz);
-    int k = 0;
+  if (use) row_products(sx, sy, sz, tp, tn, (int64_t)bi, acc);
+  block_reduce_sums(acc, s_red, a.partials + ((int64_t)b * gridDim.x + blockIdx.x) * kNumSums);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// normal equations for a GIVEN association (the differentiable op of the taped ICP): forward + backward
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kIcpBlock) k_icp_linearize_idx(const float *src, int ns, const float *tp,
+                                                                 const float *tn, const int64_t *idx,
+                                                                 float *partials) {
+  __shared__ float s_red[kIcpBlock / 32][kNumSums];
+  const int i = blockIdx.x * kIcpBlock + threadIdx.x;
+  float acc[kNumSums];
 #pragma unroll
-    for (int p = 0; p < 6; ++p)
-#pragma unroll
-      for (int q = p; q < 6; ++q) acc[k++] = A[p] * A[q];
-#pragma unroll
-    for (int p = 0; p < 6; ++p) acc[21 + p] = A[p] * r;
-    acc[27] = r * r;
+  for (int k = 0; k < kNumSums; ++k) acc[k] = 0.0f;
+  if (i < ns) {
+    const int64_t j = idx[i];
+    if (j >= 0) row_products(src[(int64_t)i * 3], src[(int64_t)i * 3 + 1], src[(int64_t)i * 3 + 2], tp, tn, j, acc);
   }
-  // deterministic block reduction: butterfly inside the warp, then warps in index order
-#pragma unroll
-  for (int k = 0; k < kNumSums; ++k) {
-    float v = acc[k];
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    acc[k] = v;
-  }
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  if (lane == 0) {
-#pragma unroll
-    for (int k = 0; k < kNumSums; ++k) s_red[warp][k] = acc[k];
-  }
-  __syncthreads();
+  block_reduce_sums(acc, s_red, partials + (int64_t)blockIdx.x * kNumSums);
+}
+
+__global__ void k_icp_reduce_partials(const float *partials, int nblocks, float *sums) {
   if (threadIdx.x < kNumSums) {
     float v = 0.0f;
+    for (int j = 0; j < nblocks; ++j) v += partials[(int64_t)j * kNumSums + threadIdx.x];
+    sums[threadIdx.x] = v;
+  }
+}
+
+// d(loss)/d(source point), d/d(associated target point), d/d(associated target normal) from d(loss)/d(28 sums).
+// One thread per source point; the target gradients are written per SOURCE row (the caller scatters them with the
+// association), so there are no atomics.
+__global__ void __launch_bounds__(kIcpBlock) k_icp_linearize_bwd(const float *src, int ns, const float *tp,
+                                                                 const float *tn, const int64_t *idx, const float *g,
+                                                                 float *g_src, float *g_tp, float *g_tn) {
+  __shared__ float s_g[kNumSums];
+  if (threadIdx.x < kNumSums) s_g[threadIdx.x] = g[threadIdx.x];
+  __syncthreads();
+  const int i = blockIdx.x * kIcpBlock + threadIdx.x;
+  if (i >= ns) return;
+  float gs[3] = {0.f, 0.f, 0.f}, gp[3] = {0.f, 0.f, 0.f}, gn[3] = {0.f, 0.f, 0.f};
+  const int64_t j = idx[i];
+  if (j >= 0) {
+    const float sx = src[(int64_t)i * 3], sy = src[(int64_t)i * 3 + 1], sz = src[(int64_t)i * 3 + 2];
+    const float px = tp[j * 3], py = tp[j * 3 + 1], pz = tp[j * 3 + 2];
+    const float nx = tn[j * 3], ny = tn[j * 3 + 1], nz = tn[j * 3 + 2];
+    float A[6] = {nx, ny, nz, nz * sy - ny * sz, nx * sz - nz * sx, ny * sx - nx * sy};
+    const float r = (nx * (px - sx) + ny * (py - sy)) + nz * (pz - sz);
+    // dL/dA_p = sum_{q>=p} G[p,q] A_q + sum_{q<=p} G[q,p] A_q + h_p r ;  dL/dr = sum_p h_p A_p + 2 g_rr r
+    float a[6];
+    float gr = 2.0f * s_g[27] * r;
 #pragma unroll
-    for (int w = 0; w < kIcpBlock / 32; ++w) v += s_red[w][threadIdx.x];
-    a.partials[((int64_t)b * gridDim.x + blockIdx.x) * kNumSums + threadIdx.x] = v;
+    for (int p = 0; p < 6; ++p) {
+      float v = s_g[21 + p] * r;
+      gr += s_g[21 + p] * A[p];
+#pragma unroll
+      for (int q = 0; q < 6; ++q) {
+        const int lo = p < q ? p : q, hi = p < q ? q : p;
+        const int k = lo * 6 - lo * (lo - 1) / 2 + (hi - lo);  // index of (lo,hi) in the upper-triangular order
+        v += s_g[k] * A[q] * ((p == q) ? 2.0f : 1.0f);
+      }
+      a[p] = v;
+    }
+    // A3 = nz sy - ny sz, A4 = nx sz - nz sx, A5 = ny sx - nx sy ;  r = n . (p - s)
+    gs[0] = (-nz * a[4] + ny * a[5]) - gr * nx;
+    gs[1] = (nz * a[3] - nx * a[5]) - gr * ny;
+    gs[2] = (-ny * a[3] + nx * a[4]) - gr * nz;
+    gn[0] = (a[0] + sz * a[4] - sy * a[5]) + gr * (px - sx);
+    gn[1] = (a[1] - sz * a[3] + sx * a[5]) + gr * (py - sy);
+    gn[2] = (a[2] + sy * a[3] - sx * a[4]) + gr * (pz - sz);
+    gp[0] = gr * nx; gp[1] = gr * ny; gp[2] = gr * nz;
+  }
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    g_src[(int64_t)i * 3 + c] = gs[c];
+    g_tp[(int64_t)i * 3 + c] = gp[c];
+    g_tn[(int64_t)i * 3 + c] = gn[c];
   }
 }
 
@@ -1010,5 +1094,40 @@ extern "C" int gsx_knn1(const float *src_points, const int32_t *src_count, int n
     k_icp_knn_linearize<false><<<grid, kIcpBlock, 0, s>>>(ka);
   }
   GSX_CHECK_LAUNCH("gsx_knn1");
+  return 0;
+}
+
+extern "C" int64_t gsx_icp_normal_eq_scratch_bytes(int ns) {
+  if (ns < 1) return -1;
+  return (int64_t)((ns + kIcpBlock - 1) / kIcpBlock) * kNumSums * 4;
+}
+
+extern "C" int gsx_icp_normal_eq_fwd(const float *src_points, int ns, const float *tgt_points,
+                                     const float *tgt_normals, const int64_t *nn_idx, float *sums_out, void *scratch,
+                                     int64_t scratch_bytes, void *stream) {
+  GSX_CHECK_ARG(src_points && tgt_points && tgt_normals && nn_idx && sums_out && scratch,
+                "gsx_icp_normal_eq_fwd: null pointer");
+  GSX_CHECK_ARG(ns >= 1 && scratch_bytes >= gsx_icp_normal_eq_scratch_bytes(ns), "gsx_icp_normal_eq_fwd: bad sizes");
+  const int nblk = (ns + kIcpBlock - 1) / kIcpBlock;
+  cudaStream_t s = (cudaStream_t)stream;
+  k_icp_linearize_idx<<<nblk, kIcpBlock, 0, s>>>(src_points, ns, tgt_points, tgt_normals, nn_idx, (float *)scratch);
+  k_icp_reduce_partials<<<1, 32, 0, s>>>((const float *)scratch, nblk, sums_out);
+  GSX_CHECK_LAUNCH("gsx_icp_normal_eq_fwd");
+  return 0;
+}
+
+extern "C" int gsx_icp_normal_eq_bwd(const float *src_points, int ns, const float *tgt_points,
+                                     const float *tgt_normals, const int64_t *nn_idx, const float *g_sums,
+                                     float *g_src, float *g_tgt_points_rows, float *g_tgt_normals_rows,
+                                     void *stream) {
+  GSX_CHECK_ARG(src_points && tgt_points && tgt_normals && nn_idx && g_sums && g_src && g_tgt_points_rows &&
+                    g_tgt_normals_rows,
+                "gsx_icp_normal_eq_bwd: null pointer");
+  GSX_CHECK_ARG(ns >= 1, "gsx_icp_normal_eq_bwd: bad sizes");
+  const int nblk = (ns + kIcpBlock - 1) / kIcpBlock;
+  k_icp_linearize_bwd<<<nblk, kIcpBlock, 0, (cudaStream_t)stream>>>(src_points, ns, tgt_points, tgt_normals, nn_idx,
+                                                                    g_sums, g_src, g_tgt_points_rows,
+                                                                    g_tgt_normals_rows);
+  GSX_CHECK_LAUNCH("gsx_icp_normal_eq_bwd");
   return 0;
 }

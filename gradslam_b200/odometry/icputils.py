@@ -150,28 +150,87 @@ def _wants_grad(*tensors):
     return torch.is_grad_enabled() and any(torch.is_tensor(t) and t.requires_grad for t in tensors)
 
 
+class _NormalEqFn(torch.autograd.Function):
+    """(src (Ns,3), tgt (Nt,3), tgt_normals (Nt,3), nn_idx (Ns,) int64) -> the 28 sums of the point-to-plane normal
+    equations.  forward = gsx_icp_normal_eq_fwd, backward = gsx_icp_normal_eq_bwd (hand-written kernels)."""
+
+    @staticmethod
+    def forward(ctx, src, tgt, tgt_n, idx):
+        src_c, tgt_c, tn_c, idx_c = src.detach().contiguous(), tgt.detach().contiguous(), tgt_n.detach().contiguous(), \
+            idx.contiguous()
+        for name, t in (("src", src_c), ("tgt", tgt_c), ("tgt_normals", tn_c)):
+            _C.require_cuda(t, name)
+        ns, dev = src_c.shape[0], src_c.device
+        sums = torch.empty(28, dtype=torch.float32, device=dev)
+        lib = _C.lib()
+        nbytes = lib.gsx_icp_normal_eq_scratch_bytes(ns)
+        scratch = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        with torch.cuda.device(dev):
+            rc = lib.gsx_icp_normal_eq_fwd(_C.ptr(src_c), ns, _C.ptr(tgt_c), _C.ptr(tn_c), _C.ptr(idx_c), _C.ptr(sums),
+                                           _C.ptr(scratch), nbytes, _C.stream_ptr(dev))
+        _C.check(rc, "gsx_icp_normal_eq_fwd")
+        ctx.saved = (src_c, tgt_c, tn_c, idx_c)
+        return sums
+
+    @staticmethod
+    def backward(ctx, g):
+        src_c, tgt_c, tn_c, idx_c = ctx.saved
+        ns, dev = src_c.shape[0], src_c.device
+        g = g.contiguous().float()
+        g_src = torch.empty_like(src_c)
+        rows_p, rows_n = torch.empty_like(src_c), torch.empty_like(src_c)
+        with torch.cuda.device(dev):
+            rc = _C.lib().gsx_icp_normal_eq_bwd(_C.ptr(src_c), ns, _C.ptr(tgt_c), _C.ptr(tn_c), _C.ptr(idx_c), _C.ptr(g),
+                                                _C.ptr(g_src), _C.ptr(rows_p), _C.ptr(rows_n), _C.stream_ptr(dev))
+        _C.check(rc, "gsx_icp_normal_eq_bwd")
+        safe = idx_c.clamp(min=0)  # rows with idx < 0 carry zero gradients
+        g_tgt = torch.zeros_like(tgt_c).index_add_(0, safe, rows_p)
+        g_tn = torch.zeros_like(tn_c).index_add_(0, safe, rows_n)
+        return g_src, g_tgt, g_tn, None
+
+
+_TRIU = {}
+
+
+def _normal_equations(src, tgt, tgt_n, dist_thresh):
+    """Association (CUDA exact 1-NN, index-only) + the differentiable normal-equation op.  src (Ns,3)."""
+    d2, idx = knn1(src.detach().unsqueeze(0), tgt.detach().unsqueeze(0))
+    idx = idx[0]
+    if dist_thresh is not None:
+        idx = torch.where(d2[0] < dist_thresh, idx, torch.full_like(idx, -1))
+    sums = _NormalEqFn.apply(src, tgt, tgt_n, idx)
+    key = str(src.device)
+    if key not in _TRIU:
+        _TRIU[key] = torch.triu_indices(6, 6, device=src.device)
+    iu = _TRIU[key]
+    upper = torch.zeros(6, 6, dtype=sums.dtype, device=sums.device).index_put((iu[0], iu[1]), sums[:21])
+    M = upper + upper.t() - torch.diag(torch.diagonal(upper))
+    return M, sums[21:27].view(6, 1), sums[27], idx
+
+
 def _taped_icp(src_pc, tgt_pc, tgt_normals, initial_transform, mode, numiters, damp, dist_thresh, lambda_max=2.0,
                B=1.0, B2=1.0, nu=200.0):
-    """Differentiable variant used when an input requires grad: the association is the CUDA exact 1-NN (no gradient,
-    as in the reference), the rest of the LM / gradLM iteration is torch ops so PyTorch's tape yields the same
-    gradients as the reference (icputils.py:235-545).  Slower than the fused loop; forward values agree with it."""
+    """Differentiable variant used when an input requires grad.  The association is the CUDA exact 1-NN (no
+    gradient, as in the reference); the row build + A^T A / A^T b reduction is ONE op with hand-written forward and
+    backward kernels (`_NormalEqFn`); the 6x6 solve, se3_exp and the LM / gradLM gates are torch ops, so the tape yields
+    the gradients of the reference (icputils.py:235-545).  Slower than the fused loop; forward values agree with it."""
     from ..geometry.geometryutils import transform_pointcloud
     from ..geometry.se3utils import se3_exp
 
     dtype, device = src_pc.dtype, src_pc.device
     damp = torch.tensor(damp, dtype=dtype, device=device)
     lambda_min = 1 / lambda_max
+    eye6 = torch.eye(6, dtype=dtype, device=device)
     T = torch.eye(4, dtype=dtype, device=device) if initial_transform is None else initial_transform
     src = transform_pointcloud(src_pc[0], T)
+    tgt, tgt_n = tgt_pc[0], tgt_normals[0]
     idx = None
     for _ in range(numiters):
-        A, b, idx = gauss_newton_solve(src.unsqueeze(0), tgt_pc, tgt_normals, dist_thresh)
-        xi = solve_linear_system(A, b, damp)
+        M, rhs, err, idx = _normal_equations(src, tgt, tgt_n, dist_thresh)
+        xi = torch.inverse(M + eye6 * damp) @ rhs
         dT = se3_exp(xi)
-        err = torch.dot(b[:, 0], b[:, 0])
         one_step = transform_pointcloud(src, dT)
-        _, b1, _ = gauss_newton_solve(one_step.unsqueeze(0), tgt_pc, tgt_normals, dist_thresh)
-        new_err = torch.dot(b1[:, 0], b1[:, 0])
+        _, _, new_err, _ = _normal_equations(one_step, tgt, tgt_n, dist_thresh)
         if mode == 0:
             if new_err < err:
                 src, damp, T = one_step, damp / 2, torch.mm(dT, T)
@@ -184,7 +243,7 @@ def _taped_icp(src_pc, tgt_pc, tgt_normals, initial_transform, mode, numiters, d
             dT = se3_exp(sig * xi)
             src = transform_pointcloud(src, dT)
             T = torch.mm(dT, T)
-    return T, idx
+    return T, idx[idx >= 0]
 
 
 def _single(src_pc, tgt_pc, tgt_normals, initial_transform, mode, numiters, damp, dist_thresh, **kw):

@@ -188,6 +188,19 @@ int gsx_knn1(const float *src_points, const int32_t *src_count, int ns_stride, c
              const int32_t *tgt_count, int nt_stride, int B, int64_t *idx_out, float *d2_out, void *scratch,
              int64_t scratch_bytes, void *stream);
 
+/* K6 as a differentiable op: for a GIVEN association nn_idx (int64 (ns), -1 = row unused) reduce the point-to-plane
+ * rows A_i = [n, s x n], r_i = n.(p - s) (gauss_newton_solve, icputils.py:210-230) to the 28 sums
+ * [upper triangle of A^T A (21, row-major), A^T r (6), r^T r] (the matmuls of solve_linear_system, icputils.py:85-90).
+ * Backward: from d(loss)/d(sums) the gradient w.r.t. every source point (ns,3) and, per SOURCE row, w.r.t. its
+ * associated target point and normal (ns,3 each; the caller scatter-adds them through nn_idx).  Single clouds
+ * (B = 1), deterministic, no atomics.  scratch: gsx_icp_normal_eq_scratch_bytes(ns) bytes. */
+int64_t gsx_icp_normal_eq_scratch_bytes(int ns);
+int gsx_icp_normal_eq_fwd(const float *src_points, int ns, const float *tgt_points, const float *tgt_normals,
+                          const int64_t *nn_idx, float *sums_out, void *scratch, int64_t scratch_bytes, void *stream);
+int gsx_icp_normal_eq_bwd(const float *src_points, int ns, const float *tgt_points, const float *tgt_normals,
+                          const int64_t *nn_idx, const float *g_sums, float *g_src, float *g_tgt_points_rows,
+                          float *g_tgt_normals_rows, void *stream);
+
 /* full ICP / gradICP on given clouds.  initial_transform (B,16) or NULL (identity).  transform_out (B,16).
  * nn_idx_out optional int64 (B, ns_stride): association of the last iteration (-1 = filtered out).
  * scratch: gsx_icp_align_scratch_bytes(B, ns_stride, nt_stride) bytes. */

@@ -165,3 +165,40 @@ def test_pointfusion_map_gradients_match_oracle_autograd():
         pc2, _ = slam(gs.RGBDImages(rgb.to(DEV), depth.to(DEV), K.to(DEV), poses.to(DEV)))
     assert pc2.num_points_per_pointcloud.tolist() == [n]
     torch.testing.assert_close(pc2.points_list[0], pc.points_list[0].detach(), rtol=1e-6, atol=1e-6)
+
+
+def test_normal_equation_op_forward_and_backward():
+    """K6 as an op: the 28 sums and their hand-written backward against a plain torch construction of A, b
+    (icputils.py:210-230) and PyTorch autograd, including filtered rows (idx = -1) and shared targets."""
+    from gradslam_b200.odometry.icputils import _NormalEqFn
+
+    g = torch.Generator().manual_seed(7)
+    ns, nt = 700, 300
+    src = torch.randn(ns, 3, generator=g)
+    tgt = torch.randn(nt, 3, generator=g)
+    tn = torch.nn.functional.normalize(torch.randn(nt, 3, generator=g), dim=1)
+    idx = torch.randint(0, nt, (ns,), generator=g)
+    idx[::7] = -1
+    w = torch.randn(28, generator=g)
+
+    def ref(s, p, n):
+        keep = idx >= 0
+        s, pp, nn = s[keep], p[idx[keep]], n[idx[keep]]
+        sx, sy, sz = s[:, 0:1], s[:, 1:2], s[:, 2:3]
+        nx, ny, nz = nn[:, 0:1], nn[:, 1:2], nn[:, 2:3]
+        A = torch.cat([nx, ny, nz, nz * sy - ny * sz, nx * sz - nz * sx, ny * sx - nx * sy], 1)
+        b = nx * (pp[:, 0:1] - sx) + ny * (pp[:, 1:2] - sy) + nz * (pp[:, 2:3] - sz)
+        AtA, Atb = A.t() @ A, A.t() @ b
+        iu = torch.triu_indices(6, 6)
+        return torch.cat([AtA[iu[0], iu[1]], Atb[:, 0], (b * b).sum().view(1)])
+
+    a = [t.clone().double().requires_grad_(True) for t in (src, tgt, tn)]
+    want = ref(*a)
+    (want * w.double()).sum().backward()
+    b_ = [t.clone().to(DEV).requires_grad_(True) for t in (src, tgt, tn)]
+    got = _NormalEqFn.apply(b_[0], b_[1], b_[2], idx.to(DEV))
+    torch.testing.assert_close(got.cpu().double(), want.detach(), rtol=1e-4, atol=1e-3)
+    (got * w.to(DEV)).sum().backward()
+    for x, y in zip(b_, a):
+        scale = y.grad.abs().max().item()
+        torch.testing.assert_close(x.grad.cpu().double(), y.grad, rtol=1e-3, atol=1e-4 * scale)
