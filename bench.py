@@ -137,6 +137,10 @@ def run_reference(args, rank, world):
     sample_B, sample_L = 1, args.cpu_sample_frames
     # warm-up steps run a shorter sample; every timed step is the same bounded sample of the workload
     best_thread_count(args.height, args.width)  # doubles as warm-up
+    # keep the whole arm within ~2 minutes whatever --steps is: shrink the per-step sample if needed
+    _, dt4, _, _ = cpu_reference_run(1, 4, args.height, args.width)
+    budget_frames = int(120.0 / max(1, args.steps) / max(dt4 / 4.0, 1e-3))
+    sample_L = max(2, min(sample_L, budget_frames))
     vals = []
     for _ in range(max(1, args.steps)):
         fps, dt, cores, _ = cpu_reference_run(sample_B, sample_L, args.height, args.width)
