@@ -120,6 +120,8 @@ def _launch_merge_append(pointclouds, frames, vmap, nmap, sigma):
     rgb, c_bs = _frame_base(frames.rgb_image, P * 3)
     K = frames.intrinsics.contiguous()
     poses = None if vmap is not None else frames.poses.contiguous()
+    if vmap is not None:  # cached maps of a sliced sequence are strided views: the kernels want dense (B,H,W,3)
+        vmap, nmap = vmap.contiguous(), nmap.contiguous()
     st = pointclouds._store
     cin = pointclouds._counts_dev[pointclouds._cur]
     cout = pointclouds._counts_dev[pointclouds._cur ^ 1]
@@ -185,6 +187,8 @@ def _fused_update(pointclouds, frames, dist_th, dot_th, sigma):
     vmap, nmap = frames._global_vertex_map, frames._global_normal_map
     if vmap is None or nmap is None:
         vmap = nmap = None
+    else:
+        vmap, nmap = vmap.contiguous(), nmap.contiguous()
     if pointclouds._bound > 0:
         ws = _Workspace.get(dev, B, H, W)
         st = pointclouds._store

@@ -172,3 +172,27 @@ def test_update_map_fusion_threshold_monotonicity():
     assert (looser.num_points_per_pointcloud <= loose.num_points_per_pointcloud).all()
     assert (loose.num_points_per_pointcloud <= strict.num_points_per_pointcloud).all()
     assert (base.num_points_per_pointcloud == n0).all()  # inputs untouched
+
+
+def test_sliced_sequence_with_cached_maps():
+    """Maps computed once on the whole (B, L) RGBDImages and then sliced per frame are strided views; the fusion must
+    give the same bits as the on-the-fly path."""
+    import gradslam_b200 as gs
+
+    B, L, H, W = 2, 3, 32, 40
+    rgb, depth, K, poses = make_sequence(B, L, H, W, seed=23)
+    dev = _dev()
+    frames = _frames(gs, rgb, depth, K, poses, dev)
+    frames.global_vertex_map, frames.global_normal_map  # K1 over the full sequence; slices below are views
+    slam = gs.PointFusion(odom="gt", device=dev)
+    pc = gs.Pointclouds(device=dev)
+    for s in range(L):
+        live = frames[:, s]
+        assert not live.global_vertex_map.is_contiguous() or B == 1
+        pc, _ = slam.step(pc, live, None, inplace=True)
+    ref, _ = slam(_frames(gs, rgb, depth, K, poses, dev))
+    assert pc.num_points_per_pointcloud.tolist() == ref.num_points_per_pointcloud.tolist()
+    for b in range(B):
+        assert torch.equal(pc.points_list[b], ref.points_list[b])
+        assert torch.equal(pc.normals_list[b], ref.normals_list[b])
+        assert torch.equal(pc.features_list[b], ref.features_list[b])
