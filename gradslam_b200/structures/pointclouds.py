@@ -469,14 +469,15 @@ class Pointclouds(object):
         if not self.has_points:
             return other
         other._B = self._B
+        keep = max(self._N, 1)  # copy the populated rows only (one sync beats cloning gigabytes of spare capacity)
         for key in _ATTRS:
             st = self._store[key]
-            other._store[key] = None if st is None else fn(st)
+            other._store[key] = None if st is None else fn(st[:, :keep])
         other.device = other._store["points"].device
         other._counts_dev = self._counts_dev.clone().to(other.device)
         other._cur = self._cur
         other._counts_host = None if self._counts_host is None else list(self._counts_host)
-        other._bound = self._bound
+        other._bound = min(self._bound, keep)
         other._overflow = None if self._overflow is None else self._overflow.clone().to(other.device)
         other._uninit, other._tail_dirty = self._uninit, self._tail_dirty
         return other
