@@ -39,6 +39,7 @@ def parse():
     ap.add_argument("--cpu-sample-frames", type=int, default=12, help="frames of the CPU-baseline sample (B=1)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-icp", action="store_true", help="skip the secondary ICP-odometry measurement")
+    ap.add_argument("--no-raw", action="store_true", help="skip the dataset-native (uint8/uint16) ingest measurement")
     return ap.parse_args()
 
 
@@ -269,6 +270,24 @@ def main():
     run_steps(frames_host, 3, d2h=True)
     ms_e2e, res = timed(frames_host, args.steps, d2h=True)
 
+    # extra: the same job fed in dataset-native form (uint8 colour + uint16 depth, 5 B/pixel over PCIe instead of 16)
+    raw_extra = None
+    if not args.no_raw:
+        import numpy as np
+
+        from gradslam_b200.ingest import RawRGBD
+
+        col_u8 = torch.from_numpy((rgb_h.numpy() * 255.0).astype(np.uint8)).pin_memory()
+        dep_u16 = torch.from_numpy(np.round(depth_h.numpy()[..., 0] * 5000.0).astype(np.uint16)).pin_memory()
+        raw = RawRGBD(col_u8, dep_u16, K_h, poses_h, scaling_factor=5000.0)
+        run_steps(raw, 3, d2h=True)
+        ms_raw, _ = timed(raw, args.steps, d2h=True)
+        raw_extra = {"value": B * L * world * args.steps / (ms_raw / 1e3), "unit": UNIT, "ms_per_step": ms_raw / args.steps,
+                     "h2d_bytes_per_step": col_u8.numel() + dep_u16.numel() * 2 + (K_h.numel() + poses_h.numel()) * 4,
+                     "note": "PointFusion(odom='gt')(RawRGBD): uint8 colour + uint16 depth (TUM/ICL on-disk format, "
+                             "depth = u16/5000) uploaded from pinned memory and converted on the device"}
+        del raw, col_u8, dep_u16
+
     frames_per_step = B * L * world
     value = frames_per_step * args.steps / (ms_dev / 1e3)
     e2e = frames_per_step * args.steps / (ms_e2e / 1e3)
@@ -342,7 +361,7 @@ def main():
                     "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": 2 * L * args.steps - args.steps,  # K2/K3 + K4 per frame; K2 is skipped on the empty map
             "roofline": roofline, "cpu_baseline": cpu_baseline, "clocks": clocks, "kernels": kernels,
-            "icp_odometry": icp_extra,
+            "icp_odometry": icp_extra, "e2e_raw_ingest": raw_extra,
             "final_map_points_per_sequence": (frames_info[-1]["map_points"] + frames_info[-1]["new"]) // B
             if frames_info else None,
         }

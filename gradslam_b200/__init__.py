@@ -6,5 +6,5 @@ error behaviour; the arithmetic runs in hand-written CUDA kernels behind the C A
 """
 from .version import __version__
 from .structures import Pointclouds, RGBDImages, pointclouds_from_rgbdimages
-from . import geometry, odometry, slam
+from . import geometry, ingest, odometry, slam
 from .slam import ICPSLAM, PointFusion

@@ -43,24 +43,47 @@ class PointFusion(ICPSLAM):
     def _map(self, pointclouds: Pointclouds, live_frame: RGBDImages, inplace: bool = False):
         return update_map_fusion(pointclouds, live_frame, self.dist_th, self.dot_th, self.sigma, inplace)
 
-    def _forward_sequence(self, frames: RGBDImages, chunk: int = 4):
+    def forward(self, frames):
+        """As ICPSLAM.forward; additionally accepts a `gradslam_b200.ingest.RawRGBD` batch (uint8 colour + uint16 depth)
+        when odom='gt': the raw frames are uploaded and converted on the device, overlapped with the fusion."""
+        from ..ingest import RawRGBD
+
+        if isinstance(frames, RawRGBD):
+            if self.odom != "gt" or frames.poses is None:
+                raise ValueError("RawRGBD input is supported for odom='gt' with poses; convert with "
+                                 "ingest.rgbdimages_from_raw for the other odometry modes")
+            return self._forward_sequence(frames, raw=True)
+        return super().forward(frames)
+
+    def _forward_sequence(self, frames, chunk: int = 4, raw: bool = False):
         """odom='gt': the whole (B, L) sequence runs as C calls chaining K1 -> K2/K3 -> K4 per frame with no
         host synchronisation.  Frames that live in HOST memory are uploaded `chunk` frames at a time on a side
         stream, so the copy of chunk i+1 overlaps the fusion of chunk i (pin the host tensors for this)."""
         if self.odom != "gt" or frames.poses is None or torch.is_tensor(self.sigma):
             return None
-        if torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in (
-                frames.depth_image, frames.rgb_image, frames.poses, frames.intrinsics)):
-            return None  # differentiable mode goes through the per-frame step loop
-        if frames.channels_first:
-            frames = frames.to_channels_last()
         dev = self.device
-        B, L, H, W = frames.shape
+        if raw:
+            B, L, H, W = frames.shape
+            src_depth, src_rgb = frames.depths, frames.colors
+            if src_depth.device == dev:  # already uploaded: convert in one go
+                from ..ingest import raw_to_float
+
+                rgb_f, depth_f = raw_to_float(src_rgb, src_depth, frames.scaling_factor, frames.normalize_color)
+                return self._forward_sequence(RGBDImages(rgb_f, depth_f, frames.intrinsics.to(dev),
+                                                         frames.poses.to(dev)))
+            on_device = False
+        else:
+            if torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in (
+                    frames.depth_image, frames.rgb_image, frames.poses, frames.intrinsics)):
+                return None  # differentiable mode goes through the per-frame step loop
+            if frames.channels_first:
+                frames = frames.to_channels_last()
+            B, L, H, W = frames.shape
+            src_depth, src_rgb = frames.depth_image, frames.rgb_image
+            on_device = src_depth.device == dev
         P = H * W
         K = frames.intrinsics.to(dev).contiguous()
         poses = frames.poses.to(dev).contiguous()
-        src_depth, src_rgb = frames.depth_image, frames.rgb_image
-        on_device = src_depth.device == dev
         if on_device:
             depth, rgb = src_depth.contiguous(), src_rgb.contiguous()
             chunk = L
@@ -68,6 +91,9 @@ class PointFusion(ICPSLAM):
             depth = torch.empty((B, L, H, W, 1), dtype=torch.float32, device=dev)
             rgb = torch.empty((B, L, H, W, 3), dtype=torch.float32, device=dev)
             copy_stream = torch.cuda.Stream(device=dev)
+            if raw:  # staging buffers for the 5-byte pixels; converted chunk by chunk on the compute stream
+                raw_depth = torch.empty((B, L, H, W), dtype=src_depth.dtype, device=dev)
+                raw_rgb = torch.empty((B, L, H, W, 3), dtype=torch.uint8, device=dev)
         _C.require_cuda(depth, "depth_image")
         pc = Pointclouds(device=dev)
         pc._allocate(B, L * P, 1, zero=False)
@@ -81,9 +107,10 @@ class PointFusion(ICPSLAM):
                 with torch.cuda.stream(copy_stream):
                     for s0 in range(0, L, chunk):
                         s1 = min(L, s0 + chunk)
+                        dst_d, dst_c = (raw_depth, raw_rgb) if raw else (depth, rgb)
                         for b in range(B):  # per-element slices are contiguous: true async DMA from pinned memory
-                            depth[b, s0:s1].copy_(src_depth[b, s0:s1], non_blocking=True)
-                            rgb[b, s0:s1].copy_(src_rgb[b, s0:s1], non_blocking=True)
+                            dst_d[b, s0:s1].copy_(src_depth[b, s0:s1], non_blocking=True)
+                            dst_c[b, s0:s1].copy_(src_rgb[b, s0:s1], non_blocking=True)
                         ev = torch.cuda.Event()
                         ev.record(copy_stream)
                         ready.append(ev)
@@ -91,6 +118,12 @@ class PointFusion(ICPSLAM):
                 s1 = min(L, s0 + chunk)
                 if ready:
                     main.wait_event(ready[i])
+                if raw:  # u8 / u16 -> float32 for this chunk (per element: the chunk is contiguous inside an element)
+                    for b in range(B):
+                        _C.check(_C.lib().gsx_ingest_raw(
+                            _C.ptr(raw_rgb[b, s0:s1]), _C.ptr(raw_depth[b, s0:s1]), (s1 - s0) * P,
+                            frames.scaling_factor, 1 if frames.normalize_color else 0, _C.ptr(rgb[b, s0:s1]),
+                            _C.ptr(depth[b, s0:s1]), _C.stream_ptr(dev)), "gsx_ingest_raw")
                 rc = _C.lib().gsx_pointfusion_sequence_gt(
                     _C.ptr(st["points"]), _C.ptr(st["normals"]), _C.ptr(st["colors"]), _C.ptr(st["features"]),
                     _C.ptr(pc._counts_dev), pc.capacity, min(s0 * P, pc.capacity), _C.ptr(depth), _C.ptr(rgb),
@@ -99,8 +132,8 @@ class PointFusion(ICPSLAM):
                     _C.ptr(pc._overflow_flag()), _C.stream_ptr(dev))
                 _C.check(rc, "gsx_pointfusion_sequence_gt")
             if not on_device:
-                depth.record_stream(copy_stream)
-                rgb.record_stream(copy_stream)
+                for t in ((raw_depth, raw_rgb) if raw else (depth, rgb)):
+                    t.record_stream(copy_stream)
         pc._cur = L & 1
         pc._counts_host = None
         pc._bound = pc.capacity

@@ -127,6 +127,15 @@ int gsx_pointfusion_sequence_gt(float *map_points, float *map_normals, float *ma
                                 void *workspace, uint32_t epoch0, int32_t *overflow_flag, void *stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Dataset-native ingest: 8-bit colour (n_pixels,3) and 16-bit depth (n_pixels) as stored by
+ * ICL-NUIM / TUM / ScanNet -> float32 colour and depth on the device, bit-identical to the reference loaders'
+ * host-side conversion: colour = float(u8) [/ 255 if normalize_color], depth = float32(float64(u16) /
+ * depth_scaling_factor)   (gradslam/datasets/icl.py:467-513; tum.py and scannet.py alike).  16-byte aligned
+ * buffers take the vectorised path.  The image resize the loaders can also perform is not covered (pass frames at their final size). */
+int gsx_ingest_raw(const uint8_t *rgb_u8, const uint16_t *depth_u16, int64_t n_pixels, double depth_scaling_factor,
+                   int normalize_color, float *rgb_out, float *depth_out, void *stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Table-returning association steps (API parity with gradslam's module-level helpers; the fused path
  * above never materialises these tables).  Tables are int64 (rows,4) with rows [b, n, h, w].
  * replaces find_active_map_points gradslam/slam/fusionutils.py:198-287 (gsx_active_eval + compaction),
