@@ -267,6 +267,141 @@ __global__ void __launch_bounds__(kBlock, GSX_K2_MINB) k_project_select(ProjectA
   if ((threadIdx.x & 31) == 0 && n_active) atomicAdd(a.stats + 2 * b, (unsigned long long)n_active);
 }
 
+// ---- K2 with warp-level work queues ----------------------------------------------------------------------------
+// Same arithmetic as k_project_select<true>; the difference is SIMT density.  About a third of the map points fall
+// outside the frustum, so in the plain kernel the expensive part (frame sample, tests, CAS) runs with a third of the
+// lanes idle.  Here every warp pushes its in-frustum points into a small shared-memory queue and only runs the
+// expensive part on full batches of 32 items.
+#ifndef GSX_K2_QUEUE
+#define GSX_K2_QUEUE 0  // measured slower (127 us vs 113 us): SIMT density is not what limits K2
+#endif
+constexpr int kQCap = 64;  // per-warp queue capacity (invariant: fewer than 32 items before a push of <= 32)
+
+struct QueueItem {
+  MapPoint m;
+  int n, hw;  // hw = h << 16 | w
+};
+
+__global__ void __launch_bounds__(kBlock, GSX_K2_MINB) k_project_select_q(ProjectArgs a) {
+  __shared__ Rigid s_pose, s_tinv;
+  __shared__ float s_k[12];
+  __shared__ KInv s_kinv;
+  __shared__ float q_f[kBlock / 32][kQCap][7];
+  __shared__ int q_n[kBlock / 32][kQCap], q_hw[kBlock / 32][kQCap];
+  const int b = blockIdx.y;
+  const int count = a.counts[b];
+  if ((int64_t)blockIdx.x * kBlock >= count) return;
+  if (threadIdx.x == 0) {
+    s_pose = load_rigid(a.poses + b * a.pose_bstride);
+    s_tinv = rigid_inverse(s_pose);
+  }
+  if (threadIdx.x >= 32 && threadIdx.x < 44) s_k[threadIdx.x - 32] = __ldg(a.K + b * a.K_bstride + (threadIdx.x - 32));
+  if (threadIdx.x == 64) s_kinv = load_kinv(a.K + b * a.K_bstride);
+  __syncthreads();
+  const int P = a.H * a.W;
+  const float *pts = a.pts + (int64_t)b * a.cap * 3;
+  const float *nrm = a.nrm + (int64_t)b * a.cap * 3;
+  const float *cc = a.cc + (int64_t)b * a.cap;
+  const float *dimg = a.depth + b * a.depth_bstride;
+  U128 *best = a.best + (int64_t)b * P;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float (*qf)[7] = q_f[warp];
+  int *qn = q_n[warp], *qhw = q_hw[warp];
+  int qcount = 0;  // warp-uniform
+  unsigned int n_active = 0;
+  U128 mine{0ull, 0ull}, old{0ull, 0ull};
+  int pend_pix = -1;
+
+  // the expensive part for one dense item per lane
+  auto heavy = [&](int slot) {
+    MapPoint m;
+    m.px = qf[slot][0]; m.py = qf[slot][1]; m.pz = qf[slot][2];
+    m.mx = qf[slot][3]; m.my = qf[slot][4]; m.mz = qf[slot][5];
+    m.cc = qf[slot][6];
+    const int n = qn[slot], hw = qhw[slot];
+    const int h = hw >> 16, w = hw & 0xffff;
+    const FrameSample f = frame_sample<true>(dimg, s_kinv, &s_pose, h, w, a.H, a.W);
+    const float dx = f.gv.x - m.px, dy = f.gv.y - m.py, dz = f.gv.z - m.pz;
+    const float d2 = (dx * dx + dy * dy) + dz * dz;
+    const float dot = (f.gn.x * m.mx + f.gn.y * m.my) + f.gn.z * m.mz;
+    if (pend_pix >= 0) {
+      atomic_max_rec128_finish(best + pend_pix, mine, old);
+      pend_pix = -1;
+    }
+    if ((sqrtf(d2) < a.dist_th) && (dot > a.dot_th)) {
+      const float inv_cc = 1.0f / (m.cc + 1e-20f);
+      unsigned int kb = __float_as_uint(inv_cc);
+      kb = (kb & 0x80000000u) ? ~kb : (kb | 0x80000000u);
+      const unsigned int rb = __float_as_uint(d2) | 0x80000000u;
+      const unsigned long long hi = ((unsigned long long)kb << 32) | rb;
+      const int pix = h * a.W + w;
+      mine = U128{~(unsigned long long)n, ~hi};
+      old = cas128(best + pix, U128{0ull, 0ull}, mine);
+      pend_pix = pix;
+    }
+  };
+
+  const int64_t stride = (int64_t)gridDim.x * kBlock;
+  int64_t n = (int64_t)blockIdx.x * kBlock + threadIdx.x;
+  MapPoint cur = load_map_point(pts, nrm, cc, n < count ? n : 0);
+  for (int64_t base = (int64_t)blockIdx.x * kBlock; base < count; base += stride, n += stride) {
+    const MapPoint m = cur;
+    if (n + stride < count) cur = load_map_point(pts, nrm, cc, n + stride);
+    bool live = n < count;
+    int hw = 0;
+    if (live) {
+      const float3 q = rigid_apply(s_tinv, m.px, m.py, m.pz);
+      const float hx = ((s_k[0] * q.x + s_k[1] * q.y) + s_k[2] * q.z) + s_k[3];
+      const float hy = ((s_k[4] * q.x + s_k[5] * q.y) + s_k[6] * q.z) + s_k[7];
+      const float hz = ((s_k[8] * q.x + s_k[9] * q.y) + s_k[10] * q.z) + s_k[11];
+      const float den = (hz != 0.0f) ? hz : 1.0f;
+      const float u = hx / den, v = hy / den;
+      live = (u > -1e-3f) && (u < a.u_hi) && (v > -1e-3f) && (v < a.v_hi) && (q.z > 0.0f);
+      const int w = min(max((int)rintf(u), 0), a.W - 1);
+      const int h = min(max((int)rintf(v), 0), a.H - 1);
+      hw = (h << 16) | w;
+    }
+    const unsigned int ballot = __ballot_sync(0xffffffffu, live);
+    if (live) {
+      const int slot = qcount + __popc(ballot & ((1u << lane) - 1u));
+      qf[slot][0] = m.px; qf[slot][1] = m.py; qf[slot][2] = m.pz;
+      qf[slot][3] = m.mx; qf[slot][4] = m.my; qf[slot][5] = m.mz;
+      qf[slot][6] = m.cc;
+      qn[slot] = (int)n;
+      qhw[slot] = hw;
+    }
+    const int pushed = __popc(ballot);
+    qcount += pushed;
+    if (lane == 0) n_active += (unsigned int)pushed;
+    __syncwarp();
+    if (qcount >= 32) {
+      heavy(lane);
+      __syncwarp();
+      const int rest = qcount - 32;  // < 32: move the tail to the front
+      float t[7];
+      int tn = 0, th = 0;
+      if (lane < rest) {
+#pragma unroll
+        for (int j = 0; j < 7; ++j) t[j] = qf[32 + lane][j];
+        tn = qn[32 + lane];
+        th = qhw[32 + lane];
+      }
+      __syncwarp();
+      if (lane < rest) {
+#pragma unroll
+        for (int j = 0; j < 7; ++j) qf[lane][j] = t[j];
+        qn[lane] = tn;
+        qhw[lane] = th;
+      }
+      qcount = rest;
+      __syncwarp();
+    }
+  }
+  if (lane < qcount) heavy(lane);
+  if (pend_pix >= 0) atomic_max_rec128_finish(best + pend_pix, mine, old);
+  if (lane == 0 && n_active) atomicAdd(a.stats + 2 * b, (unsigned long long)n_active);
+}
+
 // ---- K4 -------------------------------------------------------------------------------------------------
 struct MergeArgs {
   float *pts, *nrm, *col, *cc;
@@ -632,6 +767,8 @@ int launch_project_select(const ProjectArgs &a, int64_t max_count, cudaStream_t 
   if (bx < 1) bx = 1;
   if (a.gv)
     k_project_select<false><<<dim3((unsigned)bx, (unsigned)a.B), kBlock, 0, stream>>>(a);
+  else if (GSX_K2_QUEUE && a.H < 65536 && a.W < 65536)
+    k_project_select_q<<<dim3((unsigned)bx, (unsigned)a.B), kBlock, 0, stream>>>(a);
   else
     k_project_select<true><<<dim3((unsigned)bx, (unsigned)a.B), kBlock, 0, stream>>>(a);
   GSX_CHECK_LAUNCH("gsx_fusion_project_select");
