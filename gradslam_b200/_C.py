@@ -40,6 +40,12 @@ SIGNATURES = {
     "gsx_fusion_merge_append": (
         c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_vp, c_i64, c_vp, c_i64, c_vp, c_i64, c_vp, c_i64, c_vp,
                 c_vp, c_int, c_int, c_int, c_double, c_vp, c_u32, c_vp, c_vp]),
+    "gsx_fusion_merge_append_fwd": (
+        c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_vp, c_i64, c_vp, c_i64, c_vp, c_i64, c_vp, c_vp, c_int,
+                c_int, c_int, c_double, c_vp, c_u32, c_vp, c_vp, c_vp]),
+    "gsx_fusion_merge_append_bwd": (
+        c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_vp, c_vp, c_vp, c_vp, c_i64, c_vp, c_vp, c_vp, c_vp,
+                c_int, c_int, c_int, c_double, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "gsx_pointfusion_sequence_gt": (
         c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_int,
                 c_int, c_float, c_float, c_double, c_vp, c_vp, c_u32, c_vp, c_vp]),
@@ -58,6 +64,15 @@ SIGNATURES = {
     "gsx_icp_normal_eq_scratch_bytes": (c_i64, [c_int]),
     "gsx_icp_normal_eq_fwd": (c_int, [c_vp, c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_vp]),
     "gsx_icp_normal_eq_bwd": (c_int, [c_vp, c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "gsx_icp_solve_fwd": (c_int, [c_vp, c_vp, c_int, c_vp, c_vp, c_vp]),
+    "gsx_icp_solve_bwd": (c_int, [c_vp, c_vp, c_int, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "gsx_icp_update_fwd": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_float, c_float, c_float, c_float,
+                                   c_vp, c_vp, c_vp, c_vp]),
+    "gsx_icp_update_bwd": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_float, c_float, c_float, c_float,
+                                   c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "gsx_rigid_transform_fwd": (c_int, [c_vp, c_i64, c_vp, c_vp, c_vp]),
+    "gsx_rigid_transform_bwd_scratch_bytes": (c_i64, [c_i64]),
+    "gsx_rigid_transform_bwd": (c_int, [c_vp, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_vp]),
     "gsx_icp_align_scratch_bytes": (c_i64, [c_int, c_int, c_int]),
     "gsx_icp_align": (
         c_int, [c_vp, c_vp, c_int, c_vp, c_vp, c_vp, c_int, c_int, c_vp, c_int, c_int, c_float, c_int, c_float,

@@ -422,6 +422,7 @@ struct MergeArgs {
   Workspace ws;
   unsigned int epoch;
   int32_t *overflow;
+  int32_t *assoc;  // optional (B,P): +row+1 appended at `row`, -(row+1) merged into `row`, 0 untouched (kAssoc only)
 };
 
 // alpha = clamp(exp(-|v|^2 / 2 sigma^2), 1e-7, 1.01) (fusionutils.py:69-72).  The exponential is evaluated in double and
@@ -557,7 +558,7 @@ __global__ void __launch_bounds__(kBlock, GSX_K4A_MINB) k_merge_only(MergeArgs a
   *cc = tot;
 }
 
-template <bool kFused, bool kDoMerge>
+template <bool kFused, bool kDoMerge, bool kAssoc = false>
 __global__ void __launch_bounds__(kMB, GSX_K4_MINB) k_merge_append(MergeArgs a) {
   __shared__ Rigid s_pose;
   __shared__ int s_tile;
@@ -702,6 +703,7 @@ __global__ void __launch_bounds__(kMB, GSX_K4_MINB) k_merge_append(MergeArgs a) 
       pts[n * 3 + 0] = ((c0 * mp[j][0]) + (alpha[j] * fp[j].x)) * inv;
       pts[n * 3 + 1] = ((c0 * mp[j][1]) + (alpha[j] * fp[j].y)) * inv;
       pts[n * 3 + 2] = ((c0 * mp[j][2]) + (alpha[j] * fp[j].z)) * inv;
+      if (kAssoc) a.assoc[(int64_t)b * P + pix[j]] = -(int32_t)(n + 1);
       nrm[n * 3 + 0] = ((c0 * mp[j][3]) + (alpha[j] * fn[j].x)) * inv;
       nrm[n * 3 + 1] = ((c0 * mp[j][4]) + (alpha[j] * fn[j].y)) * inv;
       nrm[n * 3 + 2] = ((c0 * mp[j][5]) + (alpha[j] * fn[j].z)) * inv;
@@ -744,6 +746,7 @@ __global__ void __launch_bounds__(kMB, GSX_K4_MINB) k_merge_append(MergeArgs a) 
         nrm[n * 3 + 0] = fn[j].x; nrm[n * 3 + 1] = fn[j].y; nrm[n * 3 + 2] = fn[j].z;
         col[n * 3 + 0] = fc[j].x; col[n * 3 + 1] = fc[j].y; col[n * 3 + 2] = fc[j].z;
         if (cc) cc[n] = alpha[j];
+        if (kAssoc) a.assoc[(int64_t)b * P + pix[j]] = (int32_t)(n + 1);
       } else {
         *a.overflow = 1;
       }
@@ -787,11 +790,136 @@ int launch_merge_append(const MergeArgs &a, cudaStream_t stream) {
   if (a.gv) k_merge_append<false, false><<<grid, kMB, 0, stream>>>(a);
   else k_merge_append<true, false><<<grid, kMB, 0, stream>>>(a);
 #else
-  if (a.gv) k_merge_append<false, true><<<grid, kMB, 0, stream>>>(a);
+  if (a.assoc) k_merge_append<false, true, true><<<grid, kMB, 0, stream>>>(a);  // differentiable forward (maps given)
+  else if (a.gv) k_merge_append<false, true><<<grid, kMB, 0, stream>>>(a);
   else k_merge_append<true, true><<<grid, kMB, 0, stream>>>(a);
 #endif
   GSX_CHECK_LAUNCH("gsx_fusion_merge_append");
   return 0;
+}
+
+// ---- K4 backward ------------------------------------------------------------------------------------------
+// The differentiable forward (k_merge_append<false, true, true>) leaves, per pixel, where its sample went:
+// merged into map row n (assoc = -(n+1)), appended as row n (assoc = n+1) or dropped (0).  With the pre-merge map
+// and the frame values the backward is a pure per-pixel / per-row map - no atomics, no scan:
+//   merged   out = (c*m + a*f) * inv,  inv = 1/(c+a)   (fusionutils.py:678-699)
+//            d m = g*c*inv      d f = g*a*inv      d c += g*(m*inv - num*inv^2)      d a += g*(f*inv - num*inv^2)
+//            cc_out = c + a  =>  d c += g_cc,  d a += g_cc
+//   appended out = f, cc_out = a   =>  d f = g,  d a = g_cc
+//   alpha    a = clamp(exp(-|v|^2 / 2 sigma^2), 1e-7, 1.01) (fusionutils.py:69-72)  =>  d v = d a * e * (-2 v / 2 sigma^2)
+//            inside the clamp range, 0 outside.
+struct MergeBwdArgs {
+  const int32_t *assoc;
+  const int32_t *counts_in;
+  const float *pts, *nrm, *col, *cc;  // pre-merge map (B, cap_in, .)
+  int64_t cap_in;
+  const float *g_pts, *g_nrm, *g_col, *g_cc;  // upstream gradients (B, cap_out, .); null = zero
+  int64_t cap_out;
+  const float *gv, *gn, *rgb, *vloc;  // frame values (B, P, 3)
+  float *d_pts, *d_nrm, *d_col, *d_cc;  // (B, cap_in, .)
+  float *d_gv, *d_gn, *d_rgb, *d_vloc;  // (B, P, 3)
+  int B, P;
+  float two_sigma_sq;
+};
+
+// rows the frame did not touch pass their gradient through; padding rows get zero
+__global__ void __launch_bounds__(256) k_merge_bwd_rows(MergeBwdArgs a) {
+  const int b = blockIdx.y;
+  const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= a.cap_in) return;
+  const bool live = n < a.counts_in[b] && n < a.cap_out;
+  const int64_t ri = (int64_t)b * a.cap_in + n, ro = (int64_t)b * a.cap_out + n;
+#pragma unroll
+  for (int q = 0; q < 3; ++q) {
+    a.d_pts[ri * 3 + q] = (live && a.g_pts) ? a.g_pts[ro * 3 + q] : 0.0f;
+    a.d_nrm[ri * 3 + q] = (live && a.g_nrm) ? a.g_nrm[ro * 3 + q] : 0.0f;
+    a.d_col[ri * 3 + q] = (live && a.g_col) ? a.g_col[ro * 3 + q] : 0.0f;
+  }
+  if (a.d_cc) a.d_cc[ri] = (live && a.g_cc) ? a.g_cc[ro] : 0.0f;
+}
+
+__global__ void __launch_bounds__(256) k_merge_bwd_pixels(MergeBwdArgs a) {
+  const int b = blockIdx.y;
+  const int pix = blockIdx.x * blockDim.x + threadIdx.x;
+  if (pix >= a.P) return;
+  const int64_t fi = ((int64_t)b * a.P + pix) * 3;
+  const int32_t as = a.assoc[(int64_t)b * a.P + pix];
+  float dgv[3] = {0.f, 0.f, 0.f}, dgn[3] = {0.f, 0.f, 0.f}, dc[3] = {0.f, 0.f, 0.f}, dv[3] = {0.f, 0.f, 0.f};
+  if (as != 0) {
+    const int64_t n = (as > 0) ? (int64_t)as - 1 : -(int64_t)as - 1;
+    const int64_t ro = (int64_t)b * a.cap_out + n;
+    float g[9];
+#pragma unroll
+    for (int q = 0; q < 3; ++q) {
+      g[q] = a.g_pts ? a.g_pts[ro * 3 + q] : 0.0f;
+      g[3 + q] = a.g_nrm ? a.g_nrm[ro * 3 + q] : 0.0f;
+      g[6 + q] = a.g_col ? a.g_col[ro * 3 + q] : 0.0f;
+    }
+    const float gcc = a.g_cc ? a.g_cc[ro] : 0.0f;
+    const float vx = a.vloc[fi], vy = a.vloc[fi + 1], vz = a.vloc[fi + 2];
+    const float sq = (vx * vx + vy * vy) + vz * vz;
+    const float e = (float)exp((double)((-sq) / a.two_sigma_sq));
+    float d_alpha = gcc;
+    if (as > 0) {
+#pragma unroll
+      for (int q = 0; q < 3; ++q) {
+        dgv[q] = g[q];
+        dgn[q] = g[3 + q];
+        dc[q] = g[6 + q];
+      }
+    } else {
+      const int64_t ri = (int64_t)b * a.cap_in + n;
+      const float alpha = fminf(fmaxf(e, 1e-7f), 1.01f);
+      const float c0 = a.cc[ri];
+      const float tot = c0 + alpha;
+      const bool degenerate = tot == 0.0f;
+      const float inv = 1.0f / (degenerate ? 1.0f : tot);
+      const float dinv = degenerate ? 0.0f : -(inv * inv);
+      float f[9], m[9];
+#pragma unroll
+      for (int q = 0; q < 3; ++q) {
+        f[q] = a.gv[fi + q];
+        f[3 + q] = a.gn[fi + q];
+        f[6 + q] = a.rgb[fi + q];
+        m[q] = a.pts[ri * 3 + q];
+        m[3 + q] = a.nrm[ri * 3 + q];
+        m[6 + q] = a.col[ri * 3 + q];
+      }
+      float d_c0 = gcc;
+      float dm[9], df[9];
+#pragma unroll
+      for (int q = 0; q < 9; ++q) {
+        const float num = c0 * m[q] + alpha * f[q];
+        dm[q] = g[q] * c0 * inv;
+        df[q] = g[q] * alpha * inv;
+        d_c0 += g[q] * (m[q] * inv + num * dinv);
+        d_alpha += g[q] * (f[q] * inv + num * dinv);
+      }
+#pragma unroll
+      for (int q = 0; q < 3; ++q) {
+        a.d_pts[ri * 3 + q] = dm[q];
+        a.d_nrm[ri * 3 + q] = dm[3 + q];
+        a.d_col[ri * 3 + q] = dm[6 + q];
+        dgv[q] = df[q];
+        dgn[q] = df[3 + q];
+        dc[q] = df[6 + q];
+      }
+      a.d_cc[ri] = d_c0;
+    }
+    if (e >= 1e-7f && e <= 1.01f) {
+      const float s = d_alpha * e * (-2.0f / a.two_sigma_sq);
+      dv[0] = s * vx;
+      dv[1] = s * vy;
+      dv[2] = s * vz;
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < 3; ++q) {
+    a.d_gv[fi + q] = dgv[q];
+    a.d_gn[fi + q] = dgn[q];
+    a.d_rgb[fi + q] = dc[q];
+    a.d_vloc[fi + q] = dv[q];
+  }
 }
 
 }  // namespace gsx
@@ -849,6 +977,60 @@ extern "C" int gsx_fusion_merge_append(float *map_points, float *map_normals, fl
   const Workspace ws = carve(workspace, B, H, W);
   MergeArgs a{map_points, map_normals, map_colors, map_ccounts, counts_in, counts_out, capacity, depth, depth_bstride,
               rgb, rgb_bstride, intrinsics, K_bstride, gvertex, gnormal, poses, pose_bstride, B, H, W,
-              (float)(2.0 * (sigma * sigma)), ws, epoch, overflow_flag};
+              (float)(2.0 * (sigma * sigma)), ws, epoch, overflow_flag, nullptr};
   return launch_merge_append(a, (cudaStream_t)stream);
+}
+
+extern "C" int gsx_fusion_merge_append_fwd(float *map_points, float *map_normals, float *map_colors,
+                                           float *map_ccounts, const int32_t *counts_in, int32_t *counts_out,
+                                           int64_t capacity, const float *depth, int64_t depth_bstride,
+                                           const float *rgb, int64_t rgb_bstride, const float *intrinsics,
+                                           int64_t K_bstride, const float *gvertex, const float *gnormal, int B, int H,
+                                           int W, double sigma, void *workspace, uint32_t epoch,
+                                           int32_t *overflow_flag, int32_t *assoc_out, void *stream) {
+  GSX_CHECK_ARG(B >= 0 && H >= 2 && W >= 2, "gsx_fusion_merge_append_fwd: bad extents B=%d H=%d W=%d", B, H, W);
+  if (B == 0) return 0;
+  GSX_CHECK_ARG(map_points && map_normals && map_colors && counts_in && counts_out,
+                "gsx_fusion_merge_append_fwd: null map pointer");
+  GSX_CHECK_ARG(counts_in != counts_out, "gsx_fusion_merge_append_fwd: counts_in and counts_out must not alias");
+  GSX_CHECK_ARG(depth && rgb && intrinsics && workspace && overflow_flag && gvertex && gnormal && assoc_out,
+                "gsx_fusion_merge_append_fwd: null frame pointer");
+  GSX_CHECK_ARG(epoch >= 1 && epoch < (1u << 30), "gsx_fusion_merge_append_fwd: epoch out of range");
+  const Workspace ws = carve(workspace, B, H, W);
+  MergeArgs a{map_points, map_normals, map_colors, map_ccounts, counts_in, counts_out, capacity, depth, depth_bstride,
+              rgb, rgb_bstride, intrinsics, K_bstride, gvertex, gnormal, nullptr, 0, B, H, W,
+              (float)(2.0 * (sigma * sigma)), ws, epoch, overflow_flag, assoc_out};
+  return launch_merge_append(a, (cudaStream_t)stream);
+}
+
+extern "C" int gsx_fusion_merge_append_bwd(const int32_t *assoc, const int32_t *counts_in, const float *map_points,
+                                           const float *map_normals, const float *map_colors, const float *map_ccounts,
+                                           int64_t capacity_in, const float *g_points, const float *g_normals,
+                                           const float *g_colors, const float *g_ccounts, int64_t capacity_out,
+                                           const float *gvertex, const float *gnormal, const float *rgb,
+                                           const float *vertex, int B, int H, int W, double sigma, float *d_map_points,
+                                           float *d_map_normals, float *d_map_colors, float *d_map_ccounts,
+                                           float *d_gvertex, float *d_gnormal, float *d_rgb, float *d_vertex,
+                                           void *stream) {
+  GSX_CHECK_ARG(B >= 0 && H >= 2 && W >= 2, "gsx_fusion_merge_append_bwd: bad extents B=%d H=%d W=%d", B, H, W);
+  if (B == 0) return 0;
+  GSX_CHECK_ARG(assoc && counts_in && gvertex && gnormal && rgb && vertex, "gsx_fusion_merge_append_bwd: null input");
+  GSX_CHECK_ARG(d_gvertex && d_gnormal && d_rgb && d_vertex, "gsx_fusion_merge_append_bwd: null frame gradient");
+  GSX_CHECK_ARG(capacity_in == 0 || (map_points && map_normals && map_colors && d_map_points && d_map_normals &&
+                                     d_map_colors),
+                "gsx_fusion_merge_append_bwd: null map pointer");
+  GSX_CHECK_ARG((map_ccounts == nullptr) == (d_map_ccounts == nullptr),
+                "gsx_fusion_merge_append_bwd: ccounts and their gradient must both be given or both be null");
+  MergeBwdArgs a{assoc, counts_in, map_points, map_normals, map_colors, map_ccounts, capacity_in, g_points, g_normals,
+                 g_colors, g_ccounts, capacity_out, gvertex, gnormal, rgb, vertex, d_map_points, d_map_normals,
+                 d_map_colors, d_map_ccounts, d_gvertex, d_gnormal, d_rgb, d_vertex, B, H * W,
+                 (float)(2.0 * (sigma * sigma))};
+  cudaStream_t st = (cudaStream_t)stream;
+  if (capacity_in > 0) {
+    k_merge_bwd_rows<<<dim3((unsigned)((capacity_in + 255) / 256), (unsigned)B), 256, 0, st>>>(a);
+    GSX_CHECK_LAUNCH("gsx_fusion_merge_append_bwd(rows)");
+  }
+  k_merge_bwd_pixels<<<dim3((unsigned)((a.P + 255) / 256), (unsigned)B), 256, 0, st>>>(a);
+  GSX_CHECK_LAUNCH("gsx_fusion_merge_append_bwd(pixels)");
+  return 0;
 }

@@ -189,60 +189,134 @@ class _NormalEqFn(torch.autograd.Function):
         return g_src, g_tgt, g_tn, None
 
 
-_TRIU = {}
+class _SolveFn(torch.autograd.Function):
+    """(28 sums, damp) -> (xi (6,), dT (4,4)): damped 6x6 solve + se3_exp in one kernel (K7a).
+    forward = gsx_icp_solve_fwd, backward = gsx_icp_solve_bwd (dual numbers, one lane per input)."""
+
+    @staticmethod
+    def forward(ctx, sums, damp):
+        s, d = sums.detach().contiguous().float(), damp.detach().reshape(1).contiguous().float()
+        _C.require_cuda(s, "sums")
+        dev = s.device
+        xi = torch.empty(6, dtype=torch.float32, device=dev)
+        dT = torch.empty((4, 4), dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            rc = _C.lib().gsx_icp_solve_fwd(_C.ptr(s), _C.ptr(d), 1, _C.ptr(xi), _C.ptr(dT), _C.stream_ptr(dev))
+        _C.check(rc, "gsx_icp_solve_fwd")
+        ctx.saved = (s, d, damp.shape)
+        return xi, dT
+
+    @staticmethod
+    def backward(ctx, g_xi, g_dT):
+        s, d, damp_shape = ctx.saved
+        dev = s.device
+        g_xi = None if g_xi is None else g_xi.contiguous().float()
+        g_dT = None if g_dT is None else g_dT.contiguous().float()
+        g_s, g_d = torch.empty_like(s), torch.empty_like(d)
+        with torch.cuda.device(dev):
+            rc = _C.lib().gsx_icp_solve_bwd(_C.ptr(s), _C.ptr(d), 1, _C.ptr(g_xi), _C.ptr(g_dT), _C.ptr(g_s),
+                                            _C.ptr(g_d), _C.stream_ptr(dev))
+        _C.check(rc, "gsx_icp_solve_bwd")
+        return g_s, g_d.view(damp_shape)
+
+
+class _UpdateFn(torch.autograd.Function):
+    """(xi, err, new_err, damp, T) -> (new damp, applied step (4,4), step @ T): LM accept / reject (mode 0) or the
+    gradLM gates (mode 1), the applied se3_exp and the pose accumulation in one kernel (K7b).
+    forward = gsx_icp_update_fwd, backward = gsx_icp_update_bwd."""
+
+    @staticmethod
+    def forward(ctx, xi, err, new_err, damp, T, mode, lambda_max, B, B2, nu):
+        dev = xi.device
+        ins = [t.detach().reshape(n).contiguous().float() for t, n in ((xi, 6), (err, 1), (new_err, 1), (damp, 1),
+                                                                       (T, 16))]
+        _C.require_cuda(ins[0], "xi")
+        damp_out = torch.empty(1, dtype=torch.float32, device=dev)
+        dT = torch.empty((4, 4), dtype=torch.float32, device=dev)
+        Tn = torch.empty((4, 4), dtype=torch.float32, device=dev)
+        par = (int(mode), float(lambda_max), float(B), float(B2), float(nu))
+        with torch.cuda.device(dev):
+            rc = _C.lib().gsx_icp_update_fwd(*[_C.ptr(t) for t in ins], 1, *par, _C.ptr(damp_out), _C.ptr(dT),
+                                             _C.ptr(Tn), _C.stream_ptr(dev))
+        _C.check(rc, "gsx_icp_update_fwd")
+        ctx.saved = (ins, par, (xi.shape, err.shape, new_err.shape, damp.shape, T.shape))
+        return damp_out.view(damp.shape), dT, Tn
+
+    @staticmethod
+    def backward(ctx, g_damp, g_dT, g_T):
+        ins, par, shapes = ctx.saved
+        dev = ins[0].device
+        gs = [None if g is None else g.contiguous().float() for g in (g_damp, g_dT, g_T)]
+        outs = [torch.empty_like(t) for t in ins]
+        with torch.cuda.device(dev):
+            rc = _C.lib().gsx_icp_update_bwd(*[_C.ptr(t) for t in ins], 1, *par, *[_C.ptr(g) for g in gs],
+                                             *[_C.ptr(o) for o in outs], _C.stream_ptr(dev))
+        _C.check(rc, "gsx_icp_update_bwd")
+        return tuple(o.view(sh) for o, sh in zip(outs, shapes)) + (None,) * 5
+
+
+class _RigidTransformFn(torch.autograd.Function):
+    """(points (N,3), T (4,4)) -> R p + t (transform_pointcloud, geometryutils.py:737-794).
+    forward = gsx_rigid_transform_fwd, backward = gsx_rigid_transform_bwd (deterministic reduction for d/dT)."""
+
+    @staticmethod
+    def forward(ctx, points, T):
+        p, Tc = points.detach().contiguous().float(), T.detach().contiguous().float()
+        _C.require_cuda(p, "points")
+        dev = p.device
+        out = torch.empty_like(p)
+        with torch.cuda.device(dev):
+            rc = _C.lib().gsx_rigid_transform_fwd(_C.ptr(p), p.shape[0], _C.ptr(Tc), _C.ptr(out), _C.stream_ptr(dev))
+        _C.check(rc, "gsx_rigid_transform_fwd")
+        ctx.saved = (p, Tc)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        p, Tc = ctx.saved
+        dev, n = p.device, p.shape[0]
+        g = g.contiguous().float()
+        g_p, g_T = torch.empty_like(p), torch.empty_like(Tc)
+        lib = _C.lib()
+        nbytes = lib.gsx_rigid_transform_bwd_scratch_bytes(n)
+        scratch = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        with torch.cuda.device(dev):
+            rc = lib.gsx_rigid_transform_bwd(_C.ptr(p), n, _C.ptr(Tc), _C.ptr(g), _C.ptr(g_p), _C.ptr(g_T),
+                                             _C.ptr(scratch), nbytes, _C.stream_ptr(dev))
+        _C.check(rc, "gsx_rigid_transform_bwd")
+        return g_p, g_T
 
 
 def _normal_equations(src, tgt, tgt_n, dist_thresh):
-    """Association (CUDA exact 1-NN, index-only) + the differentiable normal-equation op.  src (Ns,3)."""
+    """Association (CUDA exact 1-NN, index-only) + the differentiable normal-equation op.  src (Ns,3) -> 28 sums."""
     d2, idx = knn1(src.detach().unsqueeze(0), tgt.detach().unsqueeze(0))
     idx = idx[0]
     if dist_thresh is not None:
         idx = torch.where(d2[0] < dist_thresh, idx, torch.full_like(idx, -1))
-    sums = _NormalEqFn.apply(src, tgt, tgt_n, idx)
-    key = str(src.device)
-    if key not in _TRIU:
-        _TRIU[key] = torch.triu_indices(6, 6, device=src.device)
-    iu = _TRIU[key]
-    upper = torch.zeros(6, 6, dtype=sums.dtype, device=sums.device).index_put((iu[0], iu[1]), sums[:21])
-    M = upper + upper.t() - torch.diag(torch.diagonal(upper))
-    return M, sums[21:27].view(6, 1), sums[27], idx
+    return _NormalEqFn.apply(src, tgt, tgt_n, idx), idx
 
 
 def _taped_icp(src_pc, tgt_pc, tgt_normals, initial_transform, mode, numiters, damp, dist_thresh, lambda_max=2.0,
                B=1.0, B2=1.0, nu=200.0):
-    """Differentiable variant used when an input requires grad.  The association is the CUDA exact 1-NN (no
-    gradient, as in the reference); the row build + A^T A / A^T b reduction is ONE op with hand-written forward and
-    backward kernels (`_NormalEqFn`); the 6x6 solve, se3_exp and the LM / gradLM gates are torch ops, so the tape yields
-    the gradients of the reference (icputils.py:235-545).  Slower than the fused loop; forward values agree with it."""
-    from ..geometry.geometryutils import transform_pointcloud
-    from ..geometry.se3utils import se3_exp
-
-    dtype, device = src_pc.dtype, src_pc.device
-    damp = torch.tensor(damp, dtype=dtype, device=device)
-    lambda_min = 1 / lambda_max
-    eye6 = torch.eye(6, dtype=dtype, device=device)
-    T = torch.eye(4, dtype=dtype, device=device) if initial_transform is None else initial_transform
-    src = transform_pointcloud(src_pc[0], T)
+    """Differentiable variant used when an input requires grad: the same loop as the fused kernel sequence, as a chain
+    of autograd ops that each have a hand-written forward AND backward kernel -
+    rigid transform (`_RigidTransformFn`), 1-NN association (index-only, no gradient, as in the reference), normal
+    equations (`_NormalEqFn`), damped solve + se3_exp (`_SolveFn`), LM / gradLM update (`_UpdateFn`).  PyTorch only
+    records the tape; no ATen arithmetic runs between the ops and there is no host synchronisation
+    (icputils.py:235-545)."""
+    dtype, device = torch.float32, src_pc.device
+    damp = torch.tensor([float(damp)], dtype=dtype, device=device)
+    T = torch.eye(4, dtype=dtype, device=device) if initial_transform is None else initial_transform.to(dtype)
+    src = _RigidTransformFn.apply(src_pc[0], T)
     tgt, tgt_n = tgt_pc[0], tgt_normals[0]
     idx = None
     for _ in range(numiters):
-        M, rhs, err, idx = _normal_equations(src, tgt, tgt_n, dist_thresh)
-        xi = torch.inverse(M + eye6 * damp) @ rhs
-        dT = se3_exp(xi)
-        one_step = transform_pointcloud(src, dT)
-        _, _, new_err, _ = _normal_equations(one_step, tgt, tgt_n, dist_thresh)
-        if mode == 0:
-            if new_err < err:
-                src, damp, T = one_step, damp / 2, torch.mm(dT, T)
-            else:
-                damp = damp * 2
-        else:
-            diff = (new_err - err).clamp(-70.0, 70.0)
-            damp = damp * (lambda_min + (lambda_max - lambda_min) / (1 + torch.exp(-B * diff)))
-            sig = 1 / ((1 + torch.exp(-B2 * diff)) ** (1 / nu))
-            dT = se3_exp(sig * xi)
-            src = transform_pointcloud(src, dT)
-            T = torch.mm(dT, T)
+        sums, idx = _normal_equations(src, tgt, tgt_n, dist_thresh)
+        xi, dT = _SolveFn.apply(sums, damp)
+        one_step = _RigidTransformFn.apply(src, dT)
+        sums_next, _ = _normal_equations(one_step, tgt, tgt_n, dist_thresh)
+        damp, dT_applied, T = _UpdateFn.apply(xi, sums[27], sums_next[27], damp, T, mode, lambda_max, B, B2, nu)
+        src = _RigidTransformFn.apply(src, dT_applied)
     return T, idx[idx >= 0]
 
 

@@ -376,6 +376,8 @@ def fuse_with_map(pointclouds: Pointclouds, rgbdimages: RGBDImages, pc2im_bnhw: 
     _check_frame(rgbdimages)
     if not inplace:
         pointclouds = pointclouds.clone()
+    if _wants_grad(pointclouds, rgbdimages) and rgbdimages.poses is not None:
+        return _update_differentiable(pointclouds, rgbdimages, sigma, True, table=pc2im_bnhw)
     frames = rgbdimages.to_channels_last()
     _C.require_cuda(frames.depth_image, "depth_image")
     B, _, H, W = frames.shape
@@ -404,48 +406,114 @@ def _wants_grad(pointclouds, frames):
     return any(torch.is_tensor(t) and t.requires_grad for t in ts)
 
 
-def _append_differentiable(pointclouds, frames, with_features, sigma):
-    """Appends every valid pixel through differentiable torch indexing of the K1 maps (which carry their hand-written
-    backward).  Used only when a gradient is requested; values equal the kernel path."""
-    frames = frames.to_channels_last()
-    B = len(frames)
-    gv, gn, col = frames.global_vertex_map[:, 0], frames.global_normal_map[:, 0], frames.rgb_image[:, 0]
-    mask = frames.valid_depth_mask[:, 0, ..., 0]
-    feats = None
-    if with_features:
-        alpha = get_alpha(frames.vertex_map[:, 0], sigma, dim=-1, keepdim=True)
-        feats = [alpha[i][mask[i]] for i in range(B)]
-    fresh = Pointclouds([gv[i][mask[i]] for i in range(B)], [gn[i][mask[i]] for i in range(B)],
-                        [col[i][mask[i]] for i in range(B)], feats)
-    return pointclouds.append_points(fresh)
+class _MergeAppendFn(torch.autograd.Function):
+    """K4 as one differentiable op: (pre-merge map, frame maps) -> updated map.  forward =
+    gsx_fusion_merge_append_fwd on a copy of the map (also records where every pixel went), backward =
+    gsx_fusion_merge_append_bwd; both hand-written kernels.  The per-pixel winners must already sit in the fusion
+    workspace (K2, or gsx_records_from_table); they are index-only, as in the reference (fusionutils.py:523)."""
+
+    @staticmethod
+    def forward(ctx, pack, pts, nrm, col, cc, gv, gn, rgb, vloc):
+        pointclouds, frames, sigma = pack
+        B, _, H, W = frames.shape
+        P = H * W
+        dev = pts.device
+        bound, cap_in, cap_out = pointclouds._bound, pts.shape[1], pointclouds._bound + P
+        outs = []
+        for t in (pts, nrm, col, cc):
+            if t is None:
+                outs.append(None)
+                continue
+            o = torch.zeros((B, cap_out, t.shape[2]), dtype=torch.float32, device=dev)
+            if bound > 0:
+                o[:, :bound] = t.detach()[:, :bound]
+            outs.append(o)
+        gv_c, gn_c, rgb_c, vloc_c = (t.detach().contiguous() for t in (gv, gn, rgb, vloc))
+        depth, d_bs = _frame_base(frames.depth_image.detach(), P)
+        K = frames.intrinsics.detach().contiguous()
+        ws = _Workspace.get(dev, B, H, W)
+        counts_in = pointclouds._counts_dev[pointclouds._cur].clone()
+        counts_out = pointclouds._counts_dev[pointclouds._cur ^ 1]
+        assoc = torch.zeros((B, P), dtype=torch.int32, device=dev)
+        with torch.cuda.device(dev):
+            rc = _C.lib().gsx_fusion_merge_append_fwd(
+                _C.ptr(outs[0]), _C.ptr(outs[1]), _C.ptr(outs[2]), _C.ptr(outs[3]), _C.ptr(counts_in),
+                _C.ptr(counts_out), cap_out, _C.ptr(depth), d_bs, _C.ptr(rgb_c), P * 3, _C.ptr(K), 16, _C.ptr(gv_c),
+                _C.ptr(gn_c), B, H, W, float(sigma), _C.ptr(ws.buf), ws.next_epochs(1),
+                _C.ptr(pointclouds._overflow_flag()), _C.ptr(assoc), _C.stream_ptr(dev))
+        _C.check(rc, "gsx_fusion_merge_append_fwd")
+        ctx.saved = (assoc, counts_in, pts.detach(), nrm.detach(), col.detach(), None if cc is None else cc.detach(),
+                     gv_c, gn_c, rgb_c, vloc_c)
+        ctx.dims = (B, H, W, cap_in, cap_out, float(sigma))
+        ctx.shapes = (gv.shape, rgb.shape)
+        return tuple(outs)
+
+    @staticmethod
+    def backward(ctx, g_pts, g_nrm, g_col, g_cc):
+        assoc, counts_in, pts, nrm, col, cc, gv, gn, rgb, vloc = ctx.saved
+        B, H, W, cap_in, cap_out, sigma = ctx.dims
+        dev = assoc.device
+        gs = [None if g is None else g.contiguous().float() for g in (g_pts, g_nrm, g_col, g_cc)]
+        pts_c, nrm_c, col_c = pts.contiguous(), nrm.contiguous(), col.contiguous()
+        cc_c = None if cc is None else cc.contiguous()
+        d_map = [torch.empty_like(t) for t in (pts_c, nrm_c, col_c)] + [None if cc_c is None else torch.empty_like(cc_c)]
+        d_frame = [torch.empty((B, 1, H, W, 3), dtype=torch.float32, device=dev) for _ in range(4)]
+        with torch.cuda.device(dev):
+            rc = _C.lib().gsx_fusion_merge_append_bwd(
+                _C.ptr(assoc), _C.ptr(counts_in), _C.ptr(pts_c), _C.ptr(nrm_c), _C.ptr(col_c), _C.ptr(cc_c), cap_in,
+                _C.ptr(gs[0]), _C.ptr(gs[1]), _C.ptr(gs[2]), _C.ptr(gs[3]), cap_out, _C.ptr(gv), _C.ptr(gn),
+                _C.ptr(rgb), _C.ptr(vloc), B, H, W, sigma, _C.ptr(d_map[0]), _C.ptr(d_map[1]), _C.ptr(d_map[2]),
+                _C.ptr(d_map[3]), _C.ptr(d_frame[0]), _C.ptr(d_frame[1]), _C.ptr(d_frame[2]), _C.ptr(d_frame[3]),
+                _C.stream_ptr(dev))
+        _C.check(rc, "gsx_fusion_merge_append_bwd")
+        gv_shape, rgb_shape = ctx.shapes
+        return (None, d_map[0], d_map[1], d_map[2], d_map[3], d_frame[0].view(gv_shape), d_frame[1].view(gv_shape),
+                d_frame[2].view(rgb_shape), d_frame[3].view(gv_shape))
 
 
-def _fuse_differentiable(pointclouds, frames, table, sigma):
-    """fuse_with_map as out-of-place torch ops on the rows named by `table` (fusionutils.py:654-720), so PyTorch's
-    tape links the fused map to depth / poses / colours and to the previous map.  The association (`table`) comes
-    from the CUDA kernels and is index-only, as in the reference."""
+def _update_differentiable(pointclouds, frames, sigma, with_features, dist_th=None, dot_th=None, table=None):
+    """Map update when a gradient is requested: K1 (differentiable op) -> association (K2 kernel, or the rows of
+    `table`; index-only) -> K4 (differentiable op), out of place so the pre-merge map survives for the backward.
+    Values equal the in-place kernel path bit for bit."""
     frames = frames.to_channels_last()
-    B = len(frames)
-    gv, gn, col = frames.global_vertex_map[:, 0], frames.global_normal_map[:, 0], frames.rgb_image[:, 0]
-    alpha = get_alpha(frames.vertex_map[:, 0], sigma, dim=-1, keepdim=True)  # (B,H,W,1)
-    new_mask = frames.valid_depth_mask[:, 0, ..., 0].clone()
+    _C.require_cuda(frames.depth_image, "depth_image")
+    B, _, H, W = frames.shape
+    P = H * W
     if not pointclouds.has_points:
         pointclouds.device = frames.device
+        pointclouds._allocate(B, 1, 1 if with_features else 0)
+    elif len(pointclouds) != B:
+        raise ValueError("Expected equal batch sizes for pointclouds and rgbdimages. Got {0} and {1} "
+                         "respectively.".format(len(pointclouds), B))
+    dev = pointclouds.device
     st = pointclouds._store
-    if pointclouds.has_points and table.shape[0] != 0:
-        b, n, h, w = table.unbind(1)
-        cc = st["features"][b, n]
-        a = alpha[b, h, w]
-        tot = cc + a
-        inv = 1 / torch.where(tot == 0, torch.ones_like(tot), tot)
-        for key, fmap in (("points", gv), ("normals", gn), ("colors", col)):
-            st[key] = st[key].index_put((b, n), ((cc * st[key][b, n]) + (a * fmap[b, h, w])) * inv)
-        st["features"] = st["features"].index_put((b, n), tot)
-        pointclouds._list_cache = {}
-        new_mask[b, h, w] = False
-    fresh = Pointclouds([gv[i][new_mask[i]] for i in range(B)], [gn[i][new_mask[i]] for i in range(B)],
-                        [col[i][new_mask[i]] for i in range(B)], [alpha[i][new_mask[i]] for i in range(B)])
-    return pointclouds.append_points(fresh)
+    gv, gn, vloc = frames.global_vertex_map, frames.global_normal_map, frames.vertex_map  # K1, carries its backward
+    ws = _Workspace.get(dev, B, H, W)
+    if pointclouds._bound > 0 and table is not None and table.shape[0] != 0:
+        table = table.to(dev).contiguous()
+        with torch.cuda.device(dev):
+            rc = _C.lib().gsx_records_from_table(_C.ptr(table), table.shape[0], pointclouds.capacity, B, H, W,
+                                                 _C.ptr(ws.buf), _C.stream_ptr(dev))
+        _C.check(rc, "gsx_records_from_table")
+    elif pointclouds._bound > 0 and dist_th is not None:
+        pts, nrm, ccs = (st[k].detach().contiguous() for k in ("points", "normals", "features"))
+        K = frames.intrinsics.detach().contiguous()
+        poses = frames.poses.detach().contiguous()
+        depth, d_bs = _frame_base(frames.depth_image.detach(), P)
+        gvd, gnd = gv.detach().contiguous(), gn.detach().contiguous()
+        with torch.cuda.device(dev):
+            rc = _C.lib().gsx_fusion_project_select(
+                _C.ptr(pts), _C.ptr(nrm), _C.ptr(ccs), _C.ptr(pointclouds._counts_dev[pointclouds._cur]),
+                pointclouds.capacity, pointclouds._bound, _C.ptr(poses), 16, _C.ptr(K), 16, _C.ptr(depth), d_bs,
+                _C.ptr(gvd), _C.ptr(gnd), B, H, W, float(dist_th), float(dot_th), _C.ptr(ws.buf), _C.stream_ptr(dev))
+        _C.check(rc, "gsx_fusion_project_select")
+    outs = _MergeAppendFn.apply((pointclouds, frames, sigma), st["points"], st["normals"], st["colors"],
+                                st["features"], gv, gn, frames.rgb_image, vloc)
+    for key, o in zip(("points", "normals", "colors", "features"), outs):
+        st[key] = o
+    pointclouds._uninit = False
+    pointclouds._mark_device_updated(pointclouds._bound + P)
+    return pointclouds
 
 
 # --------------------------------------------------------------------------------------------- public ops
@@ -459,7 +527,7 @@ def update_map_aggregate(pointclouds: Pointclouds, rgbdimages: RGBDImages, inpla
         pointclouds = pointclouds.clone()
     if _wants_grad(pointclouds, rgbdimages):
         _check_frame(rgbdimages)
-        return _append_differentiable(pointclouds, rgbdimages, pointclouds.has_features, 0.6)
+        return _update_differentiable(pointclouds, rgbdimages, 0.6, pointclouds.has_features)
     return _append_valid_pixels(pointclouds, rgbdimages, True)
 
 
@@ -473,7 +541,11 @@ def update_map_fusion(pointclouds: Pointclouds, rgbdimages: RGBDImages, dist_th:
     if not inplace:
         pointclouds = pointclouds.clone()
     if _wants_grad(pointclouds, rgbdimages):
-        with torch.no_grad():
-            table = find_correspondences(pointclouds, rgbdimages.detach(), dist_th, dot_th)
-        return _fuse_differentiable(pointclouds, rgbdimages, table, sigma)
+        if rgbdimages.poses is None:
+            raise ValueError("rgbdimages must have poses for map fusion")
+        if pointclouds.has_points:
+            for what in ("normals", "colors", "features"):
+                if not getattr(pointclouds, "has_" + what):
+                    raise ValueError("Pointclouds must have {} for map fusion, but did not.".format(what))
+        return _update_differentiable(pointclouds, rgbdimages, sigma, True, dist_th, dot_th)
     return _fused_update(pointclouds, rgbdimages, dist_th, dot_th, sigma)

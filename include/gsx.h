@@ -108,6 +108,32 @@ int gsx_fusion_merge_append(float *map_points, float *map_normals, float *map_co
                             int W, double sigma, void *workspace, uint32_t epoch, int32_t *overflow_flag,
                             void *stream);
 
+/* K4 as a differentiable op (autograd.Function forward / backward).
+ * replaces the tape PyTorch builds through fuse_with_map   gradslam/slam/fusionutils.py:654-720 (merge),
+ *          :702-720 + gradslam/structures/pointclouds.py:1117-1237 (append), get_alpha :16-73
+ * _fwd: same kernel as gsx_fusion_merge_append on the materialised frame maps (gvertex, gnormal), run on a COPY of
+ *       the map (the caller copies; the pre-merge map must survive for the backward), and additionally records in
+ *       assoc_out int32 (B,H,W), zero-filled by the caller, where every pixel went: +(row+1) appended as `row`,
+ *       -(row+1) merged into `row`, 0 dropped.
+ * _bwd: upstream gradients of the updated map (B,capacity_out,.) (any may be NULL = zero) -> gradients of the
+ *       pre-merge map (B,capacity_in,.) (every row written; padding rows zero) and of the frame values: world vertex /
+ *       normal maps, colours and - through the confidence weight alpha - the camera-frame vertex map, all (B,H,W,3).
+ *       map_ccounts / d_map_ccounts are both NULL for maps without confidence counts. */
+int gsx_fusion_merge_append_fwd(float *map_points, float *map_normals, float *map_colors, float *map_ccounts,
+                                const int32_t *counts_in, int32_t *counts_out, int64_t capacity,
+                                const float *depth, int64_t depth_bstride, const float *rgb, int64_t rgb_bstride,
+                                const float *intrinsics, int64_t K_bstride, const float *gvertex,
+                                const float *gnormal, int B, int H, int W, double sigma, void *workspace,
+                                uint32_t epoch, int32_t *overflow_flag, int32_t *assoc_out, void *stream);
+int gsx_fusion_merge_append_bwd(const int32_t *assoc, const int32_t *counts_in, const float *map_points,
+                                const float *map_normals, const float *map_colors, const float *map_ccounts,
+                                int64_t capacity_in, const float *g_points, const float *g_normals,
+                                const float *g_colors, const float *g_ccounts, int64_t capacity_out,
+                                const float *gvertex, const float *gnormal, const float *rgb, const float *vertex,
+                                int B, int H, int W, double sigma, float *d_map_points, float *d_map_normals,
+                                float *d_map_colors, float *d_map_ccounts, float *d_gvertex, float *d_gnormal,
+                                float *d_rgb, float *d_vertex, void *stream);
+
 /* Whole-sequence driver with ground-truth poses: for s in [s_begin,s_end): K2/K3 -> K4 with the frame
  * geometry sampled on the fly from depth (no K1 launch, no frame maps in HBM), no host sync.
  * replaces ICPSLAM.forward with odom='gt' + PointFusion._map   gradslam/slam/icpslam.py:99-138,
@@ -209,6 +235,33 @@ int gsx_icp_normal_eq_fwd(const float *src_points, int ns, const float *tgt_poin
 int gsx_icp_normal_eq_bwd(const float *src_points, int ns, const float *tgt_points, const float *tgt_normals,
                           const int64_t *nn_idx, const float *g_sums, float *g_src, float *g_tgt_points_rows,
                           float *g_tgt_normals_rows, void *stream);
+
+/* K7 as differentiable ops (n independent problems; every array is dense float32, device):
+ * _solve_: xi = (A^T A + damp I)^-1 A^T b from the 28 sums of gsx_icp_normal_eq_fwd and damp (n), then dT = se3_exp(xi).
+ *          replaces solve_linear_system   gradslam/odometry/icputils.py:22-90  and  se3_exp  geometry/se3utils.py:77-115
+ * _update_: mode 0 = LM accept / reject (icputils.py:356-365): new_err < err -> applied step se3_exp(xi), damp / 2,
+ *          else identity, damp * 2;  mode 1 = gradLM gates (icputils.py:519-543): diff = clamp(new_err - err, +-70),
+ *          damp * (1/lambda_max + (lambda_max - 1/lambda_max) / (1 + exp(-B diff))), applied step
+ *          se3_exp(xi / (1 + exp(-B2 diff))^(1/nu)).  Outputs: new damp (n), applied step (n,16), T_out = step * T (n,16).
+ * The backward entries take the forward inputs again plus the upstream gradients (any may be NULL = zero) and write
+ * the gradient of every forward input (same arithmetic evaluated on dual numbers, one lane per input). */
+int gsx_icp_solve_fwd(const float *sums, const float *damp, int n, float *xi_out, float *dT_out, void *stream);
+int gsx_icp_solve_bwd(const float *sums, const float *damp, int n, const float *g_xi, const float *g_dT,
+                      float *g_sums, float *g_damp, void *stream);
+int gsx_icp_update_fwd(const float *xi, const float *err, const float *new_err, const float *damp, const float *T,
+                       int n, int mode, float lambda_max, float B, float B2, float nu, float *damp_out,
+                       float *dT_out, float *T_out, void *stream);
+int gsx_icp_update_bwd(const float *xi, const float *err, const float *new_err, const float *damp, const float *T,
+                       int n, int mode, float lambda_max, float B, float B2, float nu, const float *g_damp_out,
+                       const float *g_dT_out, const float *g_T_out, float *g_xi, float *g_err, float *g_new_err,
+                       float *g_damp, float *g_T, void *stream);
+
+/* out = R p + t for a cloud (n,3) and one 4x4 T; backward: g_points = R^T g, g_T = sum_i g_i (x) [p_i; 1] (fixed-order
+ * reduction; bottom row zero).     replaces transform_pointcloud   gradslam/geometry/geometryutils.py:737-794 */
+int gsx_rigid_transform_fwd(const float *points, int64_t n, const float *T, float *out, void *stream);
+int64_t gsx_rigid_transform_bwd_scratch_bytes(int64_t n);
+int gsx_rigid_transform_bwd(const float *points, int64_t n, const float *T, const float *g_out, float *g_points,
+                            float *g_T, void *scratch, int64_t scratch_bytes, void *stream);
 
 /* full ICP / gradICP on given clouds.  initial_transform (B,16) or NULL (identity).  transform_out (B,16).
  * nn_idx_out optional int64 (B, ns_stride): association of the last iteration (-1 = filtered out).

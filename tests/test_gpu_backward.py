@@ -134,37 +134,185 @@ def test_icpslam_pose_gradient_wrt_live_depth():
         torch.testing.assert_close(g_gpu, g_ref, rtol=5e-2, atol=5e-3 * scale)
 
 
-def test_pointfusion_map_gradients_match_oracle_autograd():
+@pytest.mark.parametrize("B,L", [(1, 2), (2, 3)])
+def test_pointfusion_map_gradients_match_oracle_autograd(B, L):
     """PointFusion(odom='gt') in differentiable mode: d(fused map)/d(depth, colours) through the K1 backward kernel and
-    the taped merge, against PyTorch autograd of the oracle restatement (fusionutils.py:580-722)."""
+    the K4 backward kernel (gsx_fusion_merge_append_bwd), against PyTorch autograd of the oracle restatement
+    (fusionutils.py:580-722).  L=3 chains a merge into rows that were themselves merged one frame earlier."""
     import gradslam_b200 as gs
     import gsx_oracle as oracle
 
-    B, L, H, W = 1, 2, 24, 32
+    H, W = 24, 32
     rgb, depth, K, poses = make_sequence(B, L, H, W, seed=41, isolated_holes=True, yaw0=0.6)
     d_ref, c_ref = depth.clone().requires_grad_(True), rgb.clone().requires_grad_(True)
     ref = oracle.run_slam(c_ref, d_ref, K, poses, odom="gt")
     g = torch.Generator().manual_seed(5)
-    n = ref.map.counts()[0]
-    wp, wc, wf = torch.randn(n, 3, generator=g), torch.randn(n, 3, generator=g), torch.randn(n, 1, generator=g)
-    ((ref.map.points[0] * wp).sum() + (ref.map.colors[0] * wc).sum() + (ref.map.ccounts[0] * wf).sum()).backward()
+    counts = ref.map.counts()
+    # (normals are left out of the loss: the oracle's autograd of |cross| is NaN at zero-length normals; the normal
+    # channel of the K4 backward is covered by test_merge_append_op_gradients_wrt_previous_map, K1's by the tests above)
+    ws = [[torch.randn(n, c, generator=g) for c in (3, 3, 1)] for n in counts]
+    loss = 0
+    for b in range(B):
+        for t, w in zip((ref.map.points[b], ref.map.colors[b], ref.map.ccounts[b]), ws[b]):
+            loss = loss + (t * w).sum()
+    loss.backward()
 
     d_gpu, c_gpu = depth.clone().to(DEV).requires_grad_(True), rgb.clone().to(DEV).requires_grad_(True)
     slam = gs.PointFusion(odom="gt", device=DEV)
     pc, _ = slam(gs.RGBDImages(c_gpu, d_gpu, K.to(DEV), poses.to(DEV)))
-    assert pc.num_points_per_pointcloud.tolist() == [n]
-    torch.testing.assert_close(pc.points_list[0].detach().cpu(), ref.map.points[0].detach(), rtol=1e-5, atol=1e-6)
-    ((pc.points_list[0] * wp.to(DEV)).sum() + (pc.colors_list[0] * wc.to(DEV)).sum()
-     + (pc.features_list[0] * wf.to(DEV)).sum()).backward()
+    assert pc.num_points_per_pointcloud.tolist() == counts
+    loss = 0
+    for b in range(B):
+        torch.testing.assert_close(pc.points_list[b].detach().cpu(), ref.map.points[b].detach(), rtol=1e-5, atol=1e-6)
+        for t, w in zip((pc.points_list[b], pc.colors_list[b], pc.features_list[b]), ws[b]):
+            loss = loss + (t * w.to(DEV)).sum()
+    loss.backward()
     for got, want in ((d_gpu.grad.cpu(), d_ref.grad), (c_gpu.grad.cpu(), c_ref.grad)):
         assert torch.isfinite(got).all()
         scale = want.abs().max().item()
         torch.testing.assert_close(got, want, rtol=1e-3, atol=1e-4 * scale)
-    # the same call without gradients takes the fused kernels and gives the same map
+    # the same call without gradients takes the fused in-place kernels and gives the same map, bit for bit
     with torch.no_grad():
         pc2, _ = slam(gs.RGBDImages(rgb.to(DEV), depth.to(DEV), K.to(DEV), poses.to(DEV)))
-    assert pc2.num_points_per_pointcloud.tolist() == [n]
-    torch.testing.assert_close(pc2.points_list[0], pc.points_list[0].detach(), rtol=1e-6, atol=1e-6)
+    assert pc2.num_points_per_pointcloud.tolist() == counts
+    for b in range(B):
+        assert torch.equal(pc2.points_list[b], pc.points_list[b].detach())
+        assert torch.equal(pc2.normals_list[b], pc.normals_list[b].detach())
+        assert torch.equal(pc2.colors_list[b], pc.colors_list[b].detach())
+        assert torch.equal(pc2.features_list[b], pc.features_list[b].detach())
+
+
+def test_merge_append_op_gradients_wrt_previous_map():
+    """update_map_fusion with a map that requires grad: d(updated map)/d(previous map rows) through
+    gsx_fusion_merge_append_bwd (matched rows are scaled by c/(c+alpha), their confidence collects the quotient-rule
+    terms, untouched rows pass through), against float64 autograd of the same formulas on the kernel's association."""
+    import gradslam_b200 as gs
+    from gradslam_b200.slam import fusionutils as fu
+
+    B, H, W = 2, 20, 28
+    rgb, depth, K, poses = make_sequence(B, 2, H, W, seed=43, isolated_holes=True, yaw0=0.6)
+    frames = gs.RGBDImages(rgb.to(DEV), depth.to(DEV), K.to(DEV), poses.to(DEV))
+    with torch.no_grad():
+        base = fu.update_map_fusion(gs.Pointclouds(device=DEV), frames[:, 0], 0.05, 0.94, 0.6)
+        table = fu.find_correspondences(base, frames[:, 1], 0.05, 0.94)
+    assert table.shape[0] > 0
+    n0 = base.num_points_per_pointcloud.tolist()
+    leaves = {k: getattr(base, k + "_padded").clone().requires_grad_(True)
+              for k in ("points", "normals", "colors", "features")}
+    pc = gs.Pointclouds(leaves["points"], leaves["normals"], leaves["colors"], leaves["features"])
+    pc._set_counts(n0)
+    out = fu.update_map_fusion(pc, frames[:, 1], 0.05, 0.94, 0.6)
+    n1 = out.num_points_per_pointcloud.tolist()
+    g = torch.Generator().manual_seed(3)
+    wts = {k: torch.randn(B, max(n1), c, generator=g).to(DEV) for k, c in (("points", 3), ("normals", 3), ("colors", 3),
+                                                                              ("features", 1))}
+    mask = out.nonpad_mask.unsqueeze(-1)
+    sum((getattr(out, k + "_padded") * wts[k] * mask).sum() for k in wts).backward()
+
+    # float64 reference on the same association (fusionutils.py:654-699)
+    f1 = frames[:, 1]
+    ref = {k: v.detach().double().requires_grad_(True) for k, v in leaves.items()}
+    b, n, h, w = table.unbind(1)
+    alpha = fu.get_alpha(f1.vertex_map[:, 0].double(), 0.6, dim=-1, keepdim=True)[b, h, w]
+    cc = ref["features"][b, n]
+    tot = cc + alpha
+    new = {}
+    for k, fmap in (("points", f1.global_vertex_map), ("normals", f1.global_normal_map), ("colors", f1.rgb_image)):
+        new[k] = ref[k].index_put((b, n), (cc * ref[k][b, n] + alpha * fmap[:, 0].double()[b, h, w]) / tot)
+    new["features"] = ref["features"].index_put((b, n), tot)
+    live = (torch.arange(max(n0), device=DEV).view(1, -1) < torch.tensor(n0, device=DEV).view(-1, 1)).unsqueeze(-1)
+    sum((new[k] * wts[k][:, :max(n0)].double() * live).sum() for k in new).backward()
+    for k in leaves:
+        got, want = leaves[k].grad.double() * live, ref[k].grad
+        torch.testing.assert_close(got, want, rtol=1e-4, atol=1e-5 * want.abs().max().item())
+
+
+def _lm_reference_functions():
+    import importlib.util
+    import os
+    spec = importlib.util.spec_from_file_location(
+        "icp_diff_ref", os.path.join(os.path.dirname(os.path.abspath(__file__)), "test_icp_diff_host.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def test_solve_update_transform_ops_forward_and_backward():
+    """K7 ops on the device (gsx_icp_solve_*, gsx_icp_update_*, gsx_rigid_transform_*) against float64 autograd of the
+    reference formulas (solve_linear_system icputils.py:22-90, se3_exp se3utils.py:77-115, gates icputils.py:519-543,
+    transform_pointcloud geometryutils.py:737-794)."""
+    from gradslam_b200.odometry import icputils as iu
+    refm = _lm_reference_functions()
+    g = torch.Generator().manual_seed(11)
+    A = torch.randn(300, 6, dtype=torch.float64, generator=g)
+    bb = torch.randn(300, dtype=torch.float64, generator=g) * 0.05
+    M = A.t() @ A
+    tri = torch.triu_indices(6, 6)
+    sums64 = torch.cat([M[tri[0], tri[1]], A.t() @ bb, (bb * bb).sum().view(1)])
+    damp64 = torch.tensor([1e-3], dtype=torch.float64)
+    wo = torch.randn(22, dtype=torch.float64, generator=g)
+    # solve
+    s_ref, d_ref = sums64.clone().requires_grad_(True), damp64.clone().requires_grad_(True)
+    o_ref = refm._solve(torch.cat([s_ref, d_ref]))
+    (o_ref * wo).sum().backward()
+    s_gpu, d_gpu = sums64.float().to(DEV).requires_grad_(True), damp64.float().to(DEV).requires_grad_(True)
+    xi, dT = iu._SolveFn.apply(s_gpu, d_gpu)
+    torch.testing.assert_close(torch.cat([xi, dT.reshape(-1)]).detach().cpu().double(), o_ref.detach(), rtol=0, atol=2e-6)
+    ((xi * wo[:6].float().to(DEV)).sum() + (dT.reshape(-1) * wo[6:].float().to(DEV)).sum()).backward()
+    for got, want in ((s_gpu.grad, s_ref.grad), (d_gpu.grad, d_ref.grad)):
+        torch.testing.assert_close(got.cpu().double(), want, rtol=1e-3, atol=2e-4 * s_ref.grad.abs().max().item())
+    # update, both modes and both branches
+    for mode, err, nerr in ((1, 0.5, 0.3), (1, 0.3, 0.5), (0, 0.5, 0.3), (0, 0.3, 0.5)):
+        xi64 = torch.randn(6, dtype=torch.float64, generator=g) * 0.05
+        T64 = refm._se3_exp(torch.randn(6, dtype=torch.float64, generator=g) * 0.3)
+        inp = torch.cat([xi64, torch.tensor([err, nerr, 1e-3], dtype=torch.float64), T64.reshape(-1)]).requires_grad_(True)
+        wu = torch.randn(33, dtype=torch.float64, generator=g)
+        o_ref = refm._update(inp, mode, 2.0, 1.0, 1.0, 200.0)
+        (o_ref * wu).sum().backward()
+        leaf = [t.float().to(DEV).requires_grad_(True) for t in (xi64, torch.tensor(err), torch.tensor(nerr),
+                                                                  torch.tensor([1e-3]), T64)]
+        dmp, dTa, Tn = iu._UpdateFn.apply(*leaf, mode, 2.0, 1.0, 1.0, 200.0)
+        got = torch.cat([dmp.reshape(-1), dTa.reshape(-1), Tn.reshape(-1)])
+        torch.testing.assert_close(got.detach().cpu().double(), o_ref.detach(), rtol=0, atol=2e-6)
+        (got * wu.float().to(DEV)).sum().backward()
+        g_got = torch.cat([t.grad.reshape(-1) for t in leaf]).cpu().double()
+        torch.testing.assert_close(g_got, inp.grad, rtol=1e-4, atol=2e-5)
+    # rigid transform
+    P64 = torch.randn(1000, 3, dtype=torch.float64, generator=g)
+    T64 = refm._se3_exp(torch.randn(6, dtype=torch.float64, generator=g) * 0.5)
+    wp = torch.randn(1000, 3, dtype=torch.float64, generator=g)
+    p_ref, t_ref = P64.clone().requires_grad_(True), T64.clone().requires_grad_(True)
+    ((p_ref @ t_ref[:3, :3].t() + t_ref[:3, 3]) * wp).sum().backward()
+    p_gpu, t_gpu = P64.float().to(DEV).requires_grad_(True), T64.float().to(DEV).requires_grad_(True)
+    out = iu._RigidTransformFn.apply(p_gpu, t_gpu)
+    torch.testing.assert_close(out.detach().cpu().double(), (P64 @ T64[:3, :3].t() + T64[:3, 3]), rtol=0, atol=1e-5)
+    (out * wp.float().to(DEV)).sum().backward()
+    torch.testing.assert_close(p_gpu.grad.cpu().double(), p_ref.grad, rtol=1e-4, atol=1e-5)
+    torch.testing.assert_close(t_gpu.grad.cpu().double(), t_ref.grad, rtol=1e-4, atol=1e-3)
+
+
+def test_icp_lm_function_gradients_match_oracle_autograd():
+    """point_to_plane_ICP (LM accept / reject, icputils.py:235-367) in differentiable mode against the oracle's tape."""
+    import gsx_oracle as oracle
+    from gradslam_b200.odometry.icputils import point_to_plane_ICP
+
+    rgb, depth, K, poses = make_sequence(1, 1, 40, 56, seed=29, hole_fraction=0.0, yaw0=0.6)
+    m = oracle.frame_maps(depth, K, poses)
+    tgt = m["gvertex"][0, 0].reshape(-1, 3).contiguous()
+    tgt_n = m["gnormal"][0, 0].reshape(-1, 3).contiguous()
+    T_true = oracle.se3_exp(torch.tensor([0.01, -0.005, 0.008, 0.01, -0.01, 0.005]))
+    src0 = oracle.rigid_apply(T_true, tgt)
+    s_ref = src0.clone().requires_grad_(True)
+    T_ref, _ = oracle.point_to_plane_icp(s_ref, tgt, tgt_n, torch.eye(4), numiters=4)
+    wT = torch.randn(4, 4, generator=torch.Generator().manual_seed(2))
+    (T_ref * wT).sum().backward()
+    s_gpu = src0.clone().to(DEV).requires_grad_(True)
+    T_gpu, _ = point_to_plane_ICP(s_gpu.unsqueeze(0), tgt.to(DEV).unsqueeze(0), tgt_n.to(DEV).unsqueeze(0),
+                                  torch.eye(4, device=DEV), numiters=4)
+    torch.testing.assert_close(T_gpu.detach().cpu(), T_ref.detach(), rtol=0, atol=1e-4)
+    (T_gpu * wT.to(DEV)).sum().backward()
+    scale = s_ref.grad.abs().max().item()
+    torch.testing.assert_close(s_gpu.grad.cpu(), s_ref.grad, rtol=2e-2, atol=2e-3 * scale)
 
 
 def test_normal_equation_op_forward_and_backward():
