@@ -20,7 +20,10 @@ Parity status: PINNED.  `tests/golden/make_golden.py` runs the UNMODIFIED
 reference (imported from /root/reference under the shims in
 tests/golden/ref_loader.py) and freezes its outputs; `tests/test_oracle_golden.py`
 checks this oracle against those fixtures and against the reference's own
-golden vectors (tests/data/msrd_b2s3) and known-answer tests.
+golden vectors (tests/data/msrd_b2s3) and known-answer tests.  Backward passes
+are pinned too: `tests/golden/make_golden_grad.py` records the reference's
+autograd gradients (tests/golden/ref_grad.npz) and the same test file compares
+this oracle's autograd with them.
 
 Canonical arithmetic.  The reference computes 3-term dot products through
 einsum/bmm, whose rounding order is whatever the BLAS picks.  So that the CUDA

@@ -284,3 +284,58 @@ def test_reference_fuse_known_answer():
     out = oracle.fuse_with_map(smap, maps, image, table, 0.6)
     want = torch.tensor([[5.0, 5, 5], [1.5, 2, 1.5], [0.5, 2, 1.5], [3, 2, 1], [-1, 0, 1], [0, 2.5, 0.5], [8, 8, 8]])
     torch.testing.assert_close(out.colors[0], want, rtol=1e-5, atol=1e-6)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# backward passes: the oracle's autograd against gradients recorded from the reference (tests/golden/ref_grad.npz,
+# written by tests/golden/make_golden_grad.py).  The CUDA backward kernels are compared with the oracle's autograd on
+# the GPU (tests/test_gpu_backward.py), so this closes the chain reference -> oracle -> kernels for d/d inputs too.
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def ref_grad():
+    return np.load(os.path.join(GOLD, "ref_grad.npz"))
+
+
+def _close_grad(got, want, rtol, atol_rel):
+    want = torch.from_numpy(np.asarray(want))
+    assert torch.isfinite(got).all()
+    torch.testing.assert_close(got, want, rtol=rtol, atol=atol_rel * want.abs().max().item())
+
+
+def test_oracle_pointfusion_gradients_match_reference(ref_grad):
+    rgb, depth, K, poses = make_sequence(1, 2, 24, 32, seed=41, isolated_holes=True, yaw0=0.6)
+    d, c = depth.clone().requires_grad_(True), rgb.clone().requires_grad_(True)
+    res = oracle.run_slam(c, d, K, poses, odom="gt")
+    n = res.map.counts()[0]
+    assert n == int(ref_grad["pf_gt/count"][0])
+    g = torch.Generator().manual_seed(5)
+    wp, wc, wf = torch.randn(n, 3, generator=g), torch.randn(n, 3, generator=g), torch.randn(n, 1, generator=g)
+    ((res.map.points[0] * wp).sum() + (res.map.colors[0] * wc).sum() + (res.map.ccounts[0] * wf).sum()).backward()
+    _close_grad(d.grad, ref_grad["pf_gt/d_depth"], 1e-3, 1e-4)
+    _close_grad(c.grad, ref_grad["pf_gt/d_rgb"], 1e-4, 1e-6)
+
+
+@pytest.mark.parametrize("name", ["gradicp", "icp"])
+def test_oracle_icp_gradients_match_reference(ref_grad, name):
+    rgb, depth, K, poses = make_sequence(1, 1, 40, 56, seed=31, hole_fraction=0.0, yaw0=0.6)
+    m = oracle.frame_maps(depth, K, poses)
+    tgt = m["gvertex"][0, 0].reshape(-1, 3).contiguous()
+    tgt_n = m["gnormal"][0, 0].reshape(-1, 3).contiguous()
+    T_true = oracle.se3_exp(torch.tensor([0.01, -0.005, 0.008, 0.01, -0.01, 0.005]))
+    s = oracle.rigid_apply(T_true, tgt).clone().requires_grad_(True)
+    fn = oracle.point_to_plane_gradicp if name == "gradicp" else oracle.point_to_plane_icp
+    T, _ = fn(s, tgt, tgt_n, torch.eye(4), numiters=4)
+    torch.testing.assert_close(T.detach(), torch.from_numpy(ref_grad[name + "/T"]), rtol=0, atol=1e-5)
+    w = torch.randn(4, 4, generator=torch.Generator().manual_seed(1))
+    (T * w).sum().backward()
+    _close_grad(s.grad, ref_grad[name + "/d_src"], 2e-2, 2e-3)
+
+
+def test_oracle_icpslam_pose_gradient_matches_reference(ref_grad):
+    rgb, depth, K, poses = make_sequence(1, 2, 32, 40, seed=17, isolated_holes=True, yaw0=0.6)
+    d = depth.clone().requires_grad_(True)
+    res = oracle.run_slam(rgb, d, K, poses, mode="aggregate", odom="gradicp", numiters=3, dsratio=2)
+    torch.testing.assert_close(res.poses.detach(), torch.from_numpy(ref_grad["icpslam/poses"]), rtol=0, atol=1e-5)
+    w = torch.randn(res.poses.shape, generator=torch.Generator().manual_seed(9))
+    (res.poses * w).sum().backward()
+    _close_grad(d.grad, ref_grad["icpslam/d_depth"], 5e-2, 5e-3)
