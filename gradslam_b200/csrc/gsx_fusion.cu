@@ -7,6 +7,7 @@
 //                              scan, row-major order per batch element).  No float atomics anywhere.
 // Reference op chains: gradslam/slam/fusionutils.py:198-722 (see include/gsx.h).
 #include "gsx_common.cuh"
+#include "gsx_exp.cuh"
 #include "../../include/gsx.h"
 
 namespace gsx {
@@ -428,9 +429,23 @@ struct MergeArgs {
 // alpha = clamp(exp(-|v|^2 / 2 sigma^2), 1e-7, 1.01) (fusionutils.py:69-72).  The exponential is evaluated in double and
 // rounded once: that is the correctly rounded float32 exp (up to 2^-29 odds), so the CUDA path and the CPU oracle agree
 // bit for bit and no later threshold / arg-min decision can flip because of a 1-ulp difference in a confidence weight.
+#ifndef GSX_K4_CTA_DIV
+#define GSX_K4_CTA_DIV 1  // image row / column of a pixel from one division per CTA instead of one per pixel
+#endif
+#ifndef GSX_K4_FAST_EXP
+#define GSX_K4_FAST_EXP 1  // reduced-range float64 exp (gsx_exp.cuh); 0: library exp().  Same bits either way.
+#endif
+__device__ __forceinline__ float confidence_exp(float sq_norm, float two_sigma_sq) {
+  const float x = (-sq_norm) / two_sigma_sq;
+#if GSX_K4_FAST_EXP
+  if (!(x >= -17.0f)) return 0.0f;  // exp(x) < 4.2e-8: clamps to 1e-7 below (also NaN, like fmaxf(NaN, 1e-7f))
+  return exp_f32_via_f64(x);
+#else
+  return (float)exp((double)x);
+#endif
+}
 __device__ __forceinline__ float confidence_alpha(float sq_norm, float two_sigma_sq) {
-  const float e = (float)exp((double)((-sq_norm) / two_sigma_sq));
-  return fminf(fmaxf(e, 1e-7f), 1.01f);
+  return fminf(fmaxf(confidence_exp(sq_norm, two_sigma_sq), 1e-7f), 1.01f);
 }
 
 constexpr unsigned long long kFlagAgg = 1ull, kFlagPrefix = 2ull;
@@ -561,7 +576,7 @@ __global__ void __launch_bounds__(kBlock, GSX_K4A_MINB) k_merge_only(MergeArgs a
 template <bool kFused, bool kDoMerge, bool kAssoc = false>
 __global__ void __launch_bounds__(kMB, GSX_K4_MINB) k_merge_append(MergeArgs a) {
   __shared__ Rigid s_pose;
-  __shared__ int s_tile;
+  __shared__ int s_tile, s_h0, s_w0;  // tile id; image row / column of the tile's first pixel
   __shared__ int s_warp_sums[kPix][kMB / 32];
   __shared__ int s_excl;
   __shared__ KInv s_k;
@@ -573,6 +588,8 @@ __global__ void __launch_bounds__(kMB, GSX_K4_MINB) k_merge_append(MergeArgs a) 
     // dynamic tile id: tiles start in ticket order, so every predecessor of a running tile is running or done
     const unsigned int t = atomicAdd(a.ws.ticket + b, 1u);
     s_tile = (int)(t - (a.epoch - 1u) * (unsigned int)T);
+    s_h0 = (s_tile * kMergeTile) / a.W;  // one division per CTA instead of one per pixel
+    s_w0 = s_tile * kMergeTile - s_h0 * a.W;
   }
   if (threadIdx.x == 32) s_k = load_kinv(a.K + b * a.K_bstride);
   if (kFused && threadIdx.x == 64) s_pose = load_rigid(a.poses + b * a.pose_bstride);
@@ -658,7 +675,18 @@ __global__ void __launch_bounds__(kMB, GSX_K4_MINB) k_merge_append(MergeArgs a) 
       const float *c = rgb + (int64_t)pix[j] * 3;
       fc[j] = make_float3(__ldg(c), __ldg(c + 1), __ldg(c + 2));
       if (kFused) {
-        const int h = pix[j] / a.W, w = pix[j] - h * a.W;
+        int h, w;
+        if (GSX_K4_CTA_DIV && a.W >= kMergeTile) {  // rows at least one tile wide: the tile wraps at most once
+          h = s_h0;
+          w = s_w0 + j * kMB + (int)threadIdx.x;
+          if (w >= a.W) {
+            w -= a.W;
+            ++h;
+          }
+        } else {
+          h = pix[j] / a.W;
+          w = pix[j] - h * a.W;
+        }
         const FrameSample f = frame_sample<true>(depth, k, &s_pose, h, w, a.H, a.W);
         fp[j] = f.gv;
         fn[j] = f.gn;
@@ -858,7 +886,7 @@ __global__ void __launch_bounds__(256) k_merge_bwd_pixels(MergeBwdArgs a) {
     const float gcc = a.g_cc ? a.g_cc[ro] : 0.0f;
     const float vx = a.vloc[fi], vy = a.vloc[fi + 1], vz = a.vloc[fi + 2];
     const float sq = (vx * vx + vy * vy) + vz * vz;
-    const float e = (float)exp((double)((-sq) / a.two_sigma_sq));
+    const float e = (float)exp((double)((-sq) / a.two_sigma_sq));  // (cold path: library exp)
     float d_alpha = gcc;
     if (as > 0) {
 #pragma unroll
@@ -974,6 +1002,7 @@ extern "C" int gsx_fusion_merge_append(float *map_points, float *map_normals, fl
   GSX_CHECK_ARG((gvertex && gnormal) || (poses && !gvertex && !gnormal),
                 "gsx_fusion_merge_append: pass both frame maps, or neither together with the poses");
   GSX_CHECK_ARG(epoch >= 1 && epoch < (1u << 30), "gsx_fusion_merge_append: epoch out of range");
+  GSX_CHECK_ARG(capacity <= 0x7fffffffll, "gsx_fusion_merge_append: capacity must fit int32 (counts are int32)");
   const Workspace ws = carve(workspace, B, H, W);
   MergeArgs a{map_points, map_normals, map_colors, map_ccounts, counts_in, counts_out, capacity, depth, depth_bstride,
               rgb, rgb_bstride, intrinsics, K_bstride, gvertex, gnormal, poses, pose_bstride, B, H, W,
@@ -996,6 +1025,7 @@ extern "C" int gsx_fusion_merge_append_fwd(float *map_points, float *map_normals
   GSX_CHECK_ARG(depth && rgb && intrinsics && workspace && overflow_flag && gvertex && gnormal && assoc_out,
                 "gsx_fusion_merge_append_fwd: null frame pointer");
   GSX_CHECK_ARG(epoch >= 1 && epoch < (1u << 30), "gsx_fusion_merge_append_fwd: epoch out of range");
+  GSX_CHECK_ARG(capacity <= 0x7fffffffll, "gsx_fusion_merge_append_fwd: capacity must fit int32 (counts are int32)");
   const Workspace ws = carve(workspace, B, H, W);
   MergeArgs a{map_points, map_normals, map_colors, map_ccounts, counts_in, counts_out, capacity, depth, depth_bstride,
               rgb, rgb_bstride, intrinsics, K_bstride, gvertex, gnormal, nullptr, 0, B, H, W,
