@@ -352,6 +352,8 @@ def main():
                                   "%dx%d B=1 L=%d, %.1f s wall" % (W, H, args.cpu_sample_frames, dt)}
 
     if rank == 0:
+        from gradslam_b200 import _C as _gsx
+        groups = int(_gsx.lib().gsx_pointfusion_sequence_groups(B))
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_dev / args.steps, "higher_is_better": True,
@@ -359,7 +361,8 @@ def main():
             "config": workload_config(args, world),
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": ms_e2e / args.steps},
-            "gpu_launches": 2 * L * args.steps - args.steps,  # K2/K3 + K4 per frame; K2 is skipped on the empty map
+            # K2/K3 + K4 per frame and per concurrent batch group; K2 is skipped on the empty map
+            "gpu_launches": groups * (2 * L - 1) * args.steps, "sequence_groups": groups,
             "roofline": roofline, "cpu_baseline": cpu_baseline, "clocks": clocks, "kernels": kernels,
             "icp_odometry": icp_extra, "e2e_raw_ingest": raw_extra,
             "final_map_points_per_sequence": (frames_info[-1]["map_points"] + frames_info[-1]["new"]) // B

@@ -10,6 +10,17 @@
 #include "gsx_exp.cuh"
 #include "../../include/gsx.h"
 
+// Timing-only ablations (WRONG results; never set in a product build): where does the time go?
+//   GSX_K4_ABLATE: 1 = matched rows are not read, 2 = matched rows are neither read nor written, 3 = no frame sample
+//                  (no depth stencil, no vertex / normal math), 4 = arg-min records are not cleared
+//   GSX_K2_ABLATE: 1 = no 128-bit CAS, 2 = no frame sample (depth gather + vertex / normal math)
+#ifndef GSX_K4_ABLATE
+#define GSX_K4_ABLATE 0
+#endif
+#ifndef GSX_K2_ABLATE
+#define GSX_K2_ABLATE 0
+#endif
+
 namespace gsx {
 
 constexpr int kBlock = 256;
@@ -227,7 +238,10 @@ __global__ void __launch_bounds__(kBlock, GSX_K2_MINB) k_project_select(ProjectA
       h = min(max(h, 0), a.H - 1);
       const int pix = h * a.W + w;
       float3 fv, fnm;
-      if (kFused) {
+      if (kFused && GSX_K2_ABLATE == 2) {
+        fv = make_float3(m.px, m.py, m.pz);
+        fnm = make_float3(m.mx, m.my, m.mz);
+      } else if (kFused) {
         const FrameSample f = frame_sample<true>(dimg, s_kinv, &s_pose, h, w, a.H, a.W);
         fv = f.gv;
         fnm = f.gn;
@@ -256,8 +270,12 @@ __global__ void __launch_bounds__(kBlock, GSX_K2_MINB) k_project_select(ProjectA
         const unsigned int rb = __float_as_uint(d2) | 0x80000000u;  // d2 >= 0
         const unsigned long long hi = ((unsigned long long)kb << 32) | rb;
         mine = U128{~(unsigned long long)n, ~hi};
+#if GSX_K2_ABLATE == 1
+        if (n == -1) best[pix] = mine;  // never true: keeps the key computation alive
+#else
         old = cas128(best + pix, U128{0ull, 0ull}, mine);  // optimistic: most pixels see a single candidate
         pend_pix = pix;
+#endif
       }
     }
   }
@@ -620,7 +638,7 @@ __global__ void __launch_bounds__(kMB, GSX_K4_MINB) k_merge_append(MergeArgs a) 
 #pragma unroll
   for (int j = 0; j < kPix; ++j) {
     matched[j] = (rec[j].lo | rec[j].hi) != 0ull;
-    if (matched[j]) best[pix[j]] = U128{0ull, 0ull};  // leave the workspace clean for the next frame
+    if (matched[j] && GSX_K4_ABLATE != 4) best[pix[j]] = U128{0ull, 0ull};  // leave the workspace clean for the next frame
     is_new[j] = (pix[j] < P) && (d[j] > 0.0f) && !matched[j];
     n_matched += matched[j] ? 1 : 0;
     // row-major order inside the tile: chunk j (256 consecutive pixels), then warp, then lane
@@ -687,7 +705,14 @@ __global__ void __launch_bounds__(kMB, GSX_K4_MINB) k_merge_append(MergeArgs a) 
           h = pix[j] / a.W;
           w = pix[j] - h * a.W;
         }
+#if GSX_K4_ABLATE == 3
+        FrameSample f;
+        f.gv = make_float3((float)w, (float)h, d[j]);
+        f.gn = make_float3(0.f, 0.f, 1.f);
+        f.v = f.gv;
+#else
         const FrameSample f = frame_sample<true>(depth, k, &s_pose, h, w, a.H, a.W);
+#endif
         fp[j] = f.gv;
         fn[j] = f.gn;
         // alpha from the LOCAL vertex (fusionutils.py:657, 69-72)
@@ -709,20 +734,24 @@ __global__ void __launch_bounds__(kMB, GSX_K4_MINB) k_merge_append(MergeArgs a) 
   float mp[kPix][10];
 #pragma unroll
   for (int j = 0; j < kPix; ++j) {
-    if (kDoMerge && matched[j] && cc) {
+    if (kDoMerge && matched[j] && cc && GSX_K4_ABLATE != 2) {
       const int64_t n = (int64_t)(~rec[j].lo);
 #pragma unroll
       for (int q = 0; q < 3; ++q) {
+#if GSX_K4_ABLATE == 1
+        mp[j][q] = mp[j][3 + q] = mp[j][6 + q] = mp[j][9] = 1.0f;
+        continue;
+#endif
         mp[j][q] = pts[n * 3 + q];
         mp[j][3 + q] = nrm[n * 3 + q];
         mp[j][6 + q] = col[n * 3 + q];
       }
-      mp[j][9] = cc[n];
+      if (GSX_K4_ABLATE != 1) mp[j][9] = cc[n];
     }
   }
 #pragma unroll
   for (int j = 0; j < kPix; ++j) {
-    if (kDoMerge && matched[j] && cc) {
+    if (kDoMerge && matched[j] && cc && GSX_K4_ABLATE != 2) {
       // confidence-weighted running mean (fusionutils.py:678-699); exactly one pixel owns this map row
       const int64_t n = (int64_t)(~rec[j].lo);
       const float c0 = mp[j][9];
@@ -948,6 +977,35 @@ __global__ void __launch_bounds__(256) k_merge_bwd_pixels(MergeBwdArgs a) {
     a.d_rgb[fi + q] = dc[q];
     a.d_vloc[fi + q] = dv[q];
   }
+}
+
+// One frame (K2 + K4, frame geometry sampled on the fly) for the batch elements [b0, b0 + nb) of a B_total-element
+// problem, on `st`.  All pointers are the FULL-batch base pointers; batch elements are independent, so disjoint groups
+// may run concurrently on different streams (gsx_pointfusion_sequence_gt).
+int fusion_frame_group(float *pts, float *nrm, float *col, float *cc, const int32_t *cin, int32_t *cout, int64_t cap,
+                       int64_t max_count, const float *poses, int64_t pose_bs, const float *K, int64_t K_bs,
+                       const float *depth, int64_t d_bs, const float *rgb, int64_t rgb_bs, int B_total, int b0, int nb,
+                       int H, int W, float dist_th, float dot_th, double sigma, void *workspace, uint32_t epoch,
+                       int32_t *overflow, cudaStream_t st) {
+  const int64_t P = (int64_t)H * W;
+  Workspace ws = carve(workspace, B_total, H, W);
+  ws.best += (int64_t)b0 * P;
+  ws.tile_state += (int64_t)b0 * ws.tiles;
+  ws.ticket += b0;
+  ws.stats += 2 * b0;
+  float *gp = pts + (int64_t)b0 * cap * 3, *gn = nrm + (int64_t)b0 * cap * 3, *gc = col + (int64_t)b0 * cap * 3;
+  float *gcc = cc ? cc + (int64_t)b0 * cap : nullptr;
+  const float *gposes = poses + (int64_t)b0 * pose_bs, *gK = K + (int64_t)b0 * K_bs;
+  const float *gdepth = depth + (int64_t)b0 * d_bs, *grgb = rgb + (int64_t)b0 * rgb_bs;
+  if (max_count > 0 && gcc) {
+    ProjectArgs pa{gp, gn, gcc, cin + b0, cap, gposes, pose_bs, gK, K_bs, nullptr, nullptr, gdepth, d_bs, nb, H, W,
+                   dist_th, dot_th, (float)(W - 0.999), (float)(H - 0.999), ws.best, ws.stats};
+    const int rc = launch_project_select(pa, max_count, st);
+    if (rc) return rc;
+  }
+  MergeArgs ma{gp, gn, gc, gcc, cin + b0, cout + b0, cap, gdepth, d_bs, grgb, rgb_bs, gK, K_bs, nullptr, nullptr,
+               gposes, pose_bs, nb, H, W, (float)(2.0 * (sigma * sigma)), ws, epoch, overflow, nullptr};
+  return launch_merge_append(ma, st);
 }
 
 }  // namespace gsx

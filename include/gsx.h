@@ -145,6 +145,10 @@ int gsx_fusion_merge_append_bwd(const int32_t *assoc, const int32_t *counts_in, 
  * epoch0 = epoch of frame s_begin (the call consumes s_end - s_begin epochs).  Splitting a sequence
  * into several calls (s_begin..s_end chunks) lets the caller overlap host->device copies of later
  * frames with the fusion of earlier ones. */
+/* number of independent batch groups gsx_pointfusion_sequence_gt runs on concurrent internal streams for a batch of
+ * B (default 2, environment GSX_SEQ_GROUPS = 1..4 overrides; never more than B).  Kernel launches per call =
+ * groups * (2 * frames - [map empty on entry]). */
+int gsx_pointfusion_sequence_groups(int B);
 int gsx_pointfusion_sequence_gt(float *map_points, float *map_normals, float *map_colors, float *map_ccounts,
                                 int32_t *counts, int64_t capacity, int64_t max_count0, const float *depth,
                                 const float *rgb, const float *intrinsics, const float *poses, int B, int L,
