@@ -9,7 +9,7 @@ SRC_DIR = os.path.join(_HERE, "csrc")
 OUT = os.path.join(_HERE, "_lib", "libgsx.so")
 
 # -fmad=false: the kernels' decisions must be bit-identical to the CPU oracle (no FMA contraction).
-# gsx_knn.cu is the one FP32-throughput-bound file; it states its FMA use explicitly with fmaf().
+# Where an FMA is wanted (the float64 polynomial of gsx_exp.cuh, the dual-number refinements) it is written as fma().
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-fmad=false", "-std=c++17",
               "--shared", "-Xcompiler", "-fPIC"]
 
