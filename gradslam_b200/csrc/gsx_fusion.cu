@@ -97,9 +97,6 @@ struct ProjectArgs {
 #ifndef GSX_K2_MINB
 #define GSX_K2_MINB 4
 #endif
-#ifndef GSX_K2_DEEP
-#define GSX_K2_DEEP 0  // 1: two-stage software pipeline (depth stencil loads one iteration ahead); measured slower
-#endif
 
 struct MapPoint {  // everything K2 needs from one map row
   float px, py, pz, mx, my, mz, cc;
@@ -151,69 +148,6 @@ __global__ void __launch_bounds__(kBlock, GSX_K2_MINB) k_project_select(ProjectA
   int64_t n = (int64_t)blockIdx.x * kBlock + threadIdx.x;
   U128 mine{0ull, 0ull}, old{0ull, 0ull};
   int pend_pix = -1;
-#if GSX_K2_DEEP
-  // Two-stage software pipeline over the grid-stride loop (fused path):
-  //   iteration k:  fetch row k+1  |  stage A(k): project, frustum test, issue the depth stencil loads
-  //                                |  stage B(k-1): frame sample from the stencil loaded last iteration, tests, CAS
-  if (kFused) {
-    MapPoint row_next = load_map_point(pts, nrm, cc, n < count ? n : 0);
-    MapPoint mb{};  // stage-B item
-    DepthStencil tb{};
-    int hb = 0, wb = 0;
-    int64_t nb = -1;
-    for (;; n += stride) {
-      const bool have_a = n < count;
-      MapPoint ma{};
-      DepthStencil ta{};
-      int ha_ = 0, wa_ = 0;
-      bool live_a = false;
-      if (have_a) {
-        ma = row_next;
-        if (n + stride < count) row_next = load_map_point(pts, nrm, cc, n + stride);
-        const float3 q = rigid_apply(s_tinv, ma.px, ma.py, ma.pz);
-        const float hx = ((s_k[0] * q.x + s_k[1] * q.y) + s_k[2] * q.z) + s_k[3];
-        const float hy = ((s_k[4] * q.x + s_k[5] * q.y) + s_k[6] * q.z) + s_k[7];
-        const float hz = ((s_k[8] * q.x + s_k[9] * q.y) + s_k[10] * q.z) + s_k[11];
-        const float den = (hz != 0.0f) ? hz : 1.0f;
-        const float u = hx / den, v = hy / den;
-        live_a = (u > -1e-3f) && (u < a.u_hi) && (v > -1e-3f) && (v < a.v_hi) && (q.z > 0.0f);
-        if (live_a) {
-          ++n_active;
-          wa_ = min(max((int)rintf(u), 0), a.W - 1);
-          ha_ = min(max((int)rintf(v), 0), a.H - 1);
-          ta = load_stencil(dimg, ha_, wa_, a.H, a.W);  // consumed next iteration
-        }
-      }
-      if (nb >= 0) {  // stage B for the previous item
-        const FrameSample f = frame_sample_from(tb, s_kinv, &s_pose, hb, wb, a.H, a.W);
-        const float dx = f.gv.x - mb.px, dy = f.gv.y - mb.py, dz = f.gv.z - mb.pz;
-        const float d2 = (dx * dx + dy * dy) + dz * dz;
-        const float dot = (f.gn.x * mb.mx + f.gn.y * mb.my) + f.gn.z * mb.mz;
-        if (pend_pix >= 0) {
-          atomic_max_rec128_finish(best + pend_pix, mine, old);
-          pend_pix = -1;
-        }
-        if ((sqrtf(d2) < a.dist_th) && (dot > a.dot_th)) {
-          const float inv_cc = 1.0f / (mb.cc + 1e-20f);
-          unsigned int kb = __float_as_uint(inv_cc);
-          kb = (kb & 0x80000000u) ? ~kb : (kb | 0x80000000u);
-          const unsigned int rb = __float_as_uint(d2) | 0x80000000u;
-          const unsigned long long hi = ((unsigned long long)kb << 32) | rb;
-          const int pix = hb * a.W + wb;
-          mine = U128{~(unsigned long long)nb, ~hi};
-          old = cas128(best + pix, U128{0ull, 0ull}, mine);
-          pend_pix = pix;
-        }
-      }
-      if (live_a) {
-        mb = ma; tb = ta; hb = ha_; wb = wa_; nb = n;
-      } else {
-        nb = -1;
-      }
-      if (!have_a) break;
-    }
-  } else
-#endif
   {
   MapPoint cur = load_map_point(pts, nrm, cc, n < count ? n : 0);
   for (; n < count; n += stride) {
@@ -284,141 +218,6 @@ __global__ void __launch_bounds__(kBlock, GSX_K2_MINB) k_project_select(ProjectA
   // bookkeeping for the roofline's algorithmic-byte count: one atomic per warp
   n_active = __reduce_add_sync(0xffffffffu, n_active);
   if ((threadIdx.x & 31) == 0 && n_active) atomicAdd(a.stats + 2 * b, (unsigned long long)n_active);
-}
-
-// ---- K2 with warp-level work queues ----------------------------------------------------------------------------
-// Same arithmetic as k_project_select<true>; the difference is SIMT density.  About a third of the map points fall
-// outside the frustum, so in the plain kernel the expensive part (frame sample, tests, CAS) runs with a third of the
-// lanes idle.  Here every warp pushes its in-frustum points into a small shared-memory queue and only runs the
-// expensive part on full batches of 32 items.
-#ifndef GSX_K2_QUEUE
-#define GSX_K2_QUEUE 0  // measured slower (127 us vs 113 us): SIMT density is not what limits K2
-#endif
-constexpr int kQCap = 64;  // per-warp queue capacity (invariant: fewer than 32 items before a push of <= 32)
-
-struct QueueItem {
-  MapPoint m;
-  int n, hw;  // hw = h << 16 | w
-};
-
-__global__ void __launch_bounds__(kBlock, GSX_K2_MINB) k_project_select_q(ProjectArgs a) {
-  __shared__ Rigid s_pose, s_tinv;
-  __shared__ float s_k[12];
-  __shared__ KInv s_kinv;
-  __shared__ float q_f[kBlock / 32][kQCap][7];
-  __shared__ int q_n[kBlock / 32][kQCap], q_hw[kBlock / 32][kQCap];
-  const int b = blockIdx.y;
-  const int count = a.counts[b];
-  if ((int64_t)blockIdx.x * kBlock >= count) return;
-  if (threadIdx.x == 0) {
-    s_pose = load_rigid(a.poses + b * a.pose_bstride);
-    s_tinv = rigid_inverse(s_pose);
-  }
-  if (threadIdx.x >= 32 && threadIdx.x < 44) s_k[threadIdx.x - 32] = __ldg(a.K + b * a.K_bstride + (threadIdx.x - 32));
-  if (threadIdx.x == 64) s_kinv = load_kinv(a.K + b * a.K_bstride);
-  __syncthreads();
-  const int P = a.H * a.W;
-  const float *pts = a.pts + (int64_t)b * a.cap * 3;
-  const float *nrm = a.nrm + (int64_t)b * a.cap * 3;
-  const float *cc = a.cc + (int64_t)b * a.cap;
-  const float *dimg = a.depth + b * a.depth_bstride;
-  U128 *best = a.best + (int64_t)b * P;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  float (*qf)[7] = q_f[warp];
-  int *qn = q_n[warp], *qhw = q_hw[warp];
-  int qcount = 0;  // warp-uniform
-  unsigned int n_active = 0;
-  U128 mine{0ull, 0ull}, old{0ull, 0ull};
-  int pend_pix = -1;
-
-  // the expensive part for one dense item per lane
-  auto heavy = [&](int slot) {
-    MapPoint m;
-    m.px = qf[slot][0]; m.py = qf[slot][1]; m.pz = qf[slot][2];
-    m.mx = qf[slot][3]; m.my = qf[slot][4]; m.mz = qf[slot][5];
-    m.cc = qf[slot][6];
-    const int n = qn[slot], hw = qhw[slot];
-    const int h = hw >> 16, w = hw & 0xffff;
-    const FrameSample f = frame_sample<true>(dimg, s_kinv, &s_pose, h, w, a.H, a.W);
-    const float dx = f.gv.x - m.px, dy = f.gv.y - m.py, dz = f.gv.z - m.pz;
-    const float d2 = (dx * dx + dy * dy) + dz * dz;
-    const float dot = (f.gn.x * m.mx + f.gn.y * m.my) + f.gn.z * m.mz;
-    if (pend_pix >= 0) {
-      atomic_max_rec128_finish(best + pend_pix, mine, old);
-      pend_pix = -1;
-    }
-    if ((sqrtf(d2) < a.dist_th) && (dot > a.dot_th)) {
-      const float inv_cc = 1.0f / (m.cc + 1e-20f);
-      unsigned int kb = __float_as_uint(inv_cc);
-      kb = (kb & 0x80000000u) ? ~kb : (kb | 0x80000000u);
-      const unsigned int rb = __float_as_uint(d2) | 0x80000000u;
-      const unsigned long long hi = ((unsigned long long)kb << 32) | rb;
-      const int pix = h * a.W + w;
-      mine = U128{~(unsigned long long)n, ~hi};
-      old = cas128(best + pix, U128{0ull, 0ull}, mine);
-      pend_pix = pix;
-    }
-  };
-
-  const int64_t stride = (int64_t)gridDim.x * kBlock;
-  int64_t n = (int64_t)blockIdx.x * kBlock + threadIdx.x;
-  MapPoint cur = load_map_point(pts, nrm, cc, n < count ? n : 0);
-  for (int64_t base = (int64_t)blockIdx.x * kBlock; base < count; base += stride, n += stride) {
-    const MapPoint m = cur;
-    if (n + stride < count) cur = load_map_point(pts, nrm, cc, n + stride);
-    bool live = n < count;
-    int hw = 0;
-    if (live) {
-      const float3 q = rigid_apply(s_tinv, m.px, m.py, m.pz);
-      const float hx = ((s_k[0] * q.x + s_k[1] * q.y) + s_k[2] * q.z) + s_k[3];
-      const float hy = ((s_k[4] * q.x + s_k[5] * q.y) + s_k[6] * q.z) + s_k[7];
-      const float hz = ((s_k[8] * q.x + s_k[9] * q.y) + s_k[10] * q.z) + s_k[11];
-      const float den = (hz != 0.0f) ? hz : 1.0f;
-      const float u = hx / den, v = hy / den;
-      live = (u > -1e-3f) && (u < a.u_hi) && (v > -1e-3f) && (v < a.v_hi) && (q.z > 0.0f);
-      const int w = min(max((int)rintf(u), 0), a.W - 1);
-      const int h = min(max((int)rintf(v), 0), a.H - 1);
-      hw = (h << 16) | w;
-    }
-    const unsigned int ballot = __ballot_sync(0xffffffffu, live);
-    if (live) {
-      const int slot = qcount + __popc(ballot & ((1u << lane) - 1u));
-      qf[slot][0] = m.px; qf[slot][1] = m.py; qf[slot][2] = m.pz;
-      qf[slot][3] = m.mx; qf[slot][4] = m.my; qf[slot][5] = m.mz;
-      qf[slot][6] = m.cc;
-      qn[slot] = (int)n;
-      qhw[slot] = hw;
-    }
-    const int pushed = __popc(ballot);
-    qcount += pushed;
-    if (lane == 0) n_active += (unsigned int)pushed;
-    __syncwarp();
-    if (qcount >= 32) {
-      heavy(lane);
-      __syncwarp();
-      const int rest = qcount - 32;  // < 32: move the tail to the front
-      float t[7];
-      int tn = 0, th = 0;
-      if (lane < rest) {
-#pragma unroll
-        for (int j = 0; j < 7; ++j) t[j] = qf[32 + lane][j];
-        tn = qn[32 + lane];
-        th = qhw[32 + lane];
-      }
-      __syncwarp();
-      if (lane < rest) {
-#pragma unroll
-        for (int j = 0; j < 7; ++j) qf[lane][j] = t[j];
-        qn[lane] = tn;
-        qhw[lane] = th;
-      }
-      qcount = rest;
-      __syncwarp();
-    }
-  }
-  if (lane < qcount) heavy(lane);
-  if (pend_pix >= 0) atomic_max_rec128_finish(best + pend_pix, mine, old);
-  if (lane == 0 && n_active) atomicAdd(a.stats + 2 * b, (unsigned long long)n_active);
 }
 
 // ---- K4 -------------------------------------------------------------------------------------------------
@@ -514,82 +313,6 @@ __device__ __forceinline__ unsigned int lookback_warp(const unsigned long long *
 #ifndef GSX_K4_MINB
 #define GSX_K4_MINB 4
 #endif
-#ifndef GSX_K4_EARLY_EXIT
-#define GSX_K4_EARLY_EXIT 0  // measured: no gain
-#endif
-#ifndef GSX_K4_EARLY_LOOKBACK
-#define GSX_K4_EARLY_LOOKBACK 0  // measured: slower (125 us vs 116 us)
-#endif
-#ifndef GSX_K4_SPLIT
-#define GSX_K4_SPLIT 0  // 1: k_merge_only (no barriers) then k_merge_append<.., false> (append + scan only); measured slower
-#endif
-#ifndef GSX_K4A_MINB
-#define GSX_K4A_MINB 4
-#endif
-
-// K4a: confidence-weighted merge of every matched pixel into its map row.  One thread per pixel, no barriers, no
-// ordering: exactly one pixel owns a map row.  The records are left in place for the append pass.
-template <bool kFused>
-__global__ void __launch_bounds__(kBlock, GSX_K4A_MINB) k_merge_only(MergeArgs a) {
-  __shared__ Rigid s_pose;
-  __shared__ KInv s_k;
-  const int b = blockIdx.y;
-  if (threadIdx.x == 32) s_k = load_kinv(a.K + b * a.K_bstride);
-  if (kFused && threadIdx.x == 64) s_pose = load_rigid(a.poses + b * a.pose_bstride);
-  __syncthreads();
-  const int P = a.H * a.W;
-  const int pix = blockIdx.x * kBlock + threadIdx.x;
-  if (pix >= P) return;
-  const U128 rec = a.ws.best[(int64_t)b * P + pix];
-  if ((rec.lo | rec.hi) == 0ull) return;
-  const int64_t n = (int64_t)(~rec.lo);
-  float *pts = a.pts + ((int64_t)b * a.cap + n) * 3;
-  float *nrm = a.nrm + ((int64_t)b * a.cap + n) * 3;
-  float *col = a.col + ((int64_t)b * a.cap + n) * 3;
-  float *cc = a.cc + (int64_t)b * a.cap + n;
-  // the map row and the frame sample are independent: all loads go out together
-  float mp[10];
-#pragma unroll
-  for (int q = 0; q < 3; ++q) {
-    mp[q] = pts[q];
-    mp[3 + q] = nrm[q];
-    mp[6 + q] = col[q];
-  }
-  mp[9] = *cc;
-  const float *c = a.rgb + b * a.rgb_bstride + (int64_t)pix * 3;
-  const float3 fc = make_float3(__ldg(c), __ldg(c + 1), __ldg(c + 2));
-  const int h = pix / a.W, w = pix - h * a.W;
-  const float *depth = a.depth + b * a.depth_bstride;
-  float3 fp, fn, v;
-  if (kFused) {
-    const FrameSample f = frame_sample<true>(depth, s_k, &s_pose, h, w, a.H, a.W);
-    fp = f.gv;
-    fn = f.gn;
-    v = f.v;
-  } else {
-    const float *g = a.gv + ((int64_t)b * P + pix) * 3, *t = a.gn + ((int64_t)b * P + pix) * 3;
-    fp = make_float3(__ldg(g), __ldg(g + 1), __ldg(g + 2));
-    fn = make_float3(__ldg(t), __ldg(t + 1), __ldg(t + 2));
-    v = backproject(s_k, (float)w, (float)h, __ldg(depth + pix));
-  }
-  // alpha from the LOCAL vertex (fusionutils.py:657, 69-72)
-  const float sq = (v.x * v.x + v.y * v.y) + v.z * v.z;
-  const float alpha = confidence_alpha(sq, a.two_sigma_sq);
-  // confidence-weighted running mean (fusionutils.py:678-699)
-  const float c0 = mp[9];
-  const float tot = c0 + alpha;
-  const float inv = 1.0f / ((tot == 0.0f) ? 1.0f : tot);
-  pts[0] = ((c0 * mp[0]) + (alpha * fp.x)) * inv;
-  pts[1] = ((c0 * mp[1]) + (alpha * fp.y)) * inv;
-  pts[2] = ((c0 * mp[2]) + (alpha * fp.z)) * inv;
-  nrm[0] = ((c0 * mp[3]) + (alpha * fn.x)) * inv;
-  nrm[1] = ((c0 * mp[4]) + (alpha * fn.y)) * inv;
-  nrm[2] = ((c0 * mp[5]) + (alpha * fn.z)) * inv;
-  col[0] = ((c0 * mp[6]) + (alpha * fc.x)) * inv;
-  col[1] = ((c0 * mp[7]) + (alpha * fc.y)) * inv;
-  col[2] = ((c0 * mp[8]) + (alpha * fc.z)) * inv;
-  *cc = tot;
-}
 
 template <bool kFused, bool kDoMerge, bool kAssoc = false>
 __global__ void __launch_bounds__(kMB, GSX_K4_MINB) k_merge_append(MergeArgs a) {
@@ -663,17 +386,6 @@ __global__ void __launch_bounds__(kMB, GSX_K4_MINB) k_merge_append(MergeArgs a) 
   }
   unsigned long long *state = a.ws.tile_state + (int64_t)b * T;
   if (threadIdx.x == 0 && tile + 1 < T) st_release_u64(state + tile, pack_state(a.epoch, kFlagAgg, (unsigned)block_total));
-#if GSX_K4_EARLY_LOOKBACK
-  // warp 0 resolves the tile's exclusive prefix right away (its successors stop walking back as soon as they see a
-  // PREFIX), the other warps go on with the merge meanwhile
-  if (warp == 0) {
-    const unsigned int excl = lookback_warp(state, tile, a.epoch, lane);
-    if (lane == 0) {
-      if (tile + 1 < T) st_release_u64(state + tile, pack_state(a.epoch, kFlagPrefix, excl + (unsigned)block_total));
-      s_excl = (int)excl;
-    }
-  }
-#endif
 
   float *pts = a.pts + (int64_t)b * a.cap * 3;
   float *nrm = a.nrm + (int64_t)b * a.cap * 3;
@@ -771,7 +483,6 @@ __global__ void __launch_bounds__(kMB, GSX_K4_MINB) k_merge_append(MergeArgs a) 
     }
   }
 
-#if !GSX_K4_EARLY_LOOKBACK
   // decoupled look-back (warp 0): exclusive prefix of new-point counts over preceding tiles of this element
   if (warp == 0) {
     const unsigned int excl = lookback_warp(state, tile, a.epoch, lane);
@@ -780,17 +491,6 @@ __global__ void __launch_bounds__(kMB, GSX_K4_MINB) k_merge_append(MergeArgs a) 
       s_excl = (int)excl;
     }
   }
-#endif
-#if GSX_K4_EARLY_EXIT
-  {
-    // only warps that have something to append need the prefix; the others retire now (exited warps count as
-    // arrived at the barrier) and free their slots for the next CTA.  Warp 0 stays: it owns s_excl / counts_out.
-    bool any_new = false;
-#pragma unroll
-    for (int j = 0; j < kPix; ++j) any_new = any_new || is_new[j];
-    if (warp != 0 && !__any_sync(0xffffffffu, any_new)) return;
-  }
-#endif
   __syncthreads();
   const int64_t base = (int64_t)count_in + s_excl;
 #pragma unroll
@@ -827,8 +527,6 @@ int launch_project_select(const ProjectArgs &a, int64_t max_count, cudaStream_t 
   if (bx < 1) bx = 1;
   if (a.gv)
     k_project_select<false><<<dim3((unsigned)bx, (unsigned)a.B), kBlock, 0, stream>>>(a);
-  else if (GSX_K2_QUEUE && a.H < 65536 && a.W < 65536)
-    k_project_select_q<<<dim3((unsigned)bx, (unsigned)a.B), kBlock, 0, stream>>>(a);
   else
     k_project_select<true><<<dim3((unsigned)bx, (unsigned)a.B), kBlock, 0, stream>>>(a);
   GSX_CHECK_LAUNCH("gsx_fusion_project_select");
@@ -838,19 +536,9 @@ int launch_project_select(const ProjectArgs &a, int64_t max_count, cudaStream_t 
 int launch_merge_append(const MergeArgs &a, cudaStream_t stream) {
   if (a.B == 0) return 0;
   const dim3 grid((unsigned)(a.ws.tiles * a.B));
-#if GSX_K4_SPLIT
-  if (a.cc) {  // maps without confidence counts are never merged (aggregation only)
-    const dim3 mgrid((unsigned)(((int64_t)a.H * a.W + kBlock - 1) / kBlock), (unsigned)a.B);
-    if (a.gv) k_merge_only<false><<<mgrid, kBlock, 0, stream>>>(a);
-    else k_merge_only<true><<<mgrid, kBlock, 0, stream>>>(a);
-  }
-  if (a.gv) k_merge_append<false, false><<<grid, kMB, 0, stream>>>(a);
-  else k_merge_append<true, false><<<grid, kMB, 0, stream>>>(a);
-#else
   if (a.assoc) k_merge_append<false, true, true><<<grid, kMB, 0, stream>>>(a);  // differentiable forward (maps given)
   else if (a.gv) k_merge_append<false, true><<<grid, kMB, 0, stream>>>(a);
   else k_merge_append<true, true><<<grid, kMB, 0, stream>>>(a);
-#endif
   GSX_CHECK_LAUNCH("gsx_fusion_merge_append");
   return 0;
 }
