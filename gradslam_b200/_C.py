@@ -47,6 +47,9 @@ SIGNATURES = {
         c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_vp, c_vp, c_vp, c_vp, c_i64, c_vp, c_vp, c_vp, c_vp,
                 c_int, c_int, c_int, c_double, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "gsx_pointfusion_sequence_groups": (c_int, [c_int]),
+    "gsx_pointfusion_sequence_gt_geo32": (
+        c_int, [c_vp, c_vp, c_vp, c_i64, c_i64, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_int,
+                c_float, c_float, c_double, c_vp, c_u32, c_vp, c_vp]),
     "gsx_pointfusion_sequence_gt": (
         c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_int,
                 c_int, c_float, c_float, c_double, c_vp, c_vp, c_u32, c_vp, c_vp]),

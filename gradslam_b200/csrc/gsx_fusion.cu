@@ -78,7 +78,7 @@ inline int64_t workspace_bytes(int B, int H, int W) {
 
 // ---- K2 + K3 ------------------------------------------------------------------------------------------
 struct ProjectArgs {
-  const float *pts, *nrm, *cc;
+  const float *pts, *nrm, *cc;  // geo32 layout: pts = geometry rows (B,cap,8), nrm = cc = null
   const int32_t *counts;
   int64_t cap;
   const float *poses;
@@ -101,8 +101,19 @@ struct ProjectArgs {
 struct MapPoint {  // everything K2 needs from one map row
   float px, py, pz, mx, my, mz, cc;
 };
+// kGeo: the "geo32" row layout under study for round 2 - geometry rows (px,py,pz,nx,ny,nz,cc,0) of exactly one 32-byte
+// sector in `pts` (two 128-bit loads), colours in their own array; nrm / cc are unused.  Same values, same results.
+template <bool kGeo>
 __device__ __forceinline__ MapPoint load_map_point(const float *pts, const float *nrm, const float *cc, int64_t n) {
   MapPoint m;
+  if (kGeo) {
+    const float4 g0 = __ldg(reinterpret_cast<const float4 *>(pts + n * 8));
+    const float4 g1 = __ldg(reinterpret_cast<const float4 *>(pts + n * 8 + 4));
+    m.px = g0.x; m.py = g0.y; m.pz = g0.z;
+    m.mx = g0.w; m.my = g1.x; m.mz = g1.y;
+    m.cc = g1.z;
+    return m;
+  }
   m.px = __ldg(pts + n * 3);
   m.py = __ldg(pts + n * 3 + 1);
   m.pz = __ldg(pts + n * 3 + 2);
@@ -120,7 +131,7 @@ __device__ __forceinline__ MapPoint load_map_point(const float *pts, const float
 //     outside the frustum, which costs bytes but removes a round trip;
 //   * the depth values under the projection (centre, right, below) are requested together;
 //   * the result of the 128-bit CAS is only looked at one iteration later.
-template <bool kFused>
+template <bool kFused, bool kGeo = false>
 __global__ void __launch_bounds__(kBlock, GSX_K2_MINB) k_project_select(ProjectArgs a) {
   __shared__ Rigid s_pose, s_tinv;
   __shared__ float s_k[12];
@@ -136,9 +147,9 @@ __global__ void __launch_bounds__(kBlock, GSX_K2_MINB) k_project_select(ProjectA
   if (threadIdx.x == 64) s_kinv = load_kinv(a.K + b * a.K_bstride);
   __syncthreads();
   const int P = a.H * a.W;
-  const float *pts = a.pts + (int64_t)b * a.cap * 3;
-  const float *nrm = a.nrm + (int64_t)b * a.cap * 3;
-  const float *cc = a.cc + (int64_t)b * a.cap;
+  const float *pts = a.pts + (int64_t)b * a.cap * (kGeo ? 8 : 3);
+  const float *nrm = kGeo ? nullptr : a.nrm + (int64_t)b * a.cap * 3;
+  const float *cc = kGeo ? nullptr : a.cc + (int64_t)b * a.cap;
   const float *gv = kFused ? nullptr : a.gv + (int64_t)b * P * 3;
   const float *gn = kFused ? nullptr : a.gn + (int64_t)b * P * 3;
   const float *dimg = a.depth + b * a.depth_bstride;
@@ -149,11 +160,11 @@ __global__ void __launch_bounds__(kBlock, GSX_K2_MINB) k_project_select(ProjectA
   U128 mine{0ull, 0ull}, old{0ull, 0ull};
   int pend_pix = -1;
   {
-  MapPoint cur = load_map_point(pts, nrm, cc, n < count ? n : 0);
+  MapPoint cur = load_map_point<kGeo>(pts, nrm, cc, n < count ? n : 0);
   for (; n < count; n += stride) {
     const MapPoint m = cur;
     const int64_t nn = n + stride;
-    if (nn < count) cur = load_map_point(pts, nrm, cc, nn);  // in flight while this point is processed
+    if (nn < count) cur = load_map_point<kGeo>(pts, nrm, cc, nn);  // in flight while this point is processed
     // world -> camera (pointclouds.py:526-573), then pinhole projection with the 4x4 K on the homogeneous
     // point (projutils.py:92-238): z == 0 divides by 1.
     const float3 q = rigid_apply(s_tinv, m.px, m.py, m.pz);
@@ -222,7 +233,7 @@ __global__ void __launch_bounds__(kBlock, GSX_K2_MINB) k_project_select(ProjectA
 
 // ---- K4 -------------------------------------------------------------------------------------------------
 struct MergeArgs {
-  float *pts, *nrm, *col, *cc;
+  float *pts, *nrm, *col, *cc;  // geo32 layout (geo = true): pts = geometry rows (B,cap,8), nrm = cc = null
   const int32_t *counts_in;
   int32_t *counts_out;
   int64_t cap;
@@ -314,7 +325,7 @@ __device__ __forceinline__ unsigned int lookback_warp(const unsigned long long *
 #define GSX_K4_MINB 4
 #endif
 
-template <bool kFused, bool kDoMerge, bool kAssoc = false>
+template <bool kFused, bool kDoMerge, bool kAssoc = false, bool kGeo = false>
 __global__ void __launch_bounds__(kMB, GSX_K4_MINB) k_merge_append(MergeArgs a) {
   __shared__ Rigid s_pose;
   __shared__ int s_tile, s_h0, s_w0;  // tile id; image row / column of the tile's first pixel
@@ -387,10 +398,10 @@ __global__ void __launch_bounds__(kMB, GSX_K4_MINB) k_merge_append(MergeArgs a) 
   unsigned long long *state = a.ws.tile_state + (int64_t)b * T;
   if (threadIdx.x == 0 && tile + 1 < T) st_release_u64(state + tile, pack_state(a.epoch, kFlagAgg, (unsigned)block_total));
 
-  float *pts = a.pts + (int64_t)b * a.cap * 3;
-  float *nrm = a.nrm + (int64_t)b * a.cap * 3;
+  float *pts = a.pts + (int64_t)b * a.cap * (kGeo ? 8 : 3);  // geo32: geometry rows (px,py,pz,nx,ny,nz,cc,0)
+  float *nrm = kGeo ? nullptr : a.nrm + (int64_t)b * a.cap * 3;
   float *col = a.col + (int64_t)b * a.cap * 3;
-  float *cc = a.cc ? a.cc + (int64_t)b * a.cap : nullptr;
+  float *cc = kGeo ? pts : (a.cc ? a.cc + (int64_t)b * a.cap : nullptr);  // geo32: only the null test is used
   const KInv k = s_k;
   const float *gvb = kFused ? nullptr : a.gv + (int64_t)b * P * 3;
   const float *gnb = kFused ? nullptr : a.gn + (int64_t)b * P * 3;
@@ -448,6 +459,16 @@ __global__ void __launch_bounds__(kMB, GSX_K4_MINB) k_merge_append(MergeArgs a) 
   for (int j = 0; j < kPix; ++j) {
     if (kDoMerge && matched[j] && cc && GSX_K4_ABLATE != 2) {
       const int64_t n = (int64_t)(~rec[j].lo);
+      if (kGeo) {
+        const float4 g0 = *reinterpret_cast<const float4 *>(pts + n * 8);
+        const float4 g1 = *reinterpret_cast<const float4 *>(pts + n * 8 + 4);
+        mp[j][0] = g0.x; mp[j][1] = g0.y; mp[j][2] = g0.z;
+        mp[j][3] = g0.w; mp[j][4] = g1.x; mp[j][5] = g1.y;
+        mp[j][9] = g1.z;
+#pragma unroll
+        for (int q = 0; q < 3; ++q) mp[j][6 + q] = col[n * 3 + q];
+        continue;
+      }
 #pragma unroll
       for (int q = 0; q < 3; ++q) {
 #if GSX_K4_ABLATE == 1
@@ -469,6 +490,23 @@ __global__ void __launch_bounds__(kMB, GSX_K4_MINB) k_merge_append(MergeArgs a) 
       const float c0 = mp[j][9];
       const float tot = c0 + alpha[j];
       const float inv = 1.0f / ((tot == 0.0f) ? 1.0f : tot);
+      if (kGeo) {
+        float4 g0, g1;
+        g0.x = ((c0 * mp[j][0]) + (alpha[j] * fp[j].x)) * inv;
+        g0.y = ((c0 * mp[j][1]) + (alpha[j] * fp[j].y)) * inv;
+        g0.z = ((c0 * mp[j][2]) + (alpha[j] * fp[j].z)) * inv;
+        g0.w = ((c0 * mp[j][3]) + (alpha[j] * fn[j].x)) * inv;
+        g1.x = ((c0 * mp[j][4]) + (alpha[j] * fn[j].y)) * inv;
+        g1.y = ((c0 * mp[j][5]) + (alpha[j] * fn[j].z)) * inv;
+        g1.z = tot;
+        g1.w = 0.0f;
+        *reinterpret_cast<float4 *>(pts + n * 8) = g0;
+        *reinterpret_cast<float4 *>(pts + n * 8 + 4) = g1;
+        col[n * 3 + 0] = ((c0 * mp[j][6]) + (alpha[j] * fc[j].x)) * inv;
+        col[n * 3 + 1] = ((c0 * mp[j][7]) + (alpha[j] * fc[j].y)) * inv;
+        col[n * 3 + 2] = ((c0 * mp[j][8]) + (alpha[j] * fc[j].z)) * inv;
+        continue;
+      }
       pts[n * 3 + 0] = ((c0 * mp[j][0]) + (alpha[j] * fp[j].x)) * inv;
       pts[n * 3 + 1] = ((c0 * mp[j][1]) + (alpha[j] * fp[j].y)) * inv;
       pts[n * 3 + 2] = ((c0 * mp[j][2]) + (alpha[j] * fp[j].z)) * inv;
@@ -498,7 +536,11 @@ __global__ void __launch_bounds__(kMB, GSX_K4_MINB) k_merge_append(MergeArgs a) 
     if (is_new[j]) {
       // append in row-major pixel order (fusionutils.py:702-720; pointclouds.py:1203-1235)
       const int64_t n = base + block_excl[j] + warp_excl[j];
-      if (n < a.cap) {
+      if (kGeo && n < a.cap) {
+        *reinterpret_cast<float4 *>(pts + n * 8) = make_float4(fp[j].x, fp[j].y, fp[j].z, fn[j].x);
+        *reinterpret_cast<float4 *>(pts + n * 8 + 4) = make_float4(fn[j].y, fn[j].z, alpha[j], 0.0f);
+        col[n * 3 + 0] = fc[j].x; col[n * 3 + 1] = fc[j].y; col[n * 3 + 2] = fc[j].z;
+      } else if (n < a.cap) {
         pts[n * 3 + 0] = fp[j].x; pts[n * 3 + 1] = fp[j].y; pts[n * 3 + 2] = fp[j].z;
         nrm[n * 3 + 0] = fn[j].x; nrm[n * 3 + 1] = fn[j].y; nrm[n * 3 + 2] = fn[j].z;
         col[n * 3 + 0] = fc[j].x; col[n * 3 + 1] = fc[j].y; col[n * 3 + 2] = fc[j].z;
@@ -515,7 +557,7 @@ __global__ void __launch_bounds__(kMB, GSX_K4_MINB) k_merge_append(MergeArgs a) 
   }
 }
 
-int launch_project_select(const ProjectArgs &a, int64_t max_count, cudaStream_t stream) {
+int launch_project_select(const ProjectArgs &a, int64_t max_count, cudaStream_t stream, bool geo = false) {
   if (a.B == 0 || max_count <= 0) return 0;
   const int64_t chunk = (int64_t)kBlock;
   int64_t bx = (max_count + chunk - 1) / chunk;
@@ -525,7 +567,9 @@ int launch_project_select(const ProjectArgs &a, int64_t max_count, cudaStream_t 
   const int64_t cap_blocks = (int64_t)kNumSMs * GSX_K2_CTAS_PER_SM;  // grid-stride beyond this many CTAs per SM
   if (bx * a.B > cap_blocks) bx = (cap_blocks + a.B - 1) / a.B;
   if (bx < 1) bx = 1;
-  if (a.gv)
+  if (geo)  // layout study: fused frame sampling only
+    k_project_select<true, true><<<dim3((unsigned)bx, (unsigned)a.B), kBlock, 0, stream>>>(a);
+  else if (a.gv)
     k_project_select<false><<<dim3((unsigned)bx, (unsigned)a.B), kBlock, 0, stream>>>(a);
   else
     k_project_select<true><<<dim3((unsigned)bx, (unsigned)a.B), kBlock, 0, stream>>>(a);
@@ -533,10 +577,11 @@ int launch_project_select(const ProjectArgs &a, int64_t max_count, cudaStream_t 
   return 0;
 }
 
-int launch_merge_append(const MergeArgs &a, cudaStream_t stream) {
+int launch_merge_append(const MergeArgs &a, cudaStream_t stream, bool geo = false) {
   if (a.B == 0) return 0;
   const dim3 grid((unsigned)(a.ws.tiles * a.B));
-  if (a.assoc) k_merge_append<false, true, true><<<grid, kMB, 0, stream>>>(a);  // differentiable forward (maps given)
+  if (geo) k_merge_append<true, true, false, true><<<grid, kMB, 0, stream>>>(a);  // layout study
+  else if (a.assoc) k_merge_append<false, true, true><<<grid, kMB, 0, stream>>>(a);  // differentiable forward (maps given)
   else if (a.gv) k_merge_append<false, true><<<grid, kMB, 0, stream>>>(a);
   else k_merge_append<true, true><<<grid, kMB, 0, stream>>>(a);
   GSX_CHECK_LAUNCH("gsx_fusion_merge_append");
@@ -674,26 +719,28 @@ int fusion_frame_group(float *pts, float *nrm, float *col, float *cc, const int3
                        int64_t max_count, const float *poses, int64_t pose_bs, const float *K, int64_t K_bs,
                        const float *depth, int64_t d_bs, const float *rgb, int64_t rgb_bs, int B_total, int b0, int nb,
                        int H, int W, float dist_th, float dot_th, double sigma, void *workspace, uint32_t epoch,
-                       int32_t *overflow, cudaStream_t st) {
+                       int32_t *overflow, cudaStream_t st, bool geo) {
   const int64_t P = (int64_t)H * W;
   Workspace ws = carve(workspace, B_total, H, W);
   ws.best += (int64_t)b0 * P;
   ws.tile_state += (int64_t)b0 * ws.tiles;
   ws.ticket += b0;
   ws.stats += 2 * b0;
-  float *gp = pts + (int64_t)b0 * cap * 3, *gn = nrm + (int64_t)b0 * cap * 3, *gc = col + (int64_t)b0 * cap * 3;
-  float *gcc = cc ? cc + (int64_t)b0 * cap : nullptr;
+  // geo32 layout study (geo = true): pts = geometry rows (B,cap,8) holding normals and counts too; nrm = cc = null
+  float *gp = pts + (int64_t)b0 * cap * (geo ? 8 : 3), *gn = geo ? nullptr : nrm + (int64_t)b0 * cap * 3;
+  float *gc = col + (int64_t)b0 * cap * 3;
+  float *gcc = geo ? gp : (cc ? cc + (int64_t)b0 * cap : nullptr);
   const float *gposes = poses + (int64_t)b0 * pose_bs, *gK = K + (int64_t)b0 * K_bs;
   const float *gdepth = depth + (int64_t)b0 * d_bs, *grgb = rgb + (int64_t)b0 * rgb_bs;
   if (max_count > 0 && gcc) {
     ProjectArgs pa{gp, gn, gcc, cin + b0, cap, gposes, pose_bs, gK, K_bs, nullptr, nullptr, gdepth, d_bs, nb, H, W,
                    dist_th, dot_th, (float)(W - 0.999), (float)(H - 0.999), ws.best, ws.stats};
-    const int rc = launch_project_select(pa, max_count, st);
+    const int rc = launch_project_select(pa, max_count, st, geo);
     if (rc) return rc;
   }
   MergeArgs ma{gp, gn, gc, gcc, cin + b0, cout + b0, cap, gdepth, d_bs, grgb, rgb_bs, gK, K_bs, nullptr, nullptr,
                gposes, pose_bs, nb, H, W, (float)(2.0 * (sigma * sigma)), ws, epoch, overflow, nullptr};
-  return launch_merge_append(ma, st);
+  return launch_merge_append(ma, st, geo);
 }
 
 }  // namespace gsx

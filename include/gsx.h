@@ -145,6 +145,17 @@ int gsx_fusion_merge_append_bwd(const int32_t *assoc, const int32_t *counts_in, 
  * epoch0 = epoch of frame s_begin (the call consumes s_end - s_begin epochs).  Splitting a sequence
  * into several calls (s_begin..s_end chunks) lets the caller overlap host->device copies of later
  * frames with the fusion of earlier ones. */
+/* LAYOUT STUDY (not used by the Python package; prepared for the next round): the same whole-sequence
+ * driver on the "geo32" map layout - map_geometry (B,capacity,8) rows (px,py,pz,nx,ny,nz,ccount,0), exactly one 32-byte
+ * sector each and 16-byte aligned, plus map_colors (B,capacity,3).  K2 then reads one sector per map point with two
+ * 128-bit loads and K4 gathers / rewrites two sectors per merged row instead of four.  Same arithmetic, same results
+ * (scripts/geo32_experiment.py compares the two layouts bit for bit and times them). */
+int gsx_pointfusion_sequence_gt_geo32(float *map_geometry, float *map_colors, int32_t *counts, int64_t capacity,
+                                      int64_t max_count0, const float *depth, const float *rgb,
+                                      const float *intrinsics, const float *poses, int B, int L, int s_begin,
+                                      int s_end, int H, int W, float dist_th, float dot_th, double sigma,
+                                      void *workspace, uint32_t epoch0, int32_t *overflow_flag, void *stream);
+
 /* number of independent batch groups gsx_pointfusion_sequence_gt runs on concurrent internal streams for a batch of
  * B (default 2, environment GSX_SEQ_GROUPS = 1..4 overrides; never more than B).  Kernel launches per call =
  * groups * (2 * frames - [map empty on entry]). */
