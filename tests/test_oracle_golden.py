@@ -339,3 +339,40 @@ def test_oracle_icpslam_pose_gradient_matches_reference(ref_grad):
     w = torch.randn(res.poses.shape, generator=torch.Generator().manual_seed(9))
     (res.poses * w).sum().backward()
     _close_grad(d.grad, ref_grad["icpslam/d_depth"], 5e-2, 5e-3)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# non-default parameters (tests/golden/make_golden_params.py): thresholds / sigma of the fusion, ICP down-sampling,
+# damping, distance threshold, gradLM gate parameters, a non-square image, a first pose that is not the identity
+# ---------------------------------------------------------------------------------------------------------------
+PARAM_CASES = [
+    ("pf_gt_tight", "pointfusion", 2, 4, 64, 64, 11, dict(), dict(odom="gt", dist_th=0.02, angle_th=10, sigma=0.3)),
+    ("pf_gt_loose", "pointfusion", 1, 4, 48, 80, 12, dict(), dict(odom="gt", dist_th=0.2, angle_th=45, sigma=1.5)),
+    ("pf_gt_yaw", "pointfusion", 2, 3, 64, 64, 13, dict(yaw0=0.6), dict(odom="gt")),
+    ("pf_icp_ds2", "pointfusion", 1, 3, 64, 64, 14, dict(yaw0=0.6), dict(odom="icp", numiters=6, dsratio=2, damp=1e-4)),
+    ("pf_gradicp_gates", "pointfusion", 1, 3, 64, 64, 15, dict(yaw0=0.6),
+     dict(odom="gradicp", numiters=6, dsratio=2, lambda_max=4.0, B=2.0, B2=0.5, nu=50.0)),
+    ("icpslam_gradicp_thresh", "aggregate", 1, 3, 64, 64, 16, dict(yaw0=0.6),
+     dict(odom="gradicp", numiters=5, dsratio=2, dist_thresh=0.5)),
+]
+
+
+@pytest.fixture(scope="module")
+def ref_params():
+    return dict(np.load(os.path.join(GOLD, "ref_slam_params.npz")))
+
+
+@pytest.mark.parametrize("case", PARAM_CASES, ids=[c[0] for c in PARAM_CASES])
+def test_slam_runs_with_other_parameters_match_frozen_reference(ref_params, case):
+    name, mode, B, L, H, W, seed, seq_kw, kw = case
+    rgb, depth, K, poses = make_sequence(B, L, H, W, seed=seed, isolated_holes=True, **seq_kw)
+    res = oracle.run_slam(rgb, depth, K, poses, mode=mode, **kw)
+    assert res.map.counts() == ref_params[name + "/counts"].tolist()
+    torch.testing.assert_close(res.poses, torch.from_numpy(ref_params[name + "/poses"]), rtol=0, atol=1e-5)
+    for b in range(B):
+        for attr, tol in (("points", 2e-5), ("normals", 2e-5), ("colors", 2e-6)):
+            torch.testing.assert_close(getattr(res.map, attr)[b],
+                                       torch.from_numpy(ref_params["%s/%s/%d" % (name, attr, b)]), rtol=0, atol=tol)
+        if mode == "pointfusion":
+            torch.testing.assert_close(res.map.ccounts[b], torch.from_numpy(ref_params["%s/ccounts/%d" % (name, b)]),
+                                       rtol=1e-6, atol=1e-7)
