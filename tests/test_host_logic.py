@@ -206,3 +206,44 @@ def test_slam_constructors_and_defaults():
     with pytest.raises(TypeError):
         slam(3)
     assert gs.ICPSLAM(odom="gt").odomprov is None
+
+
+def test_structutils_list_padded_round_trip():
+    """gradslam/structures/structutils.py:47-124: padding sizes, pad value, equisized stacking, cutting back, errors."""
+    import pytest
+    import torch
+
+    from gradslam_b200.structures import list_to_padded, padded_to_list, structutils
+
+    g = torch.Generator().manual_seed(0)
+    items = [torch.rand(n, 3, generator=g) for n in (4, 0, 7)]
+    padded = list_to_padded(items, pad_value=-1.0)
+    assert padded.shape == (3, 7, 3)
+    assert torch.equal(padded[0, :4], items[0]) and (padded[0, 4:] == -1).all() and (padded[1] == -1).all()
+    assert list_to_padded(items, (9, 5)).shape == (3, 9, 5)
+    with pytest.raises(ValueError):
+        list_to_padded(items, (9,))
+    with pytest.raises(ValueError):
+        list_to_padded([torch.rand(2, 3, 1)], (4, 4))
+    same = [torch.rand(5, 3, generator=g) for _ in range(2)]
+    assert torch.equal(list_to_padded(same, equisized=True), torch.stack(same))
+    back = padded_to_list(padded, [4, 0, 7])
+    assert all(torch.equal(a, b) for a, b in zip(back, items))
+    assert padded_to_list(padded, [(2, 2), (0, 3), (7, 1)])[2].shape == (7, 1)
+    assert len(structutils.padded_to_list(padded)) == 3
+    with pytest.raises(ValueError):
+        padded_to_list(padded[0])
+    with pytest.raises(ValueError):
+        padded_to_list(padded, [1, 2])
+    with pytest.raises(ValueError):
+        padded_to_list(padded, [(1, 2, 3)] * 3)
+
+
+def test_top_level_namespace_mirrors_the_reference():
+    """gradslam/__init__.py re-exports the geometry and structures names at the top level."""
+    import gradslam_b200 as gs
+
+    for name in ("project_points", "unproject_points", "inverse_intrinsics", "homogenize_points", "unhomogenize_points",
+                 "Pointclouds", "RGBDImages", "list_to_padded", "padded_to_list", "ICPSLAM", "PointFusion"):
+        assert hasattr(gs, name), name
+    assert gs.slam.update_map_fusion is gs.slam.fusionutils.update_map_fusion
