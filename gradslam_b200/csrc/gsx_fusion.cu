@@ -325,8 +325,11 @@ __device__ __forceinline__ unsigned int lookback_warp(const unsigned long long *
 #define GSX_K4_MINB 4
 #endif
 
+#ifndef GSX_K4_GEO_MINB
+#define GSX_K4_GEO_MINB GSX_K4_MINB  // occupancy target of the geo32 layout-study instantiation (spills 24 B at 4)
+#endif
 template <bool kFused, bool kDoMerge, bool kAssoc = false, bool kGeo = false>
-__global__ void __launch_bounds__(kMB, GSX_K4_MINB) k_merge_append(MergeArgs a) {
+__global__ void __launch_bounds__(kMB, kGeo ? GSX_K4_GEO_MINB : GSX_K4_MINB) k_merge_append(MergeArgs a) {
   __shared__ Rigid s_pose;
   __shared__ int s_tile, s_h0, s_w0;  // tile id; image row / column of the tile's first pixel
   __shared__ int s_warp_sums[kPix][kMB / 32];
