@@ -502,6 +502,21 @@ class Pointclouds(object):
     def cuda(self):
         return self.to(torch.device("cuda"))
 
+    # ------------------------------------------------------------------ export for visualisation (host side)
+    def open3d(self, index: int, include_colors: bool = True, max_num_points: Optional[int] = None,
+               include_normals: bool = False):
+        """`open3d.geometry.PointCloud` of cloud `index` (pointclouds.py:1239-1297); needs the open3d package."""
+        from .export import to_open3d
+
+        return to_open3d(self, index, include_colors, max_num_points, include_normals)
+
+    def plotly(self, index: int, include_colors: bool = True, max_num_points: Optional[int] = 200000,
+               as_figure: bool = True, point_size: int = 2):
+        """plotly Figure / Scatter3d of cloud `index` (pointclouds.py:1299-1383); needs the plotly package."""
+        from .export import to_plotly
+
+        return to_plotly(self, index, include_colors, max_num_points, as_figure, point_size)
+
     # ------------------------------------------------------------------ growth
     def append_points(self, pointclouds: "Pointclouds"):
         """Appends another batch of clouds element-wise, in place (pointclouds.py:1117-1237)."""

@@ -247,3 +247,79 @@ def test_top_level_namespace_mirrors_the_reference():
                  "Pointclouds", "RGBDImages", "list_to_padded", "padded_to_list", "ICPSLAM", "PointFusion"):
         assert hasattr(gs, name), name
     assert gs.slam.update_map_fusion is gs.slam.fusionutils.update_map_fusion
+
+
+def test_visualisation_export_host_side():
+    """Pointclouds.open3d / .plotly (pointclouds.py:1239-1383): array preparation, colour ranges, sub-sampling, and the
+    viewer objects built through stub modules (neither package is installed in the build image)."""
+    import sys
+    import types
+
+    import numpy as np
+    import pytest
+    import torch
+
+    from gradslam_b200.structures import Pointclouds
+    from gradslam_b200.structures.export import cloud_arrays
+
+    g = torch.Generator().manual_seed(0)
+    pts = [torch.rand(50, 3, generator=g), torch.rand(20, 3, generator=g)]
+    nrm = [torch.rand(50, 3, generator=g), torch.rand(20, 3, generator=g)]
+    col = [torch.rand(50, 3, generator=g) * 255, torch.rand(20, 3, generator=g)]  # one 0..255 cloud, one 0..1 cloud
+    pc = Pointclouds(pts, nrm, col)
+    p, c, n = cloud_arrays(pc, 0, include_normals=True)
+    assert p.shape == (50, 3) and np.array_equal(p, pts[0].numpy()) and np.array_equal(n, nrm[0].numpy())
+    np.testing.assert_allclose(c, (col[0] / 255).clamp(0, 1).numpy())
+    _, c1, n1 = cloud_arrays(pc, 1, color_range=255.0)
+    np.testing.assert_allclose(c1, (col[1] * 255).clamp(0, 255).numpy())
+    assert n1 is None
+    torch.manual_seed(3)
+    p_sub, c_sub, _ = cloud_arrays(pc, 0, max_num_points=10)
+    assert p_sub.shape == (10, 3) and c_sub.shape == (10, 3)
+    rows = {tuple(r) for r in pts[0].numpy().round(6).tolist()}
+    assert all(tuple(r) in rows for r in p_sub.round(6).tolist())
+    with pytest.raises(TypeError):
+        cloud_arrays(pc, 0.0)
+    with pytest.raises(TypeError):
+        pc.plotly("0")
+
+    # missing packages fail at the call with a clear message
+    for name in ("open3d", "plotly", "plotly.graph_objects"):
+        sys.modules.pop(name, None)
+    import importlib.util
+    if importlib.util.find_spec("open3d") is None:
+        with pytest.raises(ImportError, match="open3d"):
+            pc.open3d(0)
+    if importlib.util.find_spec("plotly") is None:
+        with pytest.raises(ImportError, match="plotly"):
+            pc.plotly(0)
+
+    # stub viewers: check what is handed over
+    class _Obj:
+        def __init__(self, **kw):
+            self.__dict__.update(kw)
+
+        def update_layout(self, **kw):
+            self.layout = kw
+
+    go = types.ModuleType("plotly.graph_objects")
+    go.Scatter3d = lambda **kw: _Obj(**kw)
+    go.Figure = lambda data: _Obj(data=data)
+    plotly = types.ModuleType("plotly")
+    plotly.graph_objects = go
+    o3d = types.ModuleType("open3d")
+    o3d.geometry = types.SimpleNamespace(PointCloud=lambda: _Obj())
+    o3d.utility = types.SimpleNamespace(Vector3dVector=lambda a: np.asarray(a))
+    sys.modules.update({"plotly": plotly, "plotly.graph_objects": go, "open3d": o3d})
+    try:
+        fig = pc.plotly(1, point_size=3)
+        sc = fig.data[0]
+        assert sc.mode == "markers" and sc.marker["size"] == 3 and sc.marker["color"].dtype == np.uint8
+        assert np.array_equal(sc.x, pts[1].numpy()[:, 0]) and fig.layout["showlegend"] is False
+        assert pc.plotly(1, include_colors=False, as_figure=False).marker == {"size": 2}
+        pcd = pc.open3d(0, include_normals=True)
+        assert pcd.points.shape == (50, 3) and pcd.normals.shape == (50, 3) and pcd.colors.max() <= 1.0
+        assert not hasattr(pc.open3d(0, include_colors=False), "colors")
+    finally:
+        for name in ("plotly", "plotly.graph_objects", "open3d"):
+            sys.modules.pop(name, None)
