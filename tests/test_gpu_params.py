@@ -80,3 +80,35 @@ def test_slam_with_other_parameters(frozen, case):
         else:  # set comparison: every point has a counterpart within 1e-3
             assert _nn_dist(mine, ref.map.points[b]).quantile(0.999) < 1e-3
             assert _nn_dist(ref.map.points[b], mine).quantile(0.999) < 1e-3
+
+
+from edge_cases import EDGE_CASES, edge_inputs  # noqa: E402  (tests/golden is on sys.path, see conftest.py)
+
+
+@pytest.mark.parametrize("name", EDGE_CASES)
+def test_edge_cases(frozen, name):
+    """All-invalid frames, an empty sequence, partial frames, a frame without any correspondence: bit-exact against the
+    oracle, golden-test tolerances against the frozen reference outputs; through the whole-sequence driver AND through
+    the per-frame step API."""
+    import gradslam_b200 as gs
+
+    rgb, depth, K, poses = edge_inputs(name)
+    ref = oracle.run_slam(rgb, depth, K, poses, odom="gt")
+    counts = frozen[name + "/counts"].tolist()
+    assert ref.map.counts() == counts
+    slam = gs.PointFusion(odom="gt", device=DEV)
+    frames = gs.RGBDImages(rgb.to(DEV), depth.to(DEV), K.to(DEV), poses.to(DEV))
+    pc_seq, _ = slam(frames)
+    pc_step = gs.Pointclouds(device=DEV)
+    for s in range(frames.shape[1]):
+        pc_step, _ = slam.step(pc_step, frames[:, s], None, inplace=True)
+    for pc in (pc_seq, pc_step):
+        assert [int(c) for c in pc.num_points_per_pointcloud.tolist()] == counts
+        for b, n in enumerate(counts):
+            assert torch.equal(pc.points_list[b].cpu(), ref.map.points[b])
+            assert torch.equal(pc.normals_list[b].cpu(), ref.map.normals[b])
+            assert torch.equal(pc.colors_list[b].cpu(), ref.map.colors[b])
+            assert torch.equal(pc.features_list[b].cpu(), ref.map.ccounts[b])
+            if n:
+                torch.testing.assert_close(pc.points_list[b].cpu(), torch.from_numpy(frozen["%s/points/%d" % (name, b)]),
+                                           rtol=0, atol=2e-5)

@@ -376,3 +376,23 @@ def test_slam_runs_with_other_parameters_match_frozen_reference(ref_params, case
         if mode == "pointfusion":
             torch.testing.assert_close(res.map.ccounts[b], torch.from_numpy(ref_params["%s/ccounts/%d" % (name, b)]),
                                        rtol=1e-6, atol=1e-7)
+
+
+# edge cases: all-invalid frames, an empty sequence, partial frames, a frame without any correspondence
+from edge_cases import EDGE_CASES, edge_inputs  # noqa: E402  (tests/golden is on sys.path, see conftest.py)
+
+
+@pytest.mark.parametrize("name", EDGE_CASES)
+def test_edge_cases_match_frozen_reference(ref_params, name):
+    rgb, depth, K, poses = edge_inputs(name)
+    res = oracle.run_slam(rgb, depth, K, poses, odom="gt")
+    counts = ref_params[name + "/counts"].tolist()
+    assert res.map.counts() == counts
+    for b, n in enumerate(counts):
+        if n == 0:
+            assert res.map.points[b].shape[0] == 0
+            continue
+        torch.testing.assert_close(res.map.points[b], torch.from_numpy(ref_params["%s/points/%d" % (name, b)]),
+                                   rtol=0, atol=2e-5)
+        torch.testing.assert_close(res.map.ccounts[b], torch.from_numpy(ref_params["%s/ccounts/%d" % (name, b)]),
+                                   rtol=1e-6, atol=1e-7)
