@@ -323,3 +323,22 @@ def test_visualisation_export_host_side():
     finally:
         for name in ("plotly", "plotly.graph_objects", "open3d"):
             sys.modules.pop(name, None)
+
+
+def test_downsample_pointclouds_known_answer():
+    """The reference's hand-built case (tests/odometry/test_icputils.py:800-867) restated as data: rows whose pixel lies
+    on the ds lattice survive, in table order; attributes follow; missing attributes stay missing."""
+    import torch
+
+    from gradslam_b200.odometry.icputils import downsample_pointclouds
+    from gradslam_b200.structures import Pointclouds
+
+    pts = torch.tensor([[5.0, 5, 5], [3, 3, 3], [1, 2, 3], [3, 2, 1], [1, 0, 1], [0, 0, 0]]).unsqueeze(0)
+    table = torch.tensor([[0, 0, 0, 0], [0, 1, 4, 2], [0, 2, 3, 1], [0, 3, 0, 3], [0, 4, 3, 3], [0, 5, 3, 6]])
+    ds = downsample_pointclouds(Pointclouds(pts, -pts, 2 * pts), table, 3)
+    want = torch.tensor([[5.0, 5, 5], [3, 2, 1], [1, 0, 1], [0, 0, 0]]).unsqueeze(0)
+    assert torch.equal(ds.points_padded, want) and torch.equal(ds.normals_padded, -want)
+    assert torch.equal(ds.colors_padded, 2 * want)
+    ds2 = downsample_pointclouds(Pointclouds(pts), table, 2)
+    assert torch.equal(ds2.points_padded, torch.tensor([[5.0, 5, 5], [3, 3, 3]]).unsqueeze(0))
+    assert ds2.normals_padded is None and ds2.colors_padded is None
