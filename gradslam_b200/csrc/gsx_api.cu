@@ -4,6 +4,7 @@
 #include <cstdio>
 #include <cstdint>
 #include <cstdlib>
+#include <mutex>
 
 #include "gsx_common.cuh"
 #include "../../include/gsx.h"
@@ -38,6 +39,10 @@ struct GroupStreams {
   cudaEvent_t fork, join[kMaxGroups];
 };
 static GroupStreams g_groups[kMaxDevices];
+// The group streams and their fork / join events are shared by every caller on a device: one enqueue (event record ->
+// waits -> launches -> join) must not interleave with another thread's, or a group stream could wait on the other
+// caller's fork record instead of its own.  Enqueueing is asynchronous, so the lock is held for microseconds.
+static std::mutex g_groups_mutex;
 
 static int sequence_groups(int B) {
   int g = 2;
@@ -82,6 +87,8 @@ static int sequence_gt(float *map_points, float *map_normals, float *map_colors,
   const int64_t P = (int64_t)H * W;
   cudaStream_t user = (cudaStream_t)stream;
   int G = gsx::sequence_groups(B);
+  std::unique_lock<std::mutex> lock(gsx::g_groups_mutex, std::defer_lock);
+  if (G > 1) lock.lock();
   gsx::GroupStreams *gs = G > 1 ? gsx::group_streams() : nullptr;
   if (!gs) G = 1;
   if (G > 1) {
