@@ -110,9 +110,9 @@ struct FrameSample {
   float d;
 };
 
-// local normal of pixel (h,w) given its own local vertex v and validity vf (1 or 0)
-__device__ __forceinline__ float3 frame_normal(const float *__restrict__ dimg, const KInv &k, int h, int w, int H, int W,
-                                               const float3 &v, float vf) {
+// un-normalised local normal dh x dv of pixel (h,w) given its own local vertex v
+__device__ __forceinline__ float3 frame_cross(const float *__restrict__ dimg, const KInv &k, int h, int w, int H, int W,
+                                              const float3 &v) {
   const int wa = (w < W - 1) ? w : w - 1;
   const int ha = (h < H - 1) ? h : h - 1;
   const float dr = __ldg(dimg + h * W + wa + 1);
@@ -126,9 +126,20 @@ __device__ __forceinline__ float3 frame_normal(const float *__restrict__ dimg, c
   const float cx = dhy * dvz - dhz * dvy;
   const float cy = dhz * dvx - dhx * dvz;
   const float cz = dhx * dvy - dhy * dvx;
-  const float nrm = sqrtf((cx * cx + cy * cy) + cz * cz);
+  return make_float3(cx, cy, cz);
+}
+
+// normalize(c) * vf, the zero vector staying zero (rgbdimages.py:731-743)
+__device__ __forceinline__ float3 normalize_masked(const float3 &c, float vf) {
+  const float nrm = sqrtf((c.x * c.x + c.y * c.y) + c.z * c.z);
   const float den = (nrm == 0.0f) ? 1.0f : nrm;
-  return make_float3((cx / den) * vf, (cy / den) * vf, (cz / den) * vf);
+  return make_float3((c.x / den) * vf, (c.y / den) * vf, (c.z / den) * vf);
+}
+
+// local normal of pixel (h,w) given its own local vertex v and validity vf (1 or 0)
+__device__ __forceinline__ float3 frame_normal(const float *__restrict__ dimg, const KInv &k, int h, int w, int H, int W,
+                                               const float3 &v, float vf) {
+  return normalize_masked(frame_cross(dimg, k, h, w, H, W, v), vf);
 }
 
 // The five depth values the sample of pixel (h,w) depends on: centre, the two ends of its horizontal difference

@@ -8,6 +8,7 @@
 // Reference op chains: gradslam/slam/fusionutils.py:198-722 (see include/gsx.h).
 #include "gsx_common.cuh"
 #include "gsx_exp.cuh"
+#include "gsx_thresholds.h"
 #include "../../include/gsx.h"
 
 // Timing-only ablations (WRONG results; never set in a product build): where does the time go?
@@ -92,10 +93,22 @@ struct ProjectArgs {
   float dist_th, dot_th, u_hi, v_hi;  // u_hi = float(W - 0.999), v_hi = float(H - 0.999)
   U128 *best;
   unsigned long long *stats;
+  float d2_max;  // largest float x with sqrtf(x) < dist_th (-1 if none); used by GSX_K2_FASTTEST
 };
 
 #ifndef GSX_K2_MINB
 #define GSX_K2_MINB 4
+#endif
+// Decision-exact shortcuts in K2 (round-2 candidate, OFF by default, not yet timed).  K2 only DECIDES with the frame
+// normal and with sqrt(d2); only d2 itself enters the arg-min key.  So
+//   * sqrtf(d2) < dist_th  becomes  d2 <= d2_max, with d2_max the largest float whose correctly rounded square root is
+//     below dist_th (found on the host; sqrt is monotonic, so the decision is identical);
+//   * the normal test n_frame . n_map > dot_th is first evaluated without normalising the frame normal
+//     (((R c) . m) * rsqrt(|c|^2), no IEEE square root, no three IEEE divisions) and only when that value lies within a
+//     guard band of dot_th - or the cross product is degenerate - is the canonical chain evaluated.
+// The maps must stay bit-identical (tests/test_gpu_pointfusion.py, test_gpu_fullsize.py).
+#ifndef GSX_K2_FASTTEST
+#define GSX_K2_FASTTEST 0
 #endif
 
 struct MapPoint {  // everything K2 needs from one map row
@@ -183,13 +196,50 @@ __global__ void __launch_bounds__(kBlock, GSX_K2_MINB) k_project_select(ProjectA
       h = min(max(h, 0), a.H - 1);
       const int pix = h * a.W + w;
       float3 fv, fnm;
+#if GSX_K2_FASTTEST
+      bool fast_decided = false, fast_similar = false;  // the tests were already made
+#endif
       if (kFused && GSX_K2_ABLATE == 2) {
         fv = make_float3(m.px, m.py, m.pz);
         fnm = make_float3(m.mx, m.my, m.mz);
+#if GSX_K2_FASTTEST
+      } else if (kFused) {
+        // vertex exactly as frame_sample (it enters d2 and hence the key); the normal only decides
+        const FrameSample f = frame_sample<false>(dimg, s_kinv, &s_pose, h, w, a.H, a.W);
+        fv = f.gv;
+        const float dx = fv.x - m.px, dy = fv.y - m.py, dz = fv.z - m.pz;
+        const float d2f = (dx * dx + dy * dy) + dz * dz;
+        bool similar = false;
+        if (d2f <= a.d2_max) {
+          const float vf = f.d > 0.0f ? 1.0f : 0.0f;
+          const float3 c = frame_cross(dimg, s_kinv, h, w, a.H, a.W, f.v);
+          const float c2 = (c.x * c.x + c.y * c.y) + c.z * c.z;
+          bool decided = false;
+          if (vf != 0.0f && c2 > 1e-30f && c2 < 1e30f) {
+            const float3 rc = rotate(s_pose, c.x, c.y, c.z);
+            const float approx = ((rc.x * m.mx + rc.y * m.my) + rc.z * m.mz) * rsqrtf(c2);
+            const float guard = 1e-4f * (1.0f + (fabsf(m.mx) + fabsf(m.my)) + fabsf(m.mz));
+            if (fabsf(approx - a.dot_th) > guard) {  // (false for NaN: falls through to the canonical chain)
+              similar = approx > a.dot_th;
+              decided = true;
+            }
+          }
+          if (!decided) {
+            const float3 nl = normalize_masked(c, vf);
+            const float3 gn = rotate(s_pose, nl.x, nl.y, nl.z);
+            similar = ((gn.x * m.mx + gn.y * m.my) + gn.z * m.mz) > a.dot_th;
+          }
+        }
+        // hand the decision to the common code below: a normal that passes / fails the test by construction
+        fnm = similar ? make_float3(m.mx, m.my, m.mz) : make_float3(0.f, 0.f, 0.f);
+        fast_decided = true;
+        fast_similar = similar;
+#else
       } else if (kFused) {
         const FrameSample f = frame_sample<true>(dimg, s_kinv, &s_pose, h, w, a.H, a.W);
         fv = f.gv;
         fnm = f.gn;
+#endif
       } else {
         const float *g = gv + (int64_t)pix * 3, *t = gn + (int64_t)pix * 3;
         fv = make_float3(__ldg(g), __ldg(g + 1), __ldg(g + 2));
@@ -200,7 +250,11 @@ __global__ void __launch_bounds__(kBlock, GSX_K2_MINB) k_project_select(ProjectA
       const float d2 = (dx * dx + dy * dy) + dz * dz;
       // are_normals_similar (fusionutils.py:187-195): n_frame . n_map > dot_th
       const float dot = (fnm.x * m.mx + fnm.y * m.my) + fnm.z * m.mz;
+#if GSX_K2_FASTTEST
+      live = fast_decided ? fast_similar : ((sqrtf(d2) < a.dist_th) && (dot > a.dot_th));
+#else
       live = (sqrtf(d2) < a.dist_th) && (dot > a.dot_th);
+#endif
       if (pend_pix >= 0) {  // settle the previous candidate's CAS before re-using the slot
         atomic_max_rec128_finish(best + pend_pix, mine, old);
         pend_pix = -1;
@@ -737,7 +791,8 @@ int fusion_frame_group(float *pts, float *nrm, float *col, float *cc, const int3
   const float *gdepth = depth + (int64_t)b0 * d_bs, *grgb = rgb + (int64_t)b0 * rgb_bs;
   if (max_count > 0 && gcc) {
     ProjectArgs pa{gp, gn, gcc, cin + b0, cap, gposes, pose_bs, gK, K_bs, nullptr, nullptr, gdepth, d_bs, nb, H, W,
-                   dist_th, dot_th, (float)(W - 0.999), (float)(H - 0.999), ws.best, ws.stats};
+                   dist_th, dot_th, (float)(W - 0.999), (float)(H - 0.999), ws.best, ws.stats,
+                   sqrt_lt_threshold(dist_th)};
     const int rc = launch_project_select(pa, max_count, st, geo);
     if (rc) return rc;
   }
@@ -777,7 +832,7 @@ extern "C" int gsx_fusion_project_select(const float *map_points, const float *m
   const Workspace ws = carve(workspace, B, H, W);
   ProjectArgs a{map_points, map_normals, map_ccounts, counts, capacity, poses, pose_bstride, intrinsics, K_bstride,
                 gvertex, gnormal, depth, depth_bstride, B, H, W, dist_th, dot_th, (float)(W - 0.999), (float)(H - 0.999), ws.best,
-                ws.stats};
+                ws.stats, sqrt_lt_threshold(dist_th)};
   return launch_project_select(a, max_count, (cudaStream_t)stream);
 }
 

@@ -52,3 +52,19 @@ def test_tiny_arguments_and_zero(lib):
         und, bad, wbad, err = _scan(lib, lo, hi)
         assert bad == 0 and wbad == 0 and und == 0
     assert _scan(lib, _bits(0.0), _bits(0.0) + 1)[2] == 0  # +0
+
+
+def test_sqrt_threshold(lib):
+    """gsx_thresholds.h: for every threshold t the decision `sqrtf(x) < t` equals `x <= sqrt_lt_threshold(t)` - scanned
+    2000 floats either side of the boundary and 2 M random non-negative floats per threshold (host sqrtf is the same
+    correctly rounded IEEE operation as the device's)."""
+    lib.sqrt_threshold_scan.argtypes = [ctypes.c_float, ctypes.c_int, ctypes.c_uint64, ctypes.c_void_p]
+    lib.sqrt_threshold_scan.restype = ctypes.c_uint64
+    thr = ctypes.c_float()
+    for t in (0.05, 0.02, 0.2, 1.0, 1e-3, 0.3, 7.0, 1e-20, 1e19, 3.0000002, 0.049999997):
+        assert lib.sqrt_threshold_scan(t, 2000, 2_000_000, ctypes.byref(thr)) == 0, t
+        assert thr.value >= 0
+    for t in (0.0, -1.0, float("nan")):
+        assert lib.sqrt_threshold_scan(t, 10, 1000, ctypes.byref(thr)) == 0
+        assert thr.value == -1.0
+    assert lib.sqrt_threshold_scan(float("inf"), 10, 1000, ctypes.byref(thr)) == 0
