@@ -206,13 +206,14 @@ __global__ void __launch_bounds__(kBlock, GSX_K2_MINB) k_project_select(ProjectA
       } else if (kFused) {
         // vertex exactly as frame_sample (it enters d2 and hence the key); the normal only decides
         const FrameSample f = frame_sample<false>(dimg, s_kinv, &s_pose, h, w, a.H, a.W);
+        // (unconditional, so that the neighbour depths are requested together with the centre: one round trip)
+        const float3 c = frame_cross(dimg, s_kinv, h, w, a.H, a.W, f.v);
         fv = f.gv;
         const float dx = fv.x - m.px, dy = fv.y - m.py, dz = fv.z - m.pz;
         const float d2f = (dx * dx + dy * dy) + dz * dz;
         bool similar = false;
         if (d2f <= a.d2_max) {
           const float vf = f.d > 0.0f ? 1.0f : 0.0f;
-          const float3 c = frame_cross(dimg, s_kinv, h, w, a.H, a.W, f.v);
           const float c2 = (c.x * c.x + c.y * c.y) + c.z * c.z;
           bool decided = false;
           if (vf != 0.0f && c2 > 1e-30f && c2 < 1e30f) {
