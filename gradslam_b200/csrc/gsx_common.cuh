@@ -110,6 +110,20 @@ struct FrameSample {
   float d;
 };
 
+// a x b and |c| rounded exactly like the reference's CPU build (torch.cross / Tensor.norm on float32,
+// rgbdimages.py:733-734): cross.x = fma(a.y, b.z, -(a.z * b.y)) - first product exact, second rounded - and
+// |c| = sqrt(fma(c.z, c.z, fma(c.y, c.y, c.x * c.x))).  Where a valid pixel's right AND lower neighbours are both
+// missing, a == b and the contracted cross product is rounding residue rather than 0; normalised, it decides whether
+// map points match there, so the kernels and the oracle (oracle/normal_fma.c) reproduce it bit for bit.  The library
+// is built with -fmad=false: only these explicit fused operations are fused.
+__device__ __forceinline__ float3 cross_ref(float ax, float ay, float az, float bx, float by, float bz) {
+  return make_float3(__fmaf_rn(ay, bz, -__fmul_rn(az, by)), __fmaf_rn(az, bx, -__fmul_rn(ax, bz)),
+                     __fmaf_rn(ax, by, -__fmul_rn(ay, bx)));
+}
+__device__ __forceinline__ float norm_ref(const float3 &c) {
+  return __fsqrt_rn(__fmaf_rn(c.z, c.z, __fmaf_rn(c.y, c.y, __fmul_rn(c.x, c.x))));
+}
+
 // un-normalised local normal dh x dv of pixel (h,w) given its own local vertex v
 __device__ __forceinline__ float3 frame_cross(const float *__restrict__ dimg, const KInv &k, int h, int w, int H, int W,
                                               const float3 &v) {
@@ -123,15 +137,12 @@ __device__ __forceinline__ float3 frame_cross(const float *__restrict__ dimg, co
   const float3 b0 = (ha == h) ? v : backproject(k, (float)w, (float)ha, __ldg(dimg + ha * W + w));
   const float dhx = a1.x - a0.x, dhy = a1.y - a0.y, dhz = a1.z - a0.z;
   const float dvx = b1.x - b0.x, dvy = b1.y - b0.y, dvz = b1.z - b0.z;
-  const float cx = dhy * dvz - dhz * dvy;
-  const float cy = dhz * dvx - dhx * dvz;
-  const float cz = dhx * dvy - dhy * dvx;
-  return make_float3(cx, cy, cz);
+  return cross_ref(dhx, dhy, dhz, dvx, dvy, dvz);
 }
 
 // normalize(c) * vf, the zero vector staying zero (rgbdimages.py:731-743)
 __device__ __forceinline__ float3 normalize_masked(const float3 &c, float vf) {
-  const float nrm = sqrtf((c.x * c.x + c.y * c.y) + c.z * c.z);
+  const float nrm = norm_ref(c);
   const float den = (nrm == 0.0f) ? 1.0f : nrm;
   return make_float3((c.x / den) * vf, (c.y / den) * vf, (c.z / den) * vf);
 }
@@ -173,12 +184,7 @@ __device__ __forceinline__ FrameSample frame_sample_from(const DepthStencil &t, 
   const float3 b0 = (ha == h) ? s.v : backproject(k, (float)w, (float)ha, t.u);
   const float dhx = a1.x - a0.x, dhy = a1.y - a0.y, dhz = a1.z - a0.z;
   const float dvx = b1.x - b0.x, dvy = b1.y - b0.y, dvz = b1.z - b0.z;
-  const float cx = dhy * dvz - dhz * dvy;
-  const float cy = dhz * dvx - dhx * dvz;
-  const float cz = dhx * dvy - dhy * dvx;
-  const float nrm = sqrtf((cx * cx + cy * cy) + cz * cz);
-  const float den = (nrm == 0.0f) ? 1.0f : nrm;
-  s.n = make_float3((cx / den) * vf, (cy / den) * vf, (cz / den) * vf);
+  s.n = normalize_masked(cross_ref(dhx, dhy, dhz, dvx, dvy, dvz), vf);
   if (pose) {
     s.gv = rigid_apply(*pose, s.v.x, s.v.y, s.v.z);
     s.gv.x *= vf; s.gv.y *= vf; s.gv.z *= vf;

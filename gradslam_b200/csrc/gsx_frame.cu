@@ -157,8 +157,8 @@ __device__ __forceinline__ void normal_terms(const FrameBwdArgs &a, const float 
   const float3 b1 = backproject(k, (float)w, (float)(ha + 1), __ldg(dimg + (ha + 1) * W + w));
   const float3 dh = make_float3(a1.x - a0.x, a1.y - a0.y, a1.z - a0.z);
   const float3 dv = make_float3(b1.x - b0.x, b1.y - b0.y, b1.z - b0.z);
-  const float3 c = cross3(dh, dv);
-  const float nrm = sqrtf((c.x * c.x + c.y * c.y) + c.z * c.z);
+  const float3 c = cross_ref(dh.x, dh.y, dh.z, dv.x, dv.y, dv.z);  // the forward's values (reference rounding)
+  const float nrm = norm_ref(c);
   const float den = (nrm == 0.0f) ? 1.0f : nrm;
   const float3 nh = make_float3(c.x / den, c.y / den, c.z / den);
   if (n_out) *n_out = make_float3(nh.x * vf, nh.y * vf, nh.z * vf);

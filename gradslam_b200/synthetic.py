@@ -34,16 +34,10 @@ def _room_from_cam(s, b, motion_scale=1.0, yaw0=0.0):
 
 
 def make_sequence(B, L, H, W, seed=0, hole_fraction=0.02, motion_scale=1.0, pin_memory=False,
-                  isolated_holes=False, yaw0=0.0):
+                  yaw0=0.0):
     """Returns (rgb (B,L,H,W,3), depth (B,L,H,W,1), intrinsics (B,1,4,4), poses (B,L,4,4)), all float32 CPU.
 
     poses are camera-to-world with frame 0 of every element at identity (world = camera 0).
-
-    isolated_holes=True confines the depth holes to even rows, so that no valid pixel has BOTH its
-    right and its lower neighbour missing.  At such pixels the normal is the normalised cross product
-    of two identical vectors: exactly zero in IEEE arithmetic without FMA, but normalised rounding
-    garbage wherever `a*b - b*a` is contracted to an FMA (as the reference's torch.cross does on
-    AVX2 CPUs).  Fixtures that pin the oracle against the reference use isolated holes.
 
     yaw0 turns the first camera about the vertical axis.  With yaw0 = 0 (SURVEY.md's scene) the 62-degree
     horizontal field of view only sees the far wall, so point-to-plane ICP observes 3 of the 6 degrees of
@@ -70,8 +64,6 @@ def make_sequence(B, L, H, W, seed=0, hole_fraction=0.02, motion_scale=1.0, pin_
             poses[b, s] = torch.from_numpy((T0_inv @ T).astype(np.float32))
     if hole_fraction > 0:
         holes = torch.rand((B, L, H, W, 1), generator=gen) < hole_fraction
-        if isolated_holes:
-            holes[:, :, 1::2] = False
         depth[holes] = 0.0
     rgb = torch.empty((B, L, H, W, 3), dtype=torch.float32, pin_memory=pin_memory)
     torch.rand((B, L, H, W, 3), generator=gen, out=rgb)

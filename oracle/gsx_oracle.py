@@ -31,9 +31,16 @@ kernels can be BIT-exact on every decision (thresholds, rounding to pixels,
 argmin keys) the oracle fixes one order:  every product and sum is rounded
 separately to float32 (no FMA) and 3-term sums associate left to right,
 `(a*x + b*y) + c*z`, then `+ t`; square roots and the confidence weight's exp are
-taken in float64 and rounded once (correctly rounded float32 results).  Differences
-from the reference are at the 1-ulp level and are covered by the tolerances in
-the golden tests.
+taken in float64 and rounded once (correctly rounded float32 results).  The one
+place where the reference's own rounding is known and matters for DECISIONS is the
+normal estimate: its CPU torch.cross evaluates `a*b - c*d` as fma(a, b, -(c*d)) and
+Tensor.norm as sqrt(fma(z,z,fma(y,y,x*x))) - at pixels whose right and lower
+neighbours are both missing the two differences are equal and the contracted cross
+product is rounding residue, not 0, which after normalisation decides whether a map
+point matches.  The oracle (oracle/normal_fma.c) and the kernels (gsx_common.cuh)
+use exactly that arithmetic, so local normal maps are bit-identical to the
+reference's.  Remaining differences from the reference are at the 1-ulp level and
+are covered by the tolerances in the golden tests.
 
 One deliberate deviation: the reference's merge rewrites EVERY map point as
 `(c*p) * (1/c)` each frame (fusionutils.py:682-699 operates on the whole padded
@@ -163,10 +170,9 @@ def frame_maps(depth, K, poses=None):
     dv[..., :-1, :, :] = vert[..., 1:, :, :] - vert[..., :-1, :, :]
     dh[..., :, -1, :] = dh[..., :, -2, :]
     dv[..., -1, :, :] = dv[..., -2, :, :]
-    cx = dh[..., 1] * dv[..., 2] - dh[..., 2] * dv[..., 1]
-    cy = dh[..., 2] * dv[..., 0] - dh[..., 0] * dv[..., 2]
-    cz = dh[..., 0] * dv[..., 1] - dh[..., 1] * dv[..., 0]
-    nrm = _sqrt32((cx * cx + cy * cy) + cz * cz)
+    # torch.cross / Tensor.norm as the reference's CPU build rounds them (oracle/normal_fma.c)
+    cross, nrm = cross_norm_fma(dh, dv)
+    cx, cy, cz = cross[..., 0], cross[..., 1], cross[..., 2]
     den = torch.where(nrm == 0, torch.ones_like(nrm), nrm)
     normal = torch.stack([(cx / den) * vf, (cy / den) * vf, (cz / den) * vf], -1)
 
@@ -398,13 +404,13 @@ _knn_lib = None
 
 
 def build_c(force=False):
-    """Compile oracle/knn1.c -> oracle/_build/libgsx_oracle.so (gcc, no FMA contraction)."""
+    """Compile oracle/*.c -> oracle/_build/libgsx_oracle.so (gcc, no FMA contraction)."""
     out_dir = os.path.join(_HERE, "_build")
     os.makedirs(out_dir, exist_ok=True)
     so = os.path.join(out_dir, "libgsx_oracle.so")
-    src = os.path.join(_HERE, "knn1.c")
-    if force or not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src):
-        cmd = ["gcc", "-O2", "-fPIC", "-shared", "-ffp-contract=off", "-fopenmp", src, "-o", so]
+    srcs = [os.path.join(_HERE, f) for f in ("knn1.c", "normal_fma.c")]
+    if force or not os.path.exists(so) or any(os.path.getmtime(so) < os.path.getmtime(s) for s in srcs):
+        cmd = ["gcc", "-O2", "-fPIC", "-shared", "-ffp-contract=off", "-fopenmp"] + srcs + ["-o", so, "-lm"]
         subprocess.run(cmd, check=True)
     return so
 
@@ -416,7 +422,40 @@ def _lib():
         _knn_lib.gsx_oracle_knn1.argtypes = [ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_int64,
                                               ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]
         _knn_lib.gsx_oracle_knn1.restype = None
+        _knn_lib.gsx_oracle_cross_norm_fma.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64,
+                                                        ctypes.c_void_p, ctypes.c_void_p]
+        _knn_lib.gsx_oracle_cross_norm_fma.restype = None
     return _knn_lib
+
+
+class _CrossNormFma(torch.autograd.Function):
+    """(a x b, |a x b|) with the forward rounded by oracle/normal_fma.c and the analytic backward
+    (d(a x b) = da x b + a x db;  d|c| = c . dc / |c|), so the oracle stays differentiable for the gradient tests."""
+
+    @staticmethod
+    def forward(ctx, a, b):
+        shape = a.shape
+        a2 = a.detach().contiguous().float().view(-1, 3)
+        b2 = b.detach().contiguous().float().view(-1, 3)
+        c = torch.empty_like(a2)
+        n = torch.empty(a2.shape[0], dtype=F32)
+        _lib().gsx_oracle_cross_norm_fma(a2.data_ptr(), b2.data_ptr(), a2.shape[0], c.data_ptr(), n.data_ptr())
+        c, n = c.view(shape), n.view(shape[:-1])
+        ctx.save_for_backward(a, b, c, n)
+        return c, n
+
+    @staticmethod
+    def backward(ctx, g_c, g_n):
+        a, b, c, n = ctx.saved_tensors
+        den = torch.where(n == 0, torch.ones_like(n), n).unsqueeze(-1)
+        g = g_c + g_n.unsqueeze(-1) * c / den * (n != 0).unsqueeze(-1).to(c.dtype)
+        return torch.cross(b, g, dim=-1), torch.cross(g, a, dim=-1)
+
+
+def cross_norm_fma(a, b):
+    """a x b and its length for (...,3) float32 tensors, rounded like the reference's torch.cross / Tensor.norm on
+    the CPU (oracle/normal_fma.c; rgbdimages.py:733-734)."""
+    return _CrossNormFma.apply(a, b)
 
 
 def knn1(src, tgt, threads=0):

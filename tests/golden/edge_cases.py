@@ -7,7 +7,7 @@ EDGE_CASES = ["edge_empty_mid_frame", "edge_empty_first_frame", "edge_empty_elem
 
 
 def edge_inputs(name):
-    rgb, depth, K, poses = make_sequence(2, 4, 48, 64, seed=21, isolated_holes=True)
+    rgb, depth, K, poses = make_sequence(2, 4, 48, 64, seed=21)
     if name == "edge_empty_mid_frame":      # an all-invalid frame in the middle of every sequence
         depth[:, 2] = 0
     elif name == "edge_empty_first_frame":  # one sequence starts with an all-invalid frame (its map starts later)

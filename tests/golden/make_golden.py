@@ -7,10 +7,12 @@ there) and writes
 
   tests/golden/msrd_b2s3.npz   the reference's own golden vectors for K1 (tests/data/msrd_b2s3/*.npy:
                                depths, intrinsics, poses -> vertex / normal / global maps), re-packed losslessly
-  tests/golden/ref_slam.npz    reference outputs on seeded synthetic sequences (gradslam_b200.synthetic,
-                               isolated_holes=True): PointFusion / ICPSLAM final maps + poses for odom in
-                               {gt, icp, gradicp}, the three correspondence tables of one fusion step, and
-                               an ICP / gradICP transform recovery case.
+  tests/golden/ref_slam.npz    reference outputs on seeded synthetic sequences (gradslam_b200.synthetic, the
+                               bench's own input distribution: 2 % random depth holes): PointFusion / ICPSLAM
+                               final maps + poses for odom in {gt, icp, gradicp}, the frame maps (K1) of one
+                               sequence, the three correspondence tables of one fusion step, an ICP / gradICP
+                               transform recovery case, and one FULL-SIZE run (640x480, B=1, L=6, odom=gt):
+                               per-frame map sizes, float64 checksums and every 53rd surfel of the final map.
 
 The inputs of ref_slam.npz are NOT stored: the tests regenerate them from the recorded seeds.
 """
@@ -50,6 +52,10 @@ SLAM_CASES = [
 ]
 
 
+FULL_L = 6         # frames of the full-size run
+FULL_STRIDE = 53   # every 53rd surfel of its final map is stored
+
+
 def pack_map(prefix, pc, out):
     out[prefix + "/counts"] = np.array([int(c) for c in pc.num_points_per_pointcloud], dtype=np.int64)
     for b in range(len(pc)):
@@ -70,15 +76,42 @@ def main():
     out = {}
     # ---- full SLAM runs ----------------------------------------------------------------------------------
     for name, cls, B, L, H, W, seed, kw in SLAM_CASES:
-        rgb, depth, K, poses = make_sequence(B, L, H, W, seed=seed, isolated_holes=True)
+        rgb, depth, K, poses = make_sequence(B, L, H, W, seed=seed)
         slam = (PointFusion if cls == "PointFusion" else ICPSLAM)(**kw)
         pc, rec = slam(RGBDImages(rgb, depth, K, poses))
         pack_map(name, pc, out)
         out[name + "/poses"] = rec.numpy()
         print(name, out[name + "/counts"])
 
+    # ---- frame maps (K1) on the bench's input distribution (holes next to holes included) --------------------
+    rgb, depth, K, poses = make_sequence(2, 2, 60, 80, seed=6)
+    fr = RGBDImages(rgb, depth, K, poses)
+    out["k1/vertex"] = fr.vertex_map.numpy()
+    out["k1/normal"] = fr.normal_map.numpy()
+    out["k1/gvertex"] = fr.global_vertex_map.numpy()
+    out["k1/gnormal"] = fr.global_normal_map.numpy()
+
+    # ---- full size: BASELINE.json's headline frame size, default holes, B=1, L=6 -----------------------------
+    rgb, depth, K, poses = make_sequence(1, FULL_L, 480, 640, seed=0)
+    frames = RGBDImages(rgb, depth, K, poses)
+    slam = PointFusion(odom="gt")
+    pc = Pointclouds()
+    sizes = []
+    for s in range(FULL_L):
+        pc, _ = slam.step(pc, frames[:, s], None, inplace=True)
+        sizes.append(int(pc.num_points_per_pointcloud[0]))
+    out["full480/sizes"] = np.array(sizes, dtype=np.int64)
+    idx = np.arange(0, sizes[-1], FULL_STRIDE)
+    for name, lst in (("points", pc.points_list), ("normals", pc.normals_list), ("colors", pc.colors_list),
+                      ("ccounts", pc.features_list)):
+        a = lst[0].numpy()
+        out["full480/%s_sample" % name] = a[idx]
+        out["full480/%s_sum" % name] = a.astype(np.float64).sum(0)
+        out["full480/%s_abs_sum" % name] = np.abs(a.astype(np.float64)).sum(0)
+    print("full480 sizes", sizes)
+
     # ---- one fusion step, table by table -----------------------------------------------------------------
-    rgb, depth, K, poses = make_sequence(2, 3, 64, 64, seed=4, isolated_holes=True)
+    rgb, depth, K, poses = make_sequence(2, 3, 64, 64, seed=4)
     frames = RGBDImages(rgb, depth, K, poses)
     slam = PointFusion(odom="gt")
     pc = Pointclouds()

@@ -50,7 +50,7 @@ def main():
     out = {}
 
     c = GRAD_CASES["pf_gt"]
-    rgb, depth, K, poses = make_sequence(c["B"], c["L"], c["H"], c["W"], seed=c["seed"], isolated_holes=True, yaw0=0.6)
+    rgb, depth, K, poses = make_sequence(c["B"], c["L"], c["H"], c["W"], seed=c["seed"], yaw0=0.6)
     d, col = depth.clone().requires_grad_(True), rgb.clone().requires_grad_(True)
     pc, _ = PointFusion(odom="gt")(RGBDImages(col, d, K, poses))
     n = int(pc.num_points_per_pointcloud[0])
@@ -79,7 +79,7 @@ def main():
         print("%s: |d_src| max %.3e" % (name, s.grad.abs().max()))
 
     c = GRAD_CASES["icpslam"]
-    rgb, depth, K, poses = make_sequence(c["B"], c["L"], c["H"], c["W"], seed=c["seed"], isolated_holes=True, yaw0=0.6)
+    rgb, depth, K, poses = make_sequence(c["B"], c["L"], c["H"], c["W"], seed=c["seed"], yaw0=0.6)
     d = depth.clone().requires_grad_(True)
     _, rec = ICPSLAM(odom="gradicp", numiters=c["numiters"], dsratio=c["dsratio"])(RGBDImages(rgb, d, K, poses))
     w = torch.randn(rec.shape, generator=torch.Generator().manual_seed(c["wseed"]))

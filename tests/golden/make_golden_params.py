@@ -56,7 +56,7 @@ def main():
                 out["%s/ccounts/%d" % (name, b)] = pc.features_list[b].numpy()
         print(name, out[name + "/counts"])
     for name, cls, B, L, H, W, seed, seq_kw, kw in PARAM_CASES:
-        rgb, depth, K, poses = make_sequence(B, L, H, W, seed=seed, isolated_holes=True, **seq_kw)
+        rgb, depth, K, poses = make_sequence(B, L, H, W, seed=seed, **seq_kw)
         slam = (PointFusion if cls == "PointFusion" else ICPSLAM)(**kw)
         pc, rec = slam(RGBDImages(rgb, depth, K, poses))
         pack_map(name, pc, out)

@@ -40,7 +40,7 @@ def test_backproject_backward_matches_autograd(shape):
     import gradslam_b200 as gs
 
     B, L, H, W = shape
-    rgb, depth, K, poses = make_sequence(B, L, H, W, seed=21, isolated_holes=True)  # no degenerate cross products
+    rgb, depth, K, poses = make_sequence(B, L, H, W, seed=21)  # no degenerate cross products
     g = torch.Generator().manual_seed(3)
     ups = [torch.randn(B, L, H, W, 3, generator=g).to(DEV) for _ in range(4)]
     # engine
@@ -67,7 +67,7 @@ def test_backproject_backward_matches_autograd(shape):
 def test_backward_only_global_maps_and_no_pose_grad():
     import gradslam_b200 as gs
 
-    rgb, depth, K, poses = make_sequence(1, 2, 20, 28, seed=22, isolated_holes=True)
+    rgb, depth, K, poses = make_sequence(1, 2, 20, 28, seed=22)
     d1 = depth.to(DEV).requires_grad_(True)
     fr = gs.RGBDImages(rgb.to(DEV), d1, K.to(DEV), poses.to(DEV))
     w = torch.randn(1, 2, 20, 28, 3, device=DEV)
@@ -116,7 +116,7 @@ def test_icpslam_pose_gradient_wrt_live_depth():
     import gsx_oracle as oracle
 
     B, L, H, W = 1, 2, 32, 40
-    rgb, depth, K, poses = make_sequence(B, L, H, W, seed=33, isolated_holes=True, yaw0=0.6)
+    rgb, depth, K, poses = make_sequence(B, L, H, W, seed=33, yaw0=0.6)
     w = torch.randn(4, 4, generator=torch.Generator().manual_seed(2))
     d_ref = depth.clone().requires_grad_(True)
     ref = oracle.run_slam(rgb, d_ref, K, poses, mode="aggregate", odom="gradicp", numiters=3, dsratio=2)
@@ -143,7 +143,7 @@ def test_pointfusion_map_gradients_match_oracle_autograd(B, L):
     import gsx_oracle as oracle
 
     H, W = 24, 32
-    rgb, depth, K, poses = make_sequence(B, L, H, W, seed=41, isolated_holes=True, yaw0=0.6)
+    rgb, depth, K, poses = make_sequence(B, L, H, W, seed=41, yaw0=0.6)
     d_ref, c_ref = depth.clone().requires_grad_(True), rgb.clone().requires_grad_(True)
     ref = oracle.run_slam(c_ref, d_ref, K, poses, odom="gt")
     g = torch.Generator().manual_seed(5)
@@ -190,7 +190,7 @@ def test_merge_append_op_gradients_wrt_previous_map():
     from gradslam_b200.slam import fusionutils as fu
 
     B, H, W = 2, 20, 28
-    rgb, depth, K, poses = make_sequence(B, 2, H, W, seed=43, isolated_holes=True, yaw0=0.6)
+    rgb, depth, K, poses = make_sequence(B, 2, H, W, seed=43, yaw0=0.6)
     frames = gs.RGBDImages(rgb.to(DEV), depth.to(DEV), K.to(DEV), poses.to(DEV))
     with torch.no_grad():
         base = fu.update_map_fusion(gs.Pointclouds(device=DEV), frames[:, 0], 0.05, 0.94, 0.6)

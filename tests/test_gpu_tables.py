@@ -16,11 +16,11 @@ GOLD = os.path.join(os.path.dirname(__file__), "golden")
 DOT_TH = math.cos(20 * math.pi / 180)
 
 
-def _scenario(isolated):
+def _scenario():
     import gradslam_b200 as gs
     from gradslam_b200.slam import fusionutils
 
-    rgb, depth, K, poses = make_sequence(2, 3, 64, 64, seed=4, isolated_holes=isolated)
+    rgb, depth, K, poses = make_sequence(2, 3, 64, 64, seed=4)
     frames = gs.RGBDImages(rgb.to(DEV), depth.to(DEV), K.to(DEV), poses.to(DEV))
     pc = gs.Pointclouds(device=DEV)
     smap = oracle.SurfelMap()
@@ -31,9 +31,8 @@ def _scenario(isolated):
     return gs, fusionutils, (rgb, depth, K, poses), frames, pc, smap
 
 
-@pytest.mark.parametrize("isolated", [True, False])
-def test_tables_match_oracle_and_frozen_reference(isolated):
-    gs, fu, (rgb, depth, K, poses), frames, pc, smap = _scenario(isolated)
+def test_tables_match_oracle_and_frozen_reference():
+    gs, fu, (rgb, depth, K, poses), frames, pc, smap = _scenario()
     live = frames[:, 2]
     maps = oracle.frame_maps(depth[:, 2:3], K, poses[:, 2:3])
     gv, gn = maps["gvertex"][:, 0], maps["gnormal"][:, 0]
@@ -47,11 +46,11 @@ def test_tables_match_oracle_and_frozen_reference(isolated):
     r_unique = oracle.find_best_unique_correspondences(smap, gv, r_similar)
     assert torch.equal(unique.cpu(), r_unique)
     assert torch.equal(fu.find_correspondences(pc, live, 0.05, DOT_TH).cpu(), r_unique)
-    if isolated:  # the same tables, frozen from the unmodified reference
-        ref = np.load(os.path.join(GOLD, "ref_slam.npz"))
-        assert torch.equal(active.cpu(), torch.from_numpy(ref["tables/active"]))
-        assert torch.equal(similar.cpu(), torch.from_numpy(ref["tables/similar"]))
-        assert torch.equal(unique.cpu(), torch.from_numpy(ref["tables/unique"]))
+    # the same tables, frozen from the unmodified reference
+    ref = np.load(os.path.join(GOLD, "ref_slam.npz"))
+    assert torch.equal(active.cpu(), torch.from_numpy(ref["tables/active"]))
+    assert torch.equal(similar.cpu(), torch.from_numpy(ref["tables/similar"]))
+    assert torch.equal(unique.cpu(), torch.from_numpy(ref["tables/unique"]))
     # fuse_with_map from the table == fused update == oracle
     fused = fu.fuse_with_map(pc, live, unique, 0.6, inplace=False)
     direct = fu.update_map_fusion(pc, live, 0.05, DOT_TH, 0.6, inplace=False)

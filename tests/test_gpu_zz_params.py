@@ -45,7 +45,7 @@ def test_slam_with_other_parameters(frozen, case):
     import gradslam_b200 as gs
 
     name, cls, mode, B, L, H, W, seed, seq_kw, kw = case
-    rgb, depth, K, poses = make_sequence(B, L, H, W, seed=seed, isolated_holes=True, **seq_kw)
+    rgb, depth, K, poses = make_sequence(B, L, H, W, seed=seed, **seq_kw)
     slam = getattr(gs, cls)(device=DEV, **kw)
     pc, rec = slam(gs.RGBDImages(rgb.to(DEV), depth.to(DEV), K.to(DEV), poses.to(DEV)))
     ref = oracle.run_slam(rgb, depth, K, poses, mode=mode, **kw)

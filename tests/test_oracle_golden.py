@@ -40,10 +40,23 @@ def test_vertex_maps_match_reference_golden(msrd):
 def test_normal_maps_match_reference_golden(msrd):
     maps = oracle.frame_maps(msrd["depths"], msrd["intrinsics"], msrd["poses"])
     for got, want in ((maps["normal"], msrd["normal_map"]), (maps["gnormal"], msrd["global_normal_map"])):
-        # reference criterion: >= 99 % of elements within squared error 1e-5 (test_rgbdimages.py:118-120, 152-165);
-        # the rest are pixels whose cross product cancels exactly (FMA-dependent garbage in the reference).
+        # reference criterion: >= 99 % of elements within squared error 1e-5 (test_rgbdimages.py:118-120, 152-165).
+        # The .npy vectors were produced by a build that evaluates the cross product without FMA (exactly 0 where a
+        # pixel's right and lower neighbours are both missing); the reference's CPU build in the build container
+        # contracts it (rounding residue there), which is what the oracle follows - the frozen run of THAT build is
+        # compared bit for bit in test_frame_maps_equal_frozen_reference_run.
         frac = (((got - want) ** 2) < 1e-5).float().mean().item()
-        assert frac > 0.999, frac
+        assert frac > 0.99, frac
+    # away from those pixels the agreement is tight
+    d = msrd["depths"][..., 0]
+    right = torch.zeros_like(d, dtype=torch.bool)
+    below = torch.zeros_like(d, dtype=torch.bool)
+    right[..., :, :-1] = d[..., :, 1:] <= 0
+    right[..., :, -1] = right[..., :, -2]
+    below[..., :-1, :] = d[..., 1:, :] <= 0
+    below[..., -1, :] = below[..., -2, :]
+    regular = ~(right & below)
+    assert ((((maps["normal"] - msrd["normal_map"]) ** 2) < 1e-5)[regular]).float().mean() > 0.999
     # normals are zero exactly where the depth is missing (test_rgbdimages.py:137-140)
     invalid = ~(msrd["depths"][..., 0] > 0)
     assert maps["normal"][invalid].abs().max() == 0
@@ -197,22 +210,58 @@ CASES = [
 @pytest.mark.parametrize("case", CASES, ids=[c[0] for c in CASES])
 def test_slam_runs_match_frozen_reference(ref, case):
     name, mode, B, L, H, W, seed, kw = case
-    rgb, depth, K, poses = make_sequence(B, L, H, W, seed=seed, isolated_holes=True)
+    rgb, depth, K, poses = make_sequence(B, L, H, W, seed=seed)
     res = oracle.run_slam(rgb, depth, K, poses, mode=mode, **kw)
     assert res.map.counts() == ref[name + "/counts"].tolist()
-    # north_star tolerances: 1e-4 on poses, 1e-3 on fused point coordinates (we are ~100x inside)
-    torch.testing.assert_close(res.poses, torch.from_numpy(ref[name + "/poses"]), rtol=0, atol=1e-5)
+    # north_star tolerances: 1e-4 on poses, 1e-3 on fused point coordinates.  Ground-truth odometry is ~100x inside;
+    # the ICP loops amplify the 1-ulp differences of the reference's BLAS-ordered sums (LM accept / reject, 8-10
+    # iterations), measured up to 3.6e-5 on a pose and 9e-5 on a point, so they are held to half the north_star bounds.
+    ptol, xtol = (1e-5, 2e-5) if kw["odom"] == "gt" else (5e-5, 5e-4)
+    torch.testing.assert_close(res.poses, torch.from_numpy(ref[name + "/poses"]), rtol=0, atol=ptol)
     for b in range(B):
-        torch.testing.assert_close(res.map.points[b], torch.from_numpy(ref["%s/points/%d" % (name, b)]), rtol=0, atol=2e-5)
-        torch.testing.assert_close(res.map.normals[b], torch.from_numpy(ref["%s/normals/%d" % (name, b)]), rtol=0, atol=2e-5)
+        torch.testing.assert_close(res.map.points[b], torch.from_numpy(ref["%s/points/%d" % (name, b)]), rtol=0, atol=xtol)
+        torch.testing.assert_close(res.map.normals[b], torch.from_numpy(ref["%s/normals/%d" % (name, b)]), rtol=0, atol=xtol)
         torch.testing.assert_close(res.map.colors[b], torch.from_numpy(ref["%s/colors/%d" % (name, b)]), rtol=0, atol=2e-6)
         if mode == "pointfusion":
             torch.testing.assert_close(res.map.ccounts[b], torch.from_numpy(ref["%s/ccounts/%d" % (name, b)]), rtol=1e-6, atol=1e-7)
 
 
+def test_frame_maps_equal_frozen_reference_run(ref):
+    """K1 on the bench's input distribution (random holes, so pixels whose right and lower neighbours are both missing
+    occur): local vertex and normal maps are BIT-identical to the reference's CPU run (the normal's cross product and
+    length follow its FMA rounding); the global maps go through the reference's einsum (BLAS order) and agree to
+    an ulp."""
+    rgb, depth, K, poses = make_sequence(2, 2, 60, 80, seed=6)
+    maps = oracle.frame_maps(depth, K, poses)
+    assert torch.equal(maps["vertex"], torch.from_numpy(ref["k1/vertex"]))
+    assert torch.equal(maps["normal"], torch.from_numpy(ref["k1/normal"]))
+    torch.testing.assert_close(maps["gvertex"], torch.from_numpy(ref["k1/gvertex"]), rtol=0, atol=1e-6)
+    torch.testing.assert_close(maps["gnormal"], torch.from_numpy(ref["k1/gnormal"]), rtol=0, atol=2.5e-7)
+    # the degenerate pixels exist in this input and their normals are NOT zero (neither here nor in the reference)
+    d = depth[..., 0]
+    deg = (d[:, :, :-1, :-1] > 0) & (d[:, :, :-1, 1:] <= 0) & (d[:, :, 1:, :-1] <= 0)
+    assert deg.sum() > 0
+
+
+def test_full_size_run_matches_frozen_reference(ref):
+    """640x480, B=1, L=6, odom=gt on the bench's input distribution against the unmodified reference: map sizes after
+    every frame, checksums and a 1-in-53 sample of the final surfels (tests/golden/fullsize.py states the bounds)."""
+    from golden.fullsize import FULL_L, check_against_frozen_reference
+
+    rgb, depth, K, poses = make_sequence(1, FULL_L, 480, 640, seed=0)
+    dot_th = math.cos(20 * math.pi / 180)
+    smap = oracle.SurfelMap()
+    sizes = []
+    for s in range(FULL_L):
+        maps = oracle.frame_maps(depth[:, s:s + 1], K, poses[:, s:s + 1])
+        smap = oracle.update_map_fusion(smap, maps, rgb[:, s:s + 1], poses[:, s], K[:, 0], 0.05, dot_th, 0.6)
+        sizes.append(smap.counts()[0])
+    check_against_frozen_reference(ref, sizes, smap.points[0], smap.normals[0], smap.colors[0], smap.ccounts[0])
+
+
 def test_correspondence_tables_match_frozen_reference(ref):
     """Index work: the three tables of one fusion step are identical, row for row, to the reference's."""
-    rgb, depth, K, poses = make_sequence(2, 3, 64, 64, seed=4, isolated_holes=True)
+    rgb, depth, K, poses = make_sequence(2, 3, 64, 64, seed=4)
     dot_th = math.cos(20 * math.pi / 180)
     smap = oracle.SurfelMap()
     for s in range(2):
@@ -303,7 +352,7 @@ def _close_grad(got, want, rtol, atol_rel):
 
 
 def test_oracle_pointfusion_gradients_match_reference(ref_grad):
-    rgb, depth, K, poses = make_sequence(1, 2, 24, 32, seed=41, isolated_holes=True, yaw0=0.6)
+    rgb, depth, K, poses = make_sequence(1, 2, 24, 32, seed=41, yaw0=0.6)
     d, c = depth.clone().requires_grad_(True), rgb.clone().requires_grad_(True)
     res = oracle.run_slam(c, d, K, poses, odom="gt")
     n = res.map.counts()[0]
@@ -332,7 +381,7 @@ def test_oracle_icp_gradients_match_reference(ref_grad, name):
 
 
 def test_oracle_icpslam_pose_gradient_matches_reference(ref_grad):
-    rgb, depth, K, poses = make_sequence(1, 2, 32, 40, seed=17, isolated_holes=True, yaw0=0.6)
+    rgb, depth, K, poses = make_sequence(1, 2, 32, 40, seed=17, yaw0=0.6)
     d = depth.clone().requires_grad_(True)
     res = oracle.run_slam(rgb, d, K, poses, mode="aggregate", odom="gradicp", numiters=3, dsratio=2)
     torch.testing.assert_close(res.poses.detach(), torch.from_numpy(ref_grad["icpslam/poses"]), rtol=0, atol=1e-5)
@@ -365,7 +414,7 @@ def ref_params():
 @pytest.mark.parametrize("case", PARAM_CASES, ids=[c[0] for c in PARAM_CASES])
 def test_slam_runs_with_other_parameters_match_frozen_reference(ref_params, case):
     name, mode, B, L, H, W, seed, seq_kw, kw = case
-    rgb, depth, K, poses = make_sequence(B, L, H, W, seed=seed, isolated_holes=True, **seq_kw)
+    rgb, depth, K, poses = make_sequence(B, L, H, W, seed=seed, **seq_kw)
     res = oracle.run_slam(rgb, depth, K, poses, mode=mode, **kw)
     assert res.map.counts() == ref_params[name + "/counts"].tolist()
     torch.testing.assert_close(res.poses, torch.from_numpy(ref_params[name + "/poses"]), rtol=0, atol=1e-5)
