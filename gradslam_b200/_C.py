@@ -34,33 +34,28 @@ SIGNATURES = {
                 c_vp, c_i64, c_vp]),
     "gsx_fusion_workspace_bytes": (c_i64, [c_int, c_int, c_int]),
     "gsx_fusion_workspace_stats_offset": (c_i64, [c_int, c_int, c_int]),
+    "gsx_fusion_frame_records": (
+        c_int, [c_vp, c_i64, c_vp, c_i64, c_vp, c_i64, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_double, c_vp, c_vp]),
     "gsx_fusion_project_select": (
-        c_int, [c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_vp, c_i64, c_vp, c_i64, c_vp, c_i64, c_vp, c_vp, c_int, c_int,
-                c_int, c_float, c_float, c_vp, c_vp]),
+        c_int, [c_vp, c_vp, c_i64, c_i64, c_vp, c_i64, c_vp, c_i64, c_int, c_int, c_int, c_float, c_float, c_vp, c_vp]),
     "gsx_fusion_merge_append": (
-        c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_vp, c_i64, c_vp, c_i64, c_vp, c_i64, c_vp, c_i64, c_vp,
-                c_vp, c_int, c_int, c_int, c_double, c_vp, c_u32, c_vp, c_vp]),
-    "gsx_fusion_merge_append_fwd": (
-        c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_vp, c_i64, c_vp, c_i64, c_vp, c_i64, c_vp, c_vp, c_int,
-                c_int, c_int, c_double, c_vp, c_u32, c_vp, c_vp, c_vp]),
+        c_int, [c_vp, c_vp, c_int, c_vp, c_vp, c_i64, c_vp, c_i64, c_int, c_int, c_int, c_vp, c_vp, c_vp, c_vp]),
     "gsx_fusion_merge_append_bwd": (
-        c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_vp, c_vp, c_vp, c_vp, c_i64, c_vp, c_vp, c_vp, c_vp,
-                c_int, c_int, c_int, c_double, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
+        c_int, [c_vp, c_vp, c_vp, c_vp, c_int, c_i64, c_vp, c_vp, c_i64, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int,
+                c_double, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "gsx_pointfusion_sequence_groups": (c_int, [c_int]),
-    "gsx_pointfusion_sequence_gt_geo32": (
-        c_int, [c_vp, c_vp, c_vp, c_i64, c_i64, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_int,
-                c_float, c_float, c_double, c_vp, c_u32, c_vp, c_vp]),
     "gsx_pointfusion_sequence_gt": (
-        c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_int,
-                c_int, c_float, c_float, c_double, c_vp, c_vp, c_u32, c_vp, c_vp]),
+        c_int, [c_vp, c_vp, c_vp, c_i64, c_i64, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_int,
+                c_float, c_float, c_double, c_vp, c_vp, c_vp]),
+    "gsx_debug_fail_at_frame": (None, [c_int]),
     "gsx_ingest_raw": (c_int, [c_vp, c_vp, c_i64, c_double, c_int, c_vp, c_vp, c_vp]),
     "gsx_compact_scratch_bytes": (c_i64, [c_i64]),
     "gsx_compact_indices": (c_int, [c_vp, c_i64, c_vp, c_vp, c_vp, c_u32, c_vp]),
     "gsx_active_eval": (c_int, [c_vp, c_vp, c_i64, c_i64, c_vp, c_i64, c_vp, c_i64, c_int, c_int, c_int, c_vp, c_vp,
                                 c_vp]),
-    "gsx_similar_eval": (c_int, [c_vp, c_i64, c_vp, c_vp, c_i64, c_vp, c_vp, c_int, c_int, c_int, c_float, c_float,
-                                 c_vp, c_vp]),
-    "gsx_unique_select": (c_int, [c_vp, c_i64, c_vp, c_vp, c_i64, c_vp, c_int, c_int, c_int, c_vp, c_vp, c_vp, c_vp]),
+    "gsx_similar_eval": (c_int, [c_vp, c_i64, c_vp, c_i64, c_vp, c_vp, c_int, c_int, c_int, c_float, c_float, c_vp,
+                                 c_vp]),
+    "gsx_unique_select": (c_int, [c_vp, c_i64, c_vp, c_i64, c_vp, c_int, c_int, c_int, c_vp, c_vp, c_vp, c_vp]),
     "gsx_records_from_table": (c_int, [c_vp, c_i64, c_i64, c_int, c_int, c_int, c_vp, c_vp]),
     "gsx_knn1_scratch_bytes": (c_i64, [c_int, c_int, c_int]),
     "gsx_icp_tgt_scratch_bytes": (c_i64, [c_int, c_i64]),
@@ -83,7 +78,7 @@ SIGNATURES = {
                 c_float, c_float, c_float, c_float, c_vp, c_vp, c_vp, c_i64, c_vp]),
     "gsx_icp_workspace_bytes": (c_i64, [c_int, c_int, c_int, c_int, c_i64]),
     "gsx_icp_localize": (
-        c_int, [c_vp, c_vp, c_vp, c_i64, c_i64, c_vp, c_i64, c_vp, c_i64, c_vp, c_i64, c_int, c_int, c_int, c_int,
+        c_int, [c_vp, c_vp, c_i64, c_i64, c_vp, c_i64, c_vp, c_i64, c_vp, c_i64, c_int, c_int, c_int, c_int,
                 c_int, c_int, c_float, c_int, c_float, c_float, c_float, c_float, c_float, c_vp, c_i64, c_vp, c_i64,
                 c_vp, c_i64, c_u32, c_vp, c_vp]),
 }

@@ -23,11 +23,10 @@ extern "C" int gsx_version(void) { return GSX_VERSION; }
 extern "C" const char *gsx_last_error(void) { return gsx::g_err; }
 
 namespace gsx {
-int fusion_frame_group(float *pts, float *nrm, float *col, float *cc, const int32_t *cin, int32_t *cout, int64_t cap,
-                       int64_t max_count, const float *poses, int64_t pose_bs, const float *K, int64_t K_bs,
-                       const float *depth, int64_t d_bs, const float *rgb, int64_t rgb_bs, int B_total, int b0, int nb,
-                       int H, int W, float dist_th, float dot_th, double sigma, void *workspace, uint32_t epoch,
-                       int32_t *overflow, cudaStream_t st, bool geo);
+int fusion_frame_group(float *geo, float *col, const int32_t *cin, int32_t *cout, int64_t cap, int64_t max_count,
+                       const float *poses, int64_t pose_bs, const float *K, int64_t K_bs, const float *depth,
+                       int64_t d_bs, const float *rgb, int64_t rgb_bs, int B_total, int b0, int nb, int H, int W,
+                       float dist_th, float dot_th, double sigma, void *workspace, int32_t *overflow, cudaStream_t st);
 
 // Batch elements own independent maps, so the sequence driver splits the batch into groups that walk the frame
 // sequence on their own streams: K2 of one group (issue-heavy: 60 % issue utilisation, 25 % DRAM) overlaps K4 of another
@@ -68,22 +67,28 @@ static GroupStreams *group_streams() {
 }
 }  // namespace gsx
 
+// Fault injection for the tests of the error path (tests/test_gpu_pointfusion.py): the sequence driver reports a launch
+// failure at frame `s` (once), after the earlier frames were enqueued on the group streams.  -1 = off.
+static int g_fail_at_frame = -1;
+extern "C" void gsx_debug_fail_at_frame(int s) { g_fail_at_frame = s; }
+
 extern "C" int gsx_pointfusion_sequence_groups(int B) { return B <= 0 ? 0 : gsx::sequence_groups(B); }
 
-static int sequence_gt(float *map_points, float *map_normals, float *map_colors, float *map_ccounts, int32_t *counts,
-                       int64_t capacity, int64_t max_count0, const float *depth, const float *rgb,
-                       const float *intrinsics, const float *poses, int B, int L, int s_begin, int s_end, int H, int W,
-                       float dist_th, float dot_th, double sigma, void *workspace, uint32_t epoch0,
-                       int32_t *overflow_flag, void *stream, bool geo) {
+extern "C" int gsx_pointfusion_sequence_gt(float *map_geometry, float *map_colors, int32_t *counts, int64_t capacity,
+                                           int64_t max_count0, const float *depth, const float *rgb,
+                                           const float *intrinsics, const float *poses, int B, int L, int s_begin,
+                                           int s_end, int H, int W, float dist_th, float dot_th, double sigma,
+                                           void *workspace, int32_t *overflow_flag, void *stream) {
   GSX_CHECK_ARG(B >= 0 && L >= 0 && H >= 2 && W >= 2, "gsx_pointfusion_sequence_gt: bad extents");
   GSX_CHECK_ARG(0 <= s_begin && s_begin <= s_end && s_end <= L, "gsx_pointfusion_sequence_gt: bad frame range");
   GSX_CHECK_ARG(counts && depth && rgb && intrinsics && poses, "gsx_pointfusion_sequence_gt: null pointer");
   if (B == 0 || s_begin == s_end) return 0;
-  GSX_CHECK_ARG(map_points && map_colors && (geo || (map_normals && map_ccounts)) && workspace && overflow_flag,
+  GSX_CHECK_ARG(map_geometry && map_colors && workspace && overflow_flag,
                 "gsx_pointfusion_sequence_gt: null map / workspace pointer");
+  GSX_CHECK_ARG(((reinterpret_cast<uintptr_t>(map_geometry) | reinterpret_cast<uintptr_t>(map_colors) |
+                  reinterpret_cast<uintptr_t>(workspace)) & 15) == 0,
+                "gsx_pointfusion_sequence_gt: map rows and workspace must be 16-byte aligned");
   GSX_CHECK_ARG(capacity <= 0x7fffffffll, "gsx_pointfusion_sequence_gt: capacity must fit int32 (counts are int32)");
-  GSX_CHECK_ARG(epoch0 >= 1 && epoch0 + (uint32_t)(s_end - s_begin) < (1u << 30),
-                "gsx_pointfusion_sequence_gt: epoch out of range");
   const int64_t P = (int64_t)H * W;
   cudaStream_t user = (cudaStream_t)stream;
   int G = gsx::sequence_groups(B);
@@ -95,53 +100,33 @@ static int sequence_gt(float *map_points, float *map_normals, float *map_colors,
     cudaEventRecord(gs->fork, user);
     for (int g = 0; g < G; ++g) cudaStreamWaitEvent(gs->stream[g], gs->fork, 0);
   }
-  for (int s = s_begin; s < s_end; ++s) {
+  int rc = 0;
+  for (int s = s_begin; s < s_end && rc == 0; ++s) {
     int32_t *cin = counts + (int64_t)(s & 1) * B;
     int32_t *cout = counts + (int64_t)((s + 1) & 1) * B;
     int64_t max_count = max_count0 + (int64_t)(s - s_begin) * P;
     if (max_count > capacity) max_count = capacity;
-    for (int g = 0; g < G; ++g) {
+    for (int g = 0; g < G && rc == 0; ++g) {
       const int b0 = (int)((int64_t)B * g / G), b1 = (int)((int64_t)B * (g + 1) / G);
-      const int rc = gsx::fusion_frame_group(
-          map_points, map_normals, map_colors, map_ccounts, cin, cout, capacity, max_count, poses + (int64_t)s * 16,
-          (int64_t)L * 16, intrinsics, 16, depth + (int64_t)s * P, (int64_t)L * P, rgb + (int64_t)s * P * 3,
-          (int64_t)L * P * 3, B, b0, b1 - b0, H, W, dist_th, dot_th, sigma, workspace,
-          epoch0 + (uint32_t)(s - s_begin), overflow_flag, G > 1 ? gs->stream[g] : user, geo);
-      if (rc) return rc;
+      if (s == g_fail_at_frame && g == G - 1) {
+        g_fail_at_frame = -1;
+        gsx::set_error("gsx_pointfusion_sequence_gt: injected failure at frame %d (gsx_debug_fail_at_frame)", s);
+        rc = 2;
+        break;
+      }
+      rc = gsx::fusion_frame_group(map_geometry, map_colors, cin, cout, capacity, max_count, poses + (int64_t)s * 16,
+                                   (int64_t)L * 16, intrinsics, 16, depth + (int64_t)s * P, (int64_t)L * P,
+                                   rgb + (int64_t)s * P * 3, (int64_t)L * P * 3, B, b0, b1 - b0, H, W, dist_th, dot_th,
+                                   sigma, workspace, overflow_flag, G > 1 ? gs->stream[g] : user);
     }
   }
+  // join ALWAYS, also after a failed launch: whatever was already enqueued on the group streams stays ordered before
+  // anything the caller enqueues next on its stream
   if (G > 1) {
     for (int g = 0; g < G; ++g) {
       cudaEventRecord(gs->join[g], gs->stream[g]);
       cudaStreamWaitEvent(user, gs->join[g], 0);
     }
   }
-  return 0;
-}
-
-extern "C" int gsx_pointfusion_sequence_gt(float *map_points, float *map_normals, float *map_colors,
-                                           float *map_ccounts, int32_t *counts, int64_t capacity,
-                                           int64_t max_count0, const float *depth, const float *rgb,
-                                           const float *intrinsics, const float *poses, int B, int L,
-                                           int s_begin, int s_end, int H, int W, float dist_th, float dot_th,
-                                           double sigma, float *scratch_maps,
-                                           void *workspace, uint32_t epoch0, int32_t *overflow_flag,
-                                           void *stream) {
-  (void)scratch_maps;
-  return sequence_gt(map_points, map_normals, map_colors, map_ccounts, counts, capacity, max_count0, depth, rgb,
-                     intrinsics, poses, B, L, s_begin, s_end, H, W, dist_th, dot_th, sigma, workspace, epoch0,
-                     overflow_flag, stream, false);
-}
-
-extern "C" int gsx_pointfusion_sequence_gt_geo32(float *map_geometry, float *map_colors, int32_t *counts,
-                                                 int64_t capacity, int64_t max_count0, const float *depth,
-                                                 const float *rgb, const float *intrinsics, const float *poses, int B,
-                                                 int L, int s_begin, int s_end, int H, int W, float dist_th,
-                                                 float dot_th, double sigma, void *workspace, uint32_t epoch0,
-                                                 int32_t *overflow_flag, void *stream) {
-  GSX_CHECK_ARG((reinterpret_cast<uintptr_t>(map_geometry) & 15) == 0,
-                "gsx_pointfusion_sequence_gt_geo32: geometry rows must be 16-byte aligned");
-  return sequence_gt(map_geometry, nullptr, map_colors, nullptr, counts, capacity, max_count0, depth, rgb, intrinsics,
-                     poses, B, L, s_begin, s_end, H, W, dist_th, dot_th, sigma, workspace, epoch0, overflow_flag, stream,
-                     true);
+  return rc;
 }

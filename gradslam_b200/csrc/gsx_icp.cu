@@ -93,8 +93,9 @@ __global__ void __launch_bounds__(1024) k_icp_gather_src(GatherSrcArgs a) {
 // ---------------------------------------------------------------------------------------------------------
 // gather: target cloud (stable compaction of lattice-active map points; decoupled look-back over tiles)
 // ---------------------------------------------------------------------------------------------------------
+constexpr int kGeoW = 8;  // floats per packed geometry row (px,py,pz,nx,ny,nz,ccount,0), see gsx_fusion.cu
 struct GatherTgtArgs {
-  const float *pts, *nrm;
+  const float *geo;  // (B,cap,8)
   const int32_t *counts;
   int64_t cap;
   const float *poses;
@@ -144,20 +145,21 @@ __global__ void __launch_bounds__(kIcpBlock) k_icp_gather_tgt(GatherTgtArgs a) {
   __syncthreads();
   const int tile = s_tile;
   const int count = a.counts[b];
-  const float *pts = a.pts + (int64_t)b * a.cap * 3;
-  const float *nrm = a.nrm + (int64_t)b * a.cap * 3;
+  const float *geo = a.geo + (int64_t)b * a.cap * kGeoW;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   int n[4], wexcl[4];
   bool keep[4];
-  float px[4], py[4], pz[4];
+  float px[4], py[4], pz[4], nx[4];
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
     n[j] = tile * 1024 + j * kIcpBlock + threadIdx.x;
     keep[j] = n[j] < count;
     const int nn = keep[j] ? n[j] : 0;
-    px[j] = __ldg(pts + (int64_t)nn * 3);
-    py[j] = __ldg(pts + (int64_t)nn * 3 + 1);
-    pz[j] = __ldg(pts + (int64_t)nn * 3 + 2);
+    const float4 g = __ldg(reinterpret_cast<const float4 *>(geo + (int64_t)nn * kGeoW));
+    px[j] = g.x;
+    py[j] = g.y;
+    pz[j] = g.z;
+    nx[j] = g.w;
   }
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
@@ -224,9 +226,10 @@ __global__ void __launch_bounds__(kIcpBlock) k_icp_gather_tgt(GatherTgtArgs a) {
         op[(int64_t)pos * 3 + 0] = px[j];
         op[(int64_t)pos * 3 + 1] = py[j];
         op[(int64_t)pos * 3 + 2] = pz[j];
-        on[(int64_t)pos * 3 + 0] = __ldg(nrm + (int64_t)n[j] * 3);
-        on[(int64_t)pos * 3 + 1] = __ldg(nrm + (int64_t)n[j] * 3 + 1);
-        on[(int64_t)pos * 3 + 2] = __ldg(nrm + (int64_t)n[j] * 3 + 2);
+        const float2 g = __ldg(reinterpret_cast<const float2 *>(geo + (int64_t)n[j] * kGeoW + 4));
+        on[(int64_t)pos * 3 + 0] = nx[j];
+        on[(int64_t)pos * 3 + 1] = g.x;
+        on[(int64_t)pos * 3 + 2] = g.y;
       } else if (a.overflow) {
         *a.overflow = 1;
       }
@@ -1014,7 +1017,7 @@ extern "C" int64_t gsx_icp_tgt_scratch_bytes(int B, int64_t tgt_capacity) {
   return 2 * up256((int64_t)B * tgt_capacity * 12) + grid_bytes(B, (int)tgt_capacity);
 }
 
-extern "C" int gsx_icp_localize(const float *map_points, const float *map_normals, const int32_t *counts,
+extern "C" int gsx_icp_localize(const float *map_geometry, const int32_t *counts,
                                 int64_t capacity, int64_t max_count, const float *depth, int64_t depth_bstride,
                                 const float *intrinsics, int64_t K_bstride, const float *prev_poses,
                                 int64_t prev_pose_bstride, int B, int H, int W, int ds, int mode, int numiters,
@@ -1022,9 +1025,10 @@ extern "C" int gsx_icp_localize(const float *map_points, const float *map_normal
                                 float B2p, float nu, void *tgt_scratch, int64_t tgt_capacity, float *poses_out,
                                 int64_t poses_out_bstride, void *workspace, int64_t workspace_map_capacity,
                                 uint32_t epoch, int32_t *overflow_flag, void *stream) {
-  GSX_CHECK_ARG(map_points && map_normals && counts && depth && intrinsics && prev_poses && poses_out && workspace &&
-                    tgt_scratch,
+  GSX_CHECK_ARG(map_geometry && counts && depth && intrinsics && prev_poses && poses_out && workspace && tgt_scratch,
                 "gsx_icp_localize: null pointer");
+  GSX_CHECK_ARG((reinterpret_cast<uintptr_t>(map_geometry) & 15) == 0,
+                "gsx_icp_localize: geometry rows must be 16-byte aligned");
   GSX_CHECK_ARG(B >= 1 && H >= 2 && W >= 2 && ds >= 1, "gsx_icp_localize: bad extents");
   GSX_CHECK_ARG(mode == 0 || mode == 1, "gsx_icp_localize: mode must be 0 (ICP) or 1 (gradICP)");
   GSX_CHECK_ARG(max_count <= capacity && tgt_capacity >= 1, "gsx_icp_localize: bad capacities");
@@ -1046,7 +1050,7 @@ extern "C" int gsx_icp_localize(const float *map_points, const float *map_normal
   if (tiles > w.tiles_cap) tiles = w.tiles_cap;
   if (tiles == 0) cudaMemsetAsync(w.tgt_count, 0, (size_t)B * 4, s);
   if (tiles > 0) {
-    GatherTgtArgs gt{map_points, map_normals, counts, capacity, prev_poses, prev_pose_bstride, intrinsics, K_bstride,
+    GatherTgtArgs gt{map_geometry, counts, capacity, prev_poses, prev_pose_bstride, intrinsics, K_bstride,
                      B, H, W, ds, (float)(W - 0.999), (float)(H - 0.999), tgt_p, tgt_n, w.tgt_count,
                      (int)tgt_capacity, w.tile_state, w.ticket, tiles, epoch, overflow_flag};
     k_icp_gather_tgt<<<dim3((unsigned)(tiles * B)), kIcpBlock, 0, s>>>(gt);

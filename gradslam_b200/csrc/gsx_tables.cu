@@ -9,6 +9,7 @@
 //   k_records_from_table per table row: store the row as the pixel's winner (input of K4 for fuse_with_map)
 //   k_compact            generic stable compaction flag[] -> ascending indices (single-pass decoupled look-back)
 #include "gsx_common.cuh"
+#include "gsx_thresholds.h"
 #include "../../include/gsx.h"
 
 namespace gsx {
@@ -103,8 +104,10 @@ __global__ void __launch_bounds__(kTB) k_compact(CompactArgs a) {
 }
 
 // ---- find_active_map_points ---------------------------------------------------------------------------------
+constexpr int kGeoW = 8;  // floats per packed geometry row (px,py,pz,nx,ny,nz,ccount,0), see gsx_fusion.cu
+
 struct ActiveArgs {
-  const float *pts;
+  const float *geo;
   const int32_t *counts;
   int64_t cap;
   int64_t width;  // slots per element in the flag arrays (host upper bound of the sizes)
@@ -130,8 +133,8 @@ __global__ void __launch_bounds__(kTB) k_active_eval(ActiveArgs a) {
   bool live = n < a.counts[b];
   int pix = 0;
   if (live) {
-    const float *p = a.pts + ((int64_t)b * a.cap + n) * 3;
-    const float3 q = rigid_apply(s_tinv, __ldg(p), __ldg(p + 1), __ldg(p + 2));
+    const float4 p = __ldg(reinterpret_cast<const float4 *>(a.geo + ((int64_t)b * a.cap + n) * kGeoW));
+    const float3 q = rigid_apply(s_tinv, p.x, p.y, p.z);
     const float hx = ((s_k[0] * q.x + s_k[1] * q.y) + s_k[2] * q.z) + s_k[3];
     const float hy = ((s_k[4] * q.x + s_k[5] * q.y) + s_k[6] * q.z) + s_k[7];
     const float hz = ((s_k[8] * q.x + s_k[9] * q.y) + s_k[10] * q.z) + s_k[11];
@@ -151,11 +154,11 @@ __global__ void __launch_bounds__(kTB) k_active_eval(ActiveArgs a) {
 struct RowArgs {
   const int64_t *table;
   int64_t rows;
-  const float *pts, *nrm, *cc;
+  const float *geo;  // (B,cap,8) packed geometry rows
   int64_t cap;
   const float *gv, *gn;  // (B,H,W,3)
   int B, H, W;
-  float dist_th, dot_th;
+  float d2_max, dot_th;  // sqrtf(d2) < dist_th  <=>  d2 <= d2_max (gsx_thresholds.h)
   uint8_t *flags;  // (rows)            k_similar_eval
   U128 *best;      // (B,H,W)           k_unique_select / k_records_from_table
 };
@@ -170,14 +173,14 @@ __global__ void __launch_bounds__(kTB) k_similar_eval(RowArgs a) {
   const int64_t b = a.table[r * 4], n = a.table[r * 4 + 1], h = a.table[r * 4 + 2], w = a.table[r * 4 + 3];
   bool ok = row_ok(a, b, n, h, w);
   if (ok) {
-    const float *p = a.pts + (b * a.cap + n) * 3;
-    const float *m = a.nrm + (b * a.cap + n) * 3;
+    const float *p = a.geo + (b * a.cap + n) * kGeoW;
+    const float *m = p + 3;
     const float *g = a.gv + ((b * a.H + h) * a.W + w) * 3;
     const float *q = a.gn + ((b * a.H + h) * a.W + w) * 3;
     const float dx = __ldg(g) - __ldg(p), dy = __ldg(g + 1) - __ldg(p + 1), dz = __ldg(g + 2) - __ldg(p + 2);
     const float d2 = (dx * dx + dy * dy) + dz * dz;
     const float dot = (__ldg(q) * __ldg(m) + __ldg(q + 1) * __ldg(m + 1)) + __ldg(q + 2) * __ldg(m + 2);
-    ok = (sqrtf(d2) < a.dist_th) && (dot > a.dot_th);
+    ok = (d2 <= a.d2_max) && (dot > a.dot_th);
   }
   a.flags[r] = ok ? 1 : 0;
 }
@@ -187,12 +190,12 @@ __global__ void __launch_bounds__(kTB) k_unique_select(RowArgs a) {
   if (r >= a.rows) return;
   const int64_t b = a.table[r * 4], n = a.table[r * 4 + 1], h = a.table[r * 4 + 2], w = a.table[r * 4 + 3];
   if (!row_ok(a, b, n, h, w)) return;
-  const float *p = a.pts + (b * a.cap + n) * 3;
+  const float *p = a.geo + (b * a.cap + n) * kGeoW;
   const float *g = a.gv + ((b * a.H + h) * a.W + w) * 3;
   // key of fusionutils.py:491-517: 1/(cc+1e-20), then (map - frame)^2 summed left to right, then n
   const float dx = __ldg(p) - __ldg(g), dy = __ldg(p + 1) - __ldg(g + 1), dz = __ldg(p + 2) - __ldg(g + 2);
   const float d2 = (dx * dx + dy * dy) + dz * dz;
-  const float inv_cc = 1.0f / (__ldg(a.cc + b * a.cap + n) + 1e-20f);
+  const float inv_cc = 1.0f / (__ldg(p + 6) + 1e-20f);
   unsigned int kb = __float_as_uint(inv_cc);
   kb = (kb & 0x80000000u) ? ~kb : (kb | 0x80000000u);
   const unsigned int rb = __float_as_uint(d2) | 0x80000000u;
@@ -207,13 +210,12 @@ __global__ void __launch_bounds__(kTB) k_records_from_table(RowArgs a) {
   a.best[(b * a.H + h) * a.W + w] = U128{~(unsigned long long)n, ~0ull >> 1};  // non-zero record holding n
 }
 
-// per pixel: is there a winner?  which map row?  (the record is consumed: the workspace is left clean)
-__global__ void __launch_bounds__(kTB) k_unique_emit(U128 *best, int64_t pixels, uint8_t *flags, int64_t *n_out) {
+// per pixel: is there a winner?  which map row?
+__global__ void __launch_bounds__(kTB) k_unique_emit(const U128 *best, int64_t pixels, uint8_t *flags, int64_t *n_out) {
   const int64_t i = (int64_t)blockIdx.x * kTB + threadIdx.x;
   if (i >= pixels) return;
   const U128 rec = best[i];
   const bool has = (rec.lo | rec.hi) != 0ull;
-  if (has) best[i] = U128{0ull, 0ull};
   flags[i] = has ? 1 : 0;
   n_out[i] = has ? (int64_t)(~rec.lo) : -1;
 }
@@ -249,65 +251,60 @@ extern "C" int gsx_compact_indices(const uint8_t *flags, int64_t n, int64_t *out
   return 0;
 }
 
-extern "C" int gsx_active_eval(const float *map_points, const int32_t *counts, int64_t capacity, int64_t width,
+extern "C" int gsx_active_eval(const float *map_geometry, const int32_t *counts, int64_t capacity, int64_t width,
                                const float *poses, int64_t pose_bstride, const float *intrinsics,
                                int64_t K_bstride, int B, int H, int W, uint8_t *flags, int32_t *hw, void *stream) {
-  GSX_CHECK_ARG(map_points && counts && poses && intrinsics && flags && hw, "gsx_active_eval: null pointer");
+  GSX_CHECK_ARG(map_geometry && counts && poses && intrinsics && flags && hw, "gsx_active_eval: null pointer");
   GSX_CHECK_ARG(B >= 1 && H >= 1 && W >= 1 && width >= 0 && width <= capacity, "gsx_active_eval: bad extents");
+  GSX_CHECK_ARG((reinterpret_cast<uintptr_t>(map_geometry) & 15) == 0, "gsx_active_eval: geometry rows must be 16-byte aligned");
   if (width == 0) return 0;
-  ActiveArgs a{map_points, counts, capacity, width, poses, pose_bstride, intrinsics, K_bstride, B, H, W,
+  ActiveArgs a{map_geometry, counts, capacity, width, poses, pose_bstride, intrinsics, K_bstride, B, H, W,
                (float)(W - 0.999), (float)(H - 0.999), flags, hw};
   k_active_eval<<<dim3((unsigned)tb_blocks(width), (unsigned)B), kTB, 0, (cudaStream_t)stream>>>(a);
   GSX_CHECK_LAUNCH("gsx_active_eval");
   return 0;
 }
 
-static int make_rows(RowArgs &a, const int64_t *table, int64_t rows, const float *p, const float *n, const float *c,
-                     int64_t cap, const float *gv, const float *gn, int B, int H, int W, float dist_th, float dot_th,
-                     uint8_t *flags, void *best) {
-  a = RowArgs{table, rows, p, n, c, cap, gv, gn, B, H, W, dist_th, dot_th, flags, (U128 *)best};
-  return 0;
-}
-
-extern "C" int gsx_similar_eval(const int64_t *table, int64_t rows, const float *map_points,
-                                const float *map_normals, int64_t capacity, const float *gvertex,
-                                const float *gnormal, int B, int H, int W, float dist_th, float dot_th,
-                                uint8_t *flags, void *stream) {
+extern "C" int gsx_similar_eval(const int64_t *table, int64_t rows, const float *map_geometry, int64_t capacity,
+                                const float *gvertex, const float *gnormal, int B, int H, int W, float dist_th,
+                                float dot_th, uint8_t *flags, void *stream) {
   if (rows == 0) return 0;
-  GSX_CHECK_ARG(table && map_points && map_normals && gvertex && gnormal && flags, "gsx_similar_eval: null pointer");
-  RowArgs a;
-  make_rows(a, table, rows, map_points, map_normals, nullptr, capacity, gvertex, gnormal, B, H, W, dist_th, dot_th,
-            flags, nullptr);
+  GSX_CHECK_ARG(table && map_geometry && gvertex && gnormal && flags, "gsx_similar_eval: null pointer");
+  RowArgs a{table, rows, map_geometry, capacity, gvertex, gnormal, B, H, W, sqrt_lt_threshold(dist_th), dot_th, flags,
+            nullptr};
   k_similar_eval<<<(unsigned)tb_blocks(rows), kTB, 0, (cudaStream_t)stream>>>(a);
   GSX_CHECK_LAUNCH("gsx_similar_eval");
   return 0;
 }
 
-extern "C" int gsx_unique_select(const int64_t *table, int64_t rows, const float *map_points,
-                                 const float *map_ccounts, int64_t capacity, const float *gvertex, int B, int H,
-                                 int W, void *workspace, uint8_t *pixel_flags, int64_t *pixel_n, void *stream) {
-  GSX_CHECK_ARG(workspace && pixel_flags && pixel_n, "gsx_unique_select: null pointer");
+// `records`: B*H*W 16-byte arg-min records (scratch; cleared here)
+extern "C" int gsx_unique_select(const int64_t *table, int64_t rows, const float *map_geometry, int64_t capacity,
+                                 const float *gvertex, int B, int H, int W, void *records, uint8_t *pixel_flags,
+                                 int64_t *pixel_n, void *stream) {
+  GSX_CHECK_ARG(records && pixel_flags && pixel_n, "gsx_unique_select: null pointer");
+  GSX_CHECK_ARG((reinterpret_cast<uintptr_t>(records) & 15) == 0, "gsx_unique_select: records must be 16-byte aligned");
   cudaStream_t s = (cudaStream_t)stream;
+  const int64_t pixels = (int64_t)B * H * W;
+  cudaMemsetAsync(records, 0, (size_t)pixels * 16, s);
   if (rows > 0) {
-    GSX_CHECK_ARG(table && map_points && map_ccounts && gvertex, "gsx_unique_select: null pointer");
-    RowArgs a;
-    make_rows(a, table, rows, map_points, nullptr, map_ccounts, capacity, gvertex, nullptr, B, H, W, 0.f, 0.f, nullptr,
-              workspace);
+    GSX_CHECK_ARG(table && map_geometry && gvertex, "gsx_unique_select: null pointer");
+    RowArgs a{table, rows, map_geometry, capacity, gvertex, nullptr, B, H, W, 0.f, 0.f, nullptr, (U128 *)records};
     k_unique_select<<<(unsigned)tb_blocks(rows), kTB, 0, s>>>(a);
   }
-  const int64_t pixels = (int64_t)B * H * W;
-  k_unique_emit<<<(unsigned)tb_blocks(pixels), kTB, 0, s>>>((U128 *)workspace, pixels, pixel_flags, pixel_n);
+  k_unique_emit<<<(unsigned)tb_blocks(pixels), kTB, 0, s>>>((const U128 *)records, pixels, pixel_flags, pixel_n);
   GSX_CHECK_LAUNCH("gsx_unique_select");
   return 0;
 }
 
+// Stores the rows of a unique table as the per-pixel winners of the fusion workspace (after gsx_fusion_frame_records
+// re-armed it, before gsx_fusion_merge_append consumes them): fuse_with_map on a caller-supplied table.
 extern "C" int gsx_records_from_table(const int64_t *table, int64_t rows, int64_t capacity, int B, int H, int W,
                                       void *workspace, void *stream) {
   if (rows == 0) return 0;
   GSX_CHECK_ARG(table && workspace, "gsx_records_from_table: null pointer");
-  RowArgs a;
-  make_rows(a, table, rows, nullptr, nullptr, nullptr, capacity, nullptr, nullptr, B, H, W, 0.f, 0.f, nullptr,
-            workspace);
+  const int64_t best_offset = ((int64_t)B * H * W * 32 + 255) / 256 * 256;  // frame records come first (gsx_fusion.cu)
+  RowArgs a{table, rows, nullptr, capacity, nullptr, nullptr, B, H, W, 0.f, 0.f, nullptr,
+            (U128 *)((char *)workspace + best_offset)};
   k_records_from_table<<<(unsigned)tb_blocks(rows), kTB, 0, (cudaStream_t)stream>>>(a);
   GSX_CHECK_LAUNCH("gsx_records_from_table");
   return 0;

@@ -28,14 +28,15 @@ def _check_provide_args(maps_pointclouds, frames_pointclouds, who):
 def _provide(prov, maps_pc, frames_pc, mode):
     kw = dict(lambda_max=getattr(prov, "lambda_max", 2.0), B=getattr(prov, "B", 1.0), B2=getattr(prov, "B2", 1.0),
               nu=getattr(prov, "nu", 200.0))
-    if _wants_grad(frames_pc._store["points"], maps_pc._store["points"], maps_pc._store["normals"]):
+    if _wants_grad(*frames_pc._grad_tensors(), *maps_pc._grad_tensors()):
         # differentiable mode: per-element taped loop, like the reference's providers (odometry/icp.py:84-97)
         Ts = [_taped_icp(frames_pc.points_list[b].unsqueeze(0), maps_pc.points_list[b].unsqueeze(0),
                          maps_pc.normals_list[b].unsqueeze(0), None, mode, prov.numiters, prov.damp,
                          prov.dist_thresh, **kw)[0] for b in range(len(maps_pc))]
         return torch.stack(Ts).unsqueeze(1)
-    src = frames_pc.points_padded
-    tgt, tgt_n = maps_pc.points_padded, maps_pc.normals_padded
+    # (the padded views are strided slices of the packed rows; the ICP kernels take dense (B,N,3) clouds)
+    src = frames_pc.points_padded.contiguous()
+    tgt, tgt_n = maps_pc.points_padded.contiguous(), maps_pc.normals_padded.contiguous()
     src_c = frames_pc._counts_dev[frames_pc._cur]
     tgt_c = maps_pc._counts_dev[maps_pc._cur]
     T, _ = icp_align(src, src_c, tgt, tgt_n, tgt_c, None, mode, prov.numiters, prov.damp, prov.dist_thresh,

@@ -425,7 +425,8 @@ def localize_against_map(pointclouds, live_frame, prev_frame, dsratio, odomprov)
     depth, d_bs = _frame_base(live.depth_image, H * W)
     K = live.intrinsics.contiguous()
     prev = prev_frame.poses.contiguous()
-    st = pointclouds._store
+    _C.require_cuda(pointclouds._geo, "pointclouds (geometry rows)")
+    geo = pointclouds._geo.contiguous()
     ws = _IcpWorkspace.get(dev, B, H, W, dsratio, pointclouds.capacity)
     # target capacity: lattice-active map points.  32 map points per lattice pixel on average is far beyond
     # anything a surfel map produces; if it is ever exceeded the kernel raises the map's overflow flag.
@@ -437,7 +438,7 @@ def localize_against_map(pointclouds, live_frame, prev_frame, dsratio, odomprov)
     dth = odomprov.dist_thresh
     with torch.cuda.device(dev):
         rc = _C.lib().gsx_icp_localize(
-            _C.ptr(st["points"]), _C.ptr(st["normals"]), _C.ptr(pointclouds._counts_dev[pointclouds._cur]),
+            _C.ptr(geo), _C.ptr(pointclouds._counts_dev[pointclouds._cur]),
             pointclouds.capacity, pointclouds._bound, _C.ptr(depth), d_bs, _C.ptr(K), 16, _C.ptr(prev), 16, B, H, W,
             int(dsratio), mode, int(odomprov.numiters), float(odomprov.damp), 0 if dth is None else 1,
             0.0 if dth is None else float(dth), float(getattr(odomprov, "lambda_max", 2.0)),

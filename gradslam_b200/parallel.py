@@ -3,15 +3,18 @@
 Sequences are independent (each batch element owns its map and pose chain), so a (B_total, L) job shards by
 contiguous blocks of B_total / world sequences per rank, one process per GPU, and NO traffic crosses GPUs
 while the L frames are fused.  The only exchange is at the end: an all-gather of the per-sequence sizes
-followed by a variable-length all-gather of the fused maps (points 3 + normals 3 + colours 3 + confidence 1
-floats per point), after which every rank holds all B_total maps.
+followed by a variable-length all-gather of the fused maps, after which every rank holds all B_total maps.  The maps
+travel as they are stored - packed geometry rows (8 floats) and colour rows (4 floats) - in EXACT sizes: every rank
+sends rows [0, counts[b]) of each of its elements straight out of the store to every peer, which receives them in place
+in the output store (one grouped batch of point-to-point transfers: no staging copy, no padding to the longest map, no
+zero fill of the send side).
 """
 from typing import Optional
 
 import torch
 import torch.distributed as dist
 
-from .structures.pointclouds import Pointclouds, _ATTRS
+from .structures.pointclouds import Pointclouds
 
 __all__ = ["shard_batch", "gather_maps", "gather_maps_begin", "gather_maps_end", "comm_stream"]
 
@@ -66,9 +69,8 @@ def gather_maps_begin(pointclouds: Pointclouds, group=None) -> "_GatherHandle":
             h.counts_host.copy_(all_counts, non_blocking=True)
             h.ready = torch.cuda.Event()
             h.ready.record(h.stream)
-            for st in pointclouds._store.values():
-                if st is not None:
-                    st.record_stream(h.stream)
+            for st in pointclouds._buffers():
+                st.record_stream(h.stream)
             local.record_stream(h.stream)
             all_counts.record_stream(h.stream)
         else:
@@ -77,9 +79,9 @@ def gather_maps_begin(pointclouds: Pointclouds, group=None) -> "_GatherHandle":
 
 
 def gather_maps_end(h: "_GatherHandle", wait: bool = True) -> Pointclouds:
-    """Second half: waits (host) for the sizes only, then enqueues the variable-length all-gather of the four map
-    attributes on the communication stream.  With wait=True the caller's current stream is made to wait for the
-    result; with wait=False the caller must synchronise with `parallel.comm_stream(device)` before using it."""
+    """Second half: waits (host) for the sizes only, then enqueues the exact-size exchange of the map rows on the
+    communication stream.  With wait=True the caller's current stream is made to wait for the result; with wait=False
+    the caller must synchronise with `parallel.comm_stream(device)` before using it."""
     pc, group, world = h.pc, h.group, h.world
     dev = pc.device
     B = len(pc)
@@ -88,7 +90,9 @@ def gather_maps_end(h: "_GatherHandle", wait: bool = True) -> Pointclouds:
     counts = [int(c) for c in h.counts_host.tolist()]
     nmax = max(max(counts), 1)
     rank = dist.get_rank(group)
-    pc._counts_host = counts[rank * B: (rank + 1) * B]
+    if pc._counts_host is None:  # (also raises if the local map overflowed its capacity)
+        pc._counts_host = counts[rank * B: (rank + 1) * B]
+        pc._check_overflow()
     out = Pointclouds(device=dev)
     out._B = world * B
     if h.stream is not None:
@@ -98,19 +102,38 @@ def gather_maps_end(h: "_GatherHandle", wait: bool = True) -> Pointclouds:
 
         ctx = contextlib.nullcontext()
     with ctx:
-        pc.reserve(nmax)
-        pc._zero_rows_upto(nmax)
-        for key in _ATTRS:
-            st = pc._store[key]
-            if st is None:
+        # zero-filled so that rows >= counts stay zero (the padding contract of the *_padded views); the fill is a
+        # memset on the communication stream, not a kernel competing with the next step's fusion
+        out._alloc_buffers(nmax, pc._has_normals, pc._col is not None,
+                           pc.num_features if pc.has_features else 0)
+        ops, keep = [], []
+        for src, dst in ((pc._geo, out._geo), (pc._col, out._col), (pc._feat, out._feat)):
+            if src is None:
                 continue
-            send = st[:, :nmax].contiguous()
-            recv = torch.empty((world * B, nmax, st.shape[2]), dtype=st.dtype, device=dev)
-            _all_gather(recv, send, group)
-            out._store[key] = recv
+            for b in range(B):
+                c = counts[rank * B + b]
+                if c > 0:
+                    dst[rank * B + b, :c].copy_(src[b, :c])  # own rows: local copy
+            for peer in range(world):
+                if peer == rank:
+                    continue
+                g_peer = peer if group is None else dist.get_global_rank(group, peer)
+                for b in range(B):
+                    c = counts[rank * B + b]
+                    if c > 0:
+                        ops.append(dist.P2POp(dist.isend, src[b, :c], g_peer, group))
+                    c = counts[peer * B + b]
+                    if c > 0:
+                        ops.append(dist.P2POp(dist.irecv, dst[peer * B + b, :c], g_peer, group))
+        if ops:
+            for req in dist.batch_isend_irecv(ops):
+                if h.stream is None:
+                    req.wait()
+                else:
+                    keep.append(req)
+        for t in out._buffers():
             if h.stream is not None:
-                send.record_stream(h.stream)
-                recv.record_stream(torch.cuda.current_stream(dev))
+                t.record_stream(torch.cuda.current_stream(dev))
         out._set_counts(counts)
     if h.stream is not None and wait:
         torch.cuda.current_stream(dev).wait_stream(h.stream)

@@ -7,6 +7,7 @@ table-returning helpers (`find_active_map_points`, `find_similar_map_points`,
 `find_best_unique_correspondences`, `fuse_with_map`) are kept for API parity and run the same arithmetic
 through the table kernels in csrc/gsx_tables.cu.
 """
+import threading
 import warnings
 from typing import Union
 
@@ -74,32 +75,27 @@ def are_normals_similar(tensor1: torch.Tensor, tensor2: torch.Tensor, dot_th: Un
 
 # --------------------------------------------------------------------------------------------- workspaces
 class _Workspace:
-    """Per (device, B, H, W) scratch for the fusion kernels: arg-min records + scan state, zeroed once."""
+    """Per (device, stream, B, H, W) scratch of the fusion kernels: frame records, arg-min records, scan state.  Nothing
+    in it survives from frame to frame (gsx_fusion_frame_records re-arms it), so there is no epoch or "left clean"
+    invariant to break; it is keyed by the CUDA stream as well, so maps updated concurrently from different streams or
+    threads never share records."""
 
     _cache = {}
+    _lock = threading.Lock()
 
     def __init__(self, device, B, H, W):
         nbytes = _C.lib().gsx_fusion_workspace_bytes(B, H, W)
-        self.buf = torch.zeros(nbytes, dtype=torch.uint8, device=device)
-        self.epoch = 0
+        self.buf = torch.zeros(nbytes, dtype=torch.uint8, device=device)  # (zero: the statistics start at 0)
 
     @classmethod
     def get(cls, device, B, H, W):
-        key = (str(device), B, H, W)
-        ws = cls._cache.get(key)
-        if ws is None:
-            ws = cls(device, B, H, W)
-            cls._cache[key] = ws
+        key = (str(device), torch.cuda.current_stream(device).cuda_stream, B, H, W)
+        with cls._lock:
+            ws = cls._cache.get(key)
+            if ws is None:
+                ws = cls(device, B, H, W)
+                cls._cache[key] = ws
         return ws
-
-    def next_epochs(self, n=1):
-        first = self.epoch + 1
-        self.epoch += n
-        if self.epoch >= (1 << 30) - 1:  # wrap: start over on a clean buffer
-            self.buf.zero_()
-            self.epoch = n
-            first = 1
-        return first
 
 
 def _check_frame(rgbdimages):
@@ -109,28 +105,75 @@ def _check_frame(rgbdimages):
         raise ValueError("Expected rgbdimages to have sequence length of 1. Got {0}.".format(rgbdimages.shape[1]))
 
 
-def _launch_merge_append(pointclouds, frames, vmap, nmap, sigma):
-    """K4 on the current workspace state.  vmap/nmap: (B,1,H,W,3) maps to merge/append, or None for both:
-    the kernel then samples world-frame vertex/normal from depth on the fly (needs frames.poses)."""
+def _dense(t, name, device):
+    """A tensor whose raw pointer goes to a kernel: float32, on `device`, dense."""
+    _C.require_cuda(t, name)
+    if t.device != device:
+        raise ValueError("gradslam_b200: `{}` is on {} but the map lives on {}".format(name, t.device, device))
+    return t.contiguous()
+
+
+def _sigma_value(sigma):
+    if torch.is_tensor(sigma):
+        if sigma.requires_grad and torch.is_grad_enabled():
+            raise ValueError("gradslam_b200: a sigma that requires grad is not supported by the fused map update "
+                             "(d/d sigma is only available through fusionutils.get_alpha)")
+        return float(sigma.item())
+    return float(sigma)
+
+
+def _map_ptrs(pointclouds, device):
+    """(geometry, colours) buffers of a map the kernels may touch: float32 CUDA, dense, on `device`."""
+    geo = _dense(pointclouds._geo, "pointclouds (geometry rows)", device)
+    col = _dense(pointclouds._col, "pointclouds (colour rows)", device)
+    if geo is not pointclouds._geo or col is not pointclouds._col:  # (never for stores this class allocated)
+        pointclouds._geo, pointclouds._col = geo, col
+    return geo, col
+
+
+def _launch_frame_records(ws, frames, sigma, device, maps=None, world=True):
+    """K1r: the live frame's records into the workspace.  maps = (gvertex, gnormal, vertex) materialised (B,1,H,W,3)
+    maps (differentiable mode), else everything is evaluated from depth; world=False keeps camera coordinates."""
+    B, _, H, W = frames.shape
+    P = H * W
+    depth, d_bs = _frame_base(_dense_frame(frames.depth_image, "depth_image", device), P)
+    if maps is not None:
+        gv, gn, vl = (_dense(t.detach(), "frame map", device) for t in maps)
+        K = poses = None
+    else:
+        gv = gn = vl = None
+        K = _dense(frames.intrinsics, "intrinsics", device)
+        poses = _dense(frames.poses, "poses", device) if (world and frames.poses is not None) else None
+    with torch.cuda.device(device):
+        rc = _C.lib().gsx_fusion_frame_records(_C.ptr(depth), d_bs, _C.ptr(K), 16, _C.ptr(poses), 16, _C.ptr(gv),
+                                               _C.ptr(gn), _C.ptr(vl), B, H, W, sigma, _C.ptr(ws.buf),
+                                               _C.stream_ptr(device))
+    _C.check(rc, "gsx_fusion_frame_records")
+
+
+def _dense_frame(t, name, device):
+    """Frame tensors may be views of a (B,L,...) sequence tensor (frame s of every element): the kernels take a base
+    pointer plus the element stride, so only the per-frame block has to be dense (see _frame_base)."""
+    _C.require_cuda(t, name)
+    if t.device != device:
+        raise ValueError("gradslam_b200: `{}` is on {} but the map lives on {}".format(name, t.device, device))
+    return t
+
+
+def _launch_merge_append(pointclouds, frames, ws, assoc=None):
+    """K4 on the current workspace state (frame records + per-pixel winners)."""
     B, _, H, W = frames.shape
     P = H * W
     dev = pointclouds.device
-    ws = _Workspace.get(dev, B, H, W)
-    depth, d_bs = _frame_base(frames.depth_image, P)
-    rgb, c_bs = _frame_base(frames.rgb_image, P * 3)
-    K = frames.intrinsics.contiguous()
-    poses = None if vmap is not None else frames.poses.contiguous()
-    if vmap is not None:  # cached maps of a sliced sequence are strided views: the kernels want dense (B,H,W,3)
-        vmap, nmap = vmap.contiguous(), nmap.contiguous()
-    st = pointclouds._store
+    rgb, c_bs = _frame_base(_dense_frame(frames.rgb_image, "rgb_image", dev), P * 3)
+    geo, col = _map_ptrs(pointclouds, dev)
     cin = pointclouds._counts_dev[pointclouds._cur]
     cout = pointclouds._counts_dev[pointclouds._cur ^ 1]
     with torch.cuda.device(dev):
         rc = _C.lib().gsx_fusion_merge_append(
-            _C.ptr(st["points"]), _C.ptr(st["normals"]), _C.ptr(st["colors"]), _C.ptr(st["features"]),
-            _C.ptr(cin), _C.ptr(cout), pointclouds.capacity, _C.ptr(depth), d_bs, _C.ptr(rgb), c_bs, _C.ptr(K), 16,
-            _C.ptr(poses), 16, _C.ptr(vmap), _C.ptr(nmap), B, H, W, float(sigma), _C.ptr(ws.buf), ws.next_epochs(1),
-            _C.ptr(pointclouds._overflow_flag()), _C.stream_ptr(dev))
+            _C.ptr(geo), _C.ptr(col), 1 if pointclouds._has_cc else 0, _C.ptr(cin), _C.ptr(cout),
+            pointclouds.capacity, _C.ptr(rgb), c_bs, B, H, W, _C.ptr(ws.buf), _C.ptr(pointclouds._overflow_flag()),
+            _C.ptr(assoc), _C.stream_ptr(dev))
     _C.check(rc, "gsx_fusion_merge_append")
     pointclouds._mark_device_updated(pointclouds._bound + P)
 
@@ -155,19 +198,22 @@ def _append_valid_pixels(pointclouds, frames, global_coordinates=True, sigma=0.6
     frames = frames.to_channels_last()
     _C.require_cuda(frames.depth_image, "depth_image")
     had_points = pointclouds.has_points
+    if had_points and not (pointclouds.has_normals and pointclouds.has_colors):
+        raise ValueError("Pointclouds must have normals and colors to aggregate frames into it")
+    if had_points and pointclouds._feat is not None:
+        raise ValueError("pointclouds to append and to be appended must have the same number of features")
     with_features = pointclouds.has_features if had_points else False
     _prepare_map(pointclouds, frames, with_features)
-    if global_coordinates and frames.poses is not None:
-        vmap = nmap = None  # sampled on the fly inside the kernel
-    else:
-        vmap = frames.global_vertex_map if global_coordinates else frames.vertex_map
-        nmap = frames.global_normal_map if global_coordinates else frames.normal_map
-    _launch_merge_append(pointclouds, frames, vmap, nmap, sigma)
+    B, _, H, W = frames.shape
+    dev = pointclouds.device
+    ws = _Workspace.get(dev, B, H, W)
+    _launch_frame_records(ws, frames, _sigma_value(sigma), dev, world=global_coordinates)
+    _launch_merge_append(pointclouds, frames, ws)
     return pointclouds
 
 
 def _fused_update(pointclouds, frames, dist_th, dot_th, sigma):
-    """K2/K3 then K4, in place."""
+    """K1r, K2/K3 then K4, in place."""
     frames = frames.to_channels_last()
     _C.require_cuda(frames.depth_image, "depth_image")
     if frames.poses is None:
@@ -179,30 +225,21 @@ def _fused_update(pointclouds, frames, dist_th, dot_th, sigma):
         if pointclouds.num_features != 1:
             raise ValueError("Pointclouds features must be a single confidence count per point for map fusion.")
     B, _, H, W = frames.shape
-    P = H * W
     _prepare_map(pointclouds, frames, True)
     dev = pointclouds.device
-    # Frame geometry: if the caller already materialised the global maps (they are cached on `frames`) use
-    # them, otherwise let the kernels sample vertex / normal from depth on the fly (same bits, no K1 launch).
-    vmap, nmap = frames._global_vertex_map, frames._global_normal_map
-    if vmap is None or nmap is None:
-        vmap = nmap = None
-    else:
-        vmap, nmap = vmap.contiguous(), nmap.contiguous()
+    ws = _Workspace.get(dev, B, H, W)
+    _launch_frame_records(ws, frames, _sigma_value(sigma), dev)
     if pointclouds._bound > 0:
-        ws = _Workspace.get(dev, B, H, W)
-        st = pointclouds._store
-        poses, p_bs = frames.poses.contiguous(), 16
-        K = frames.intrinsics.contiguous()
-        depth, d_bs = _frame_base(frames.depth_image, P)
+        geo, _ = _map_ptrs(pointclouds, dev)
+        poses = _dense(frames.poses, "poses", dev)
+        K = _dense(frames.intrinsics, "intrinsics", dev)
         with torch.cuda.device(dev):
             rc = _C.lib().gsx_fusion_project_select(
-                _C.ptr(st["points"]), _C.ptr(st["normals"]), _C.ptr(st["features"]),
-                _C.ptr(pointclouds._counts_dev[pointclouds._cur]), pointclouds.capacity, pointclouds._bound,
-                _C.ptr(poses), p_bs, _C.ptr(K), 16, _C.ptr(depth), d_bs, _C.ptr(vmap), _C.ptr(nmap), B, H, W,
-                float(dist_th), float(dot_th), _C.ptr(ws.buf), _C.stream_ptr(dev))
+                _C.ptr(geo), _C.ptr(pointclouds._counts_dev[pointclouds._cur]), pointclouds.capacity,
+                pointclouds._bound, _C.ptr(poses), 16, _C.ptr(K), 16, B, H, W, float(dist_th), float(dot_th),
+                _C.ptr(ws.buf), _C.stream_ptr(dev))
         _C.check(rc, "gsx_fusion_project_select")
-    _launch_merge_append(pointclouds, frames, vmap, nmap, sigma)
+    _launch_merge_append(pointclouds, frames, ws)
     return pointclouds
 
 
@@ -260,14 +297,13 @@ def find_active_map_points(pointclouds: Pointclouds, rgbdimages: RGBDImages) -> 
     _check_batch(pointclouds, rgbdimages)
     frames = rgbdimages.to_channels_last()
     B, _, H, W = frames.shape
-    st = pointclouds._store
-    _C.require_cuda(st["points"], "pointclouds.points")
+    geo = _dense(pointclouds._geo, "pointclouds (geometry rows)", device)
     width = min(max(pointclouds._bound, 1), pointclouds.capacity)
     flags = torch.empty((B, width), dtype=torch.uint8, device=device)
     hw = torch.empty((B, width), dtype=torch.int32, device=device)
-    poses, K = frames.poses.contiguous(), frames.intrinsics.contiguous()
+    poses, K = _dense(frames.poses, "poses", device), _dense(frames.intrinsics, "intrinsics", device)
     with torch.cuda.device(device):
-        rc = _C.lib().gsx_active_eval(_C.ptr(st["points"]), _C.ptr(pointclouds._counts_dev[pointclouds._cur]),
+        rc = _C.lib().gsx_active_eval(_C.ptr(geo), _C.ptr(pointclouds._counts_dev[pointclouds._cur]),
                                       pointclouds.capacity, width, _C.ptr(poses), 16, _C.ptr(K), 16, B, H, W,
                                       _C.ptr(flags), _C.ptr(hw), _C.stream_ptr(device))
     _C.check(rc, "gsx_active_eval")
@@ -301,12 +337,12 @@ def find_similar_map_points(pointclouds: Pointclouds, rgbdimages: RGBDImages, pc
     table = pc2im_bnhw.contiguous()
     rows = table.shape[0]
     gv, gn = frames.global_vertex_map.contiguous(), frames.global_normal_map.contiguous()
-    st = pointclouds._store
+    geo = _dense(pointclouds._geo, "pointclouds (geometry rows)", device)
     flags = torch.empty(rows, dtype=torch.uint8, device=device)
     with torch.cuda.device(device):
-        rc = _C.lib().gsx_similar_eval(_C.ptr(table), rows, _C.ptr(st["points"]), _C.ptr(st["normals"]),
-                                       pointclouds.capacity, _C.ptr(gv), _C.ptr(gn), B, H, W, float(dist_th),
-                                       float(dot_th), _C.ptr(flags), _C.stream_ptr(device))
+        rc = _C.lib().gsx_similar_eval(_C.ptr(table), rows, _C.ptr(geo), pointclouds.capacity, _C.ptr(gv),
+                                       _C.ptr(gn), B, H, W, float(dist_th), float(dot_th), _C.ptr(flags),
+                                       _C.stream_ptr(device))
     _C.check(rc, "gsx_similar_eval")
     keep = _compact(flags)
     similar = table[keep]
@@ -335,15 +371,16 @@ def find_best_unique_correspondences(pointclouds: Pointclouds, rgbdimages: RGBDI
     frames = rgbdimages.to_channels_last()
     B, _, H, W = frames.shape
     table = pc2im_bnhw.contiguous()
+    if pointclouds.num_features != 1:
+        raise ValueError("Pointclouds features must be a single confidence count per point.")
     gv = frames.global_vertex_map.contiguous()
-    st = pointclouds._store
-    ws = _Workspace.get(device, B, H, W)
+    geo = _dense(pointclouds._geo, "pointclouds (geometry rows)", device)
+    records = torch.empty(B * H * W * 2, dtype=torch.int64, device=device)  # 16-byte arg-min records (scratch)
     pflags = torch.empty(B * H * W, dtype=torch.uint8, device=device)
     pn = torch.empty(B * H * W, dtype=torch.int64, device=device)
     with torch.cuda.device(device):
-        rc = _C.lib().gsx_unique_select(_C.ptr(table), table.shape[0], _C.ptr(st["points"]), _C.ptr(st["features"]),
-                                        pointclouds.capacity, _C.ptr(gv), B, H, W, _C.ptr(ws.buf), _C.ptr(pflags),
-                                        _C.ptr(pn), _C.stream_ptr(device))
+        rc = _C.lib().gsx_unique_select(_C.ptr(table), table.shape[0], _C.ptr(geo), pointclouds.capacity, _C.ptr(gv),
+                                        B, H, W, _C.ptr(records), _C.ptr(pflags), _C.ptr(pn), _C.stream_ptr(device))
     _C.check(rc, "gsx_unique_select")
     pix = _compact(pflags)
     rem = pix % (H * W)
@@ -383,98 +420,93 @@ def fuse_with_map(pointclouds: Pointclouds, rgbdimages: RGBDImages, pc2im_bnhw: 
     B, _, H, W = frames.shape
     _prepare_map(pointclouds, frames, True)
     device = pointclouds.device
+    ws = _Workspace.get(device, B, H, W)
+    _launch_frame_records(ws, frames, _sigma_value(sigma), device)  # (poses None: world frame == camera frame)
     if pointclouds._bound > 0 and pc2im_bnhw.shape[0] != 0:
-        table = pc2im_bnhw.to(device).contiguous()
-        ws = _Workspace.get(device, B, H, W)
-        with torch.cuda.device(device):
-            rc = _C.lib().gsx_records_from_table(_C.ptr(table), table.shape[0], pointclouds.capacity, B, H, W,
-                                                 _C.ptr(ws.buf), _C.stream_ptr(device))
-        _C.check(rc, "gsx_records_from_table")
-    if frames.poses is not None:
-        vmap = nmap = None
-    else:
-        vmap, nmap = frames.global_vertex_map, frames.global_normal_map
-    _launch_merge_append(pointclouds, frames, vmap, nmap, sigma)
+        _records_from_table(ws, pc2im_bnhw, pointclouds, B, H, W, device)
+    _launch_merge_append(pointclouds, frames, ws)
     return pointclouds
+
+
+def _records_from_table(ws, table, pointclouds, B, H, W, device):
+    table = table.to(device).contiguous()
+    with torch.cuda.device(device):
+        rc = _C.lib().gsx_records_from_table(_C.ptr(table), table.shape[0], pointclouds.capacity, B, H, W,
+                                             _C.ptr(ws.buf), _C.stream_ptr(device))
+    _C.check(rc, "gsx_records_from_table")
 
 
 # --------------------------------------------------------------------------------------------- differentiable mode
 def _wants_grad(pointclouds, frames):
     if not torch.is_grad_enabled():
         return False
-    ts = [frames.depth_image, frames.poses, frames.rgb_image, frames.intrinsics] + list(pointclouds._store.values())
+    ts = [frames.depth_image, frames.poses, frames.rgb_image, frames.intrinsics] + pointclouds._grad_tensors()
     return any(torch.is_tensor(t) and t.requires_grad for t in ts)
 
 
 class _MergeAppendFn(torch.autograd.Function):
-    """K4 as one differentiable op: (pre-merge map, frame maps) -> updated map.  forward =
-    gsx_fusion_merge_append_fwd on a copy of the map (also records where every pixel went), backward =
-    gsx_fusion_merge_append_bwd; both hand-written kernels.  The per-pixel winners must already sit in the fusion
-    workspace (K2, or gsx_records_from_table); they are index-only, as in the reference (fusionutils.py:523)."""
+    """K4 as one differentiable op: (pre-merge map rows, frame maps) -> updated map rows.  forward =
+    gsx_fusion_merge_append on a copy of the map (also records where every pixel went), backward =
+    gsx_fusion_merge_append_bwd; both hand-written kernels, both on the packed row layout (the public
+    points / normals / colors / features tensors are slices of the rows, so autograd carries the gradients in and out
+    of the rows by itself).  The frame records and the per-pixel winners must already sit in the fusion workspace
+    (K1r from the maps; K2, or gsx_records_from_table); they are index-only, as in the reference
+    (fusionutils.py:523)."""
 
     @staticmethod
-    def forward(ctx, pack, pts, nrm, col, cc, gv, gn, rgb, vloc):
-        pointclouds, frames, sigma = pack
+    def forward(ctx, pack, geo, col, gv, gn, rgb, vloc):
+        pointclouds, frames, sigma, ws = pack
         B, _, H, W = frames.shape
         P = H * W
-        dev = pts.device
-        bound, cap_in, cap_out = pointclouds._bound, pts.shape[1], pointclouds._bound + P
+        dev = geo.device
+        bound, cap_in, cap_out = pointclouds._bound, geo.shape[1], pointclouds._bound + P
         outs = []
-        for t in (pts, nrm, col, cc):
-            if t is None:
-                outs.append(None)
-                continue
+        for t in (geo, col):
             o = torch.zeros((B, cap_out, t.shape[2]), dtype=torch.float32, device=dev)
             if bound > 0:
                 o[:, :bound] = t.detach()[:, :bound]
             outs.append(o)
         gv_c, gn_c, rgb_c, vloc_c = (t.detach().contiguous() for t in (gv, gn, rgb, vloc))
-        depth, d_bs = _frame_base(frames.depth_image.detach(), P)
-        K = frames.intrinsics.detach().contiguous()
-        ws = _Workspace.get(dev, B, H, W)
         counts_in = pointclouds._counts_dev[pointclouds._cur].clone()
         counts_out = pointclouds._counts_dev[pointclouds._cur ^ 1]
         assoc = torch.zeros((B, P), dtype=torch.int32, device=dev)
+        with_cc = 1 if pointclouds._has_cc else 0
         with torch.cuda.device(dev):
-            rc = _C.lib().gsx_fusion_merge_append_fwd(
-                _C.ptr(outs[0]), _C.ptr(outs[1]), _C.ptr(outs[2]), _C.ptr(outs[3]), _C.ptr(counts_in),
-                _C.ptr(counts_out), cap_out, _C.ptr(depth), d_bs, _C.ptr(rgb_c), P * 3, _C.ptr(K), 16, _C.ptr(gv_c),
-                _C.ptr(gn_c), B, H, W, float(sigma), _C.ptr(ws.buf), ws.next_epochs(1),
-                _C.ptr(pointclouds._overflow_flag()), _C.ptr(assoc), _C.stream_ptr(dev))
-        _C.check(rc, "gsx_fusion_merge_append_fwd")
-        ctx.saved = (assoc, counts_in, pts.detach(), nrm.detach(), col.detach(), None if cc is None else cc.detach(),
-                     gv_c, gn_c, rgb_c, vloc_c)
-        ctx.dims = (B, H, W, cap_in, cap_out, float(sigma))
+            rc = _C.lib().gsx_fusion_merge_append(
+                _C.ptr(outs[0]), _C.ptr(outs[1]), with_cc, _C.ptr(counts_in), _C.ptr(counts_out), cap_out,
+                _C.ptr(rgb_c), P * 3, B, H, W, _C.ptr(ws.buf), _C.ptr(pointclouds._overflow_flag()), _C.ptr(assoc),
+                _C.stream_ptr(dev))
+        _C.check(rc, "gsx_fusion_merge_append")
+        ctx.saved = (assoc, counts_in, geo.detach(), col.detach(), gv_c, gn_c, rgb_c, vloc_c)
+        ctx.dims = (B, H, W, cap_in, cap_out, float(sigma), with_cc)
         ctx.shapes = (gv.shape, rgb.shape)
         return tuple(outs)
 
     @staticmethod
-    def backward(ctx, g_pts, g_nrm, g_col, g_cc):
-        assoc, counts_in, pts, nrm, col, cc, gv, gn, rgb, vloc = ctx.saved
-        B, H, W, cap_in, cap_out, sigma = ctx.dims
+    def backward(ctx, g_geo, g_col):
+        assoc, counts_in, geo, col, gv, gn, rgb, vloc = ctx.saved
+        B, H, W, cap_in, cap_out, sigma, with_cc = ctx.dims
         dev = assoc.device
-        gs = [None if g is None else g.contiguous().float() for g in (g_pts, g_nrm, g_col, g_cc)]
-        pts_c, nrm_c, col_c = pts.contiguous(), nrm.contiguous(), col.contiguous()
-        cc_c = None if cc is None else cc.contiguous()
-        d_map = [torch.empty_like(t) for t in (pts_c, nrm_c, col_c)] + [None if cc_c is None else torch.empty_like(cc_c)]
+        gs = [None if g is None else g.contiguous().float() for g in (g_geo, g_col)]
+        geo_c, col_c = geo.contiguous(), col.contiguous()
+        d_map = [torch.empty_like(geo_c), torch.empty_like(col_c)]
         d_frame = [torch.empty((B, 1, H, W, 3), dtype=torch.float32, device=dev) for _ in range(4)]
         with torch.cuda.device(dev):
             rc = _C.lib().gsx_fusion_merge_append_bwd(
-                _C.ptr(assoc), _C.ptr(counts_in), _C.ptr(pts_c), _C.ptr(nrm_c), _C.ptr(col_c), _C.ptr(cc_c), cap_in,
-                _C.ptr(gs[0]), _C.ptr(gs[1]), _C.ptr(gs[2]), _C.ptr(gs[3]), cap_out, _C.ptr(gv), _C.ptr(gn),
-                _C.ptr(rgb), _C.ptr(vloc), B, H, W, sigma, _C.ptr(d_map[0]), _C.ptr(d_map[1]), _C.ptr(d_map[2]),
-                _C.ptr(d_map[3]), _C.ptr(d_frame[0]), _C.ptr(d_frame[1]), _C.ptr(d_frame[2]), _C.ptr(d_frame[3]),
-                _C.stream_ptr(dev))
+                _C.ptr(assoc), _C.ptr(counts_in), _C.ptr(geo_c), _C.ptr(col_c), with_cc, cap_in, _C.ptr(gs[0]),
+                _C.ptr(gs[1]), cap_out, _C.ptr(gv), _C.ptr(gn), _C.ptr(rgb), _C.ptr(vloc), B, H, W, sigma,
+                _C.ptr(d_map[0]), _C.ptr(d_map[1]), _C.ptr(d_frame[0]), _C.ptr(d_frame[1]), _C.ptr(d_frame[2]),
+                _C.ptr(d_frame[3]), _C.stream_ptr(dev))
         _C.check(rc, "gsx_fusion_merge_append_bwd")
         gv_shape, rgb_shape = ctx.shapes
-        return (None, d_map[0], d_map[1], d_map[2], d_map[3], d_frame[0].view(gv_shape), d_frame[1].view(gv_shape),
+        return (None, d_map[0], d_map[1], d_frame[0].view(gv_shape), d_frame[1].view(gv_shape),
                 d_frame[2].view(rgb_shape), d_frame[3].view(gv_shape))
 
 
 def _update_differentiable(pointclouds, frames, sigma, with_features, dist_th=None, dot_th=None, table=None):
-    """Map update when a gradient is requested: K1 (differentiable op) -> association (K2 kernel, or the rows of
-    `table`; index-only) -> K4 (differentiable op), out of place so the pre-merge map survives for the backward.
-    Values equal the in-place kernel path bit for bit."""
+    """Map update when a gradient is requested: K1 (differentiable op) -> frame records packed from its maps ->
+    association (K2 kernel, or the rows of `table`; index-only) -> K4 (differentiable op), out of place so the pre-merge
+    map survives for the backward.  Values equal the in-place kernel path bit for bit."""
     frames = frames.to_channels_last()
     _C.require_cuda(frames.depth_image, "depth_image")
     B, _, H, W = frames.shape
@@ -486,31 +518,25 @@ def _update_differentiable(pointclouds, frames, sigma, with_features, dist_th=No
         raise ValueError("Expected equal batch sizes for pointclouds and rgbdimages. Got {0} and {1} "
                          "respectively.".format(len(pointclouds), B))
     dev = pointclouds.device
-    st = pointclouds._store
+    sig = _sigma_value(sigma)
     gv, gn, vloc = frames.global_vertex_map, frames.global_normal_map, frames.vertex_map  # K1, carries its backward
     ws = _Workspace.get(dev, B, H, W)
+    _launch_frame_records(ws, frames, sig, dev, maps=(gv, gn, vloc))
     if pointclouds._bound > 0 and table is not None and table.shape[0] != 0:
-        table = table.to(dev).contiguous()
-        with torch.cuda.device(dev):
-            rc = _C.lib().gsx_records_from_table(_C.ptr(table), table.shape[0], pointclouds.capacity, B, H, W,
-                                                 _C.ptr(ws.buf), _C.stream_ptr(dev))
-        _C.check(rc, "gsx_records_from_table")
+        _records_from_table(ws, table, pointclouds, B, H, W, dev)
     elif pointclouds._bound > 0 and dist_th is not None:
-        pts, nrm, ccs = (st[k].detach().contiguous() for k in ("points", "normals", "features"))
-        K = frames.intrinsics.detach().contiguous()
-        poses = frames.poses.detach().contiguous()
-        depth, d_bs = _frame_base(frames.depth_image.detach(), P)
-        gvd, gnd = gv.detach().contiguous(), gn.detach().contiguous()
+        geo = _dense(pointclouds._geo.detach(), "pointclouds (geometry rows)", dev)
+        K = _dense(frames.intrinsics.detach(), "intrinsics", dev)
+        poses = _dense(frames.poses.detach(), "poses", dev)
         with torch.cuda.device(dev):
             rc = _C.lib().gsx_fusion_project_select(
-                _C.ptr(pts), _C.ptr(nrm), _C.ptr(ccs), _C.ptr(pointclouds._counts_dev[pointclouds._cur]),
-                pointclouds.capacity, pointclouds._bound, _C.ptr(poses), 16, _C.ptr(K), 16, _C.ptr(depth), d_bs,
-                _C.ptr(gvd), _C.ptr(gnd), B, H, W, float(dist_th), float(dot_th), _C.ptr(ws.buf), _C.stream_ptr(dev))
+                _C.ptr(geo), _C.ptr(pointclouds._counts_dev[pointclouds._cur]), pointclouds.capacity,
+                pointclouds._bound, _C.ptr(poses), 16, _C.ptr(K), 16, B, H, W, float(dist_th), float(dot_th),
+                _C.ptr(ws.buf), _C.stream_ptr(dev))
         _C.check(rc, "gsx_fusion_project_select")
-    outs = _MergeAppendFn.apply((pointclouds, frames, sigma), st["points"], st["normals"], st["colors"],
-                                st["features"], gv, gn, frames.rgb_image, vloc)
-    for key, o in zip(("points", "normals", "colors", "features"), outs):
-        st[key] = o
+    geo_out, col_out = _MergeAppendFn.apply((pointclouds, frames, sig, ws), pointclouds._geo, pointclouds._col, gv, gn,
+                                            frames.rgb_image, vloc)
+    pointclouds._geo, pointclouds._col = geo_out, col_out
     pointclouds._uninit = False
     pointclouds._mark_device_updated(pointclouds._bound + P)
     return pointclouds
@@ -523,11 +549,16 @@ def update_map_aggregate(pointclouds: Pointclouds, rgbdimages: RGBDImages, inpla
         raise TypeError("Expected pointclouds to be of type gradslam.Pointclouds. Got {0}.".format(type(pointclouds)))
     if not isinstance(rgbdimages, RGBDImages):
         raise TypeError("Expected rgbdimages to be of type gradslam.RGBDImages. Got {0}.".format(type(rgbdimages)))
+    if pointclouds.has_points and pointclouds.has_features:
+        # the reference appends a features-less cloud built from the frame (structures/utils.py:7-57) and
+        # Pointclouds.append_points refuses the mismatch (pointclouds.py:1170-1177)
+        raise ValueError("pointclouds to append and to be appended must either both have or not have features: "
+                         "(False != True)")
     if not inplace:
         pointclouds = pointclouds.clone()
     if _wants_grad(pointclouds, rgbdimages):
         _check_frame(rgbdimages)
-        return _update_differentiable(pointclouds, rgbdimages, 0.6, pointclouds.has_features)
+        return _update_differentiable(pointclouds, rgbdimages, 0.6, False)
     return _append_valid_pixels(pointclouds, rgbdimages, True)
 
 

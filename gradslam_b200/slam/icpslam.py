@@ -110,8 +110,7 @@ class ICPSLAM(nn.Module):
         from ..odometry.icputils import _wants_grad, downsample_pointclouds, downsample_rgbdimages, localize_against_map
 
         live_frame.poses = prev_frame.poses
-        if _wants_grad(live_frame.depth_image, prev_frame.poses, pointclouds._store["points"],
-                       pointclouds._store["normals"]):
+        if _wants_grad(live_frame.depth_image, prev_frame.poses, *pointclouds._grad_tensors()):
             # differentiable mode (reference op order, slam/icpslam.py:238-247): the K1 maps carry their hand-written
             # backward, the association kernels are index-only, the ICP algebra is taped.
             from ..geometry.geometryutils import compose_transformations

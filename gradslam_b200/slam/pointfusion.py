@@ -94,11 +94,11 @@ class PointFusion(ICPSLAM):
             if raw:  # staging buffers for the 5-byte pixels; converted chunk by chunk on the compute stream
                 raw_depth = torch.empty((B, L, H, W), dtype=src_depth.dtype, device=dev)
                 raw_rgb = torch.empty((B, L, H, W, 3), dtype=torch.uint8, device=dev)
-        _C.require_cuda(depth, "depth_image")
+        for t, name in ((depth, "depth_image"), (rgb, "rgb_image"), (K, "intrinsics"), (poses, "poses")):
+            _C.require_cuda(t, name)
         pc = Pointclouds(device=dev)
         pc._allocate(B, L * P, 1, zero=False)
         ws = _Workspace.get(dev, B, H, W)
-        st = pc._store
         main = torch.cuda.current_stream(dev)
         with torch.cuda.device(dev):
             ready = []
@@ -125,11 +125,10 @@ class PointFusion(ICPSLAM):
                             frames.scaling_factor, 1 if frames.normalize_color else 0, _C.ptr(rgb[b, s0:s1]),
                             _C.ptr(depth[b, s0:s1]), _C.stream_ptr(dev)), "gsx_ingest_raw")
                 rc = _C.lib().gsx_pointfusion_sequence_gt(
-                    _C.ptr(st["points"]), _C.ptr(st["normals"]), _C.ptr(st["colors"]), _C.ptr(st["features"]),
-                    _C.ptr(pc._counts_dev), pc.capacity, min(s0 * P, pc.capacity), _C.ptr(depth), _C.ptr(rgb),
-                    _C.ptr(K), _C.ptr(poses), B, L, s0, s1, H, W, float(self.dist_th), float(self.dot_th),
-                    float(self.sigma), None, _C.ptr(ws.buf), ws.next_epochs(s1 - s0),
-                    _C.ptr(pc._overflow_flag()), _C.stream_ptr(dev))
+                    _C.ptr(pc._geo), _C.ptr(pc._col), _C.ptr(pc._counts_dev), pc.capacity, min(s0 * P, pc.capacity),
+                    _C.ptr(depth), _C.ptr(rgb), _C.ptr(K), _C.ptr(poses), B, L, s0, s1, H, W, float(self.dist_th),
+                    float(self.dot_th), float(self.sigma), _C.ptr(ws.buf), _C.ptr(pc._overflow_flag()),
+                    _C.stream_ptr(dev))
                 _C.check(rc, "gsx_pointfusion_sequence_gt")
             if not on_device:
                 for t in ((raw_depth, raw_rgb) if raw else (depth, rgb)):

@@ -4,14 +4,20 @@ Host-side mirror of gradslam.Pointclouds (gradslam/structures/pointclouds.py:13-
 list / padded views, arithmetic helpers, `append_points`, `transform`, `pinhole_projection`, `clone`,
 `detach`, `to`, indexing.  The representation is different by design: instead of the
 reference's list <-> padded duality, rebuilt with `torch.cat` on every append, the map lives in ONE
-capacity-backed SoA store
+capacity-backed store of SECTOR-PACKED rows that the fusion kernels update IN PLACE:
 
-    points / normals / colors  (B, capacity, 3)      features  (B, capacity, C)      counts int32 (2, B)
+    geometry  (B, capacity, 8)  float32   (px, py, pz, nx, ny, nz, ccount, 0)   one 32-byte DRAM sector per surfel
+    colours   (B, capacity, 4)  float32   (r, g, b, 0)
+    counts    (2, B)            int32     ping-pong: kernels read row `cur`, write row `cur ^ 1`
 
-that the fusion kernels update IN PLACE.  Rows >= counts[b] are always zero, so `*_padded` is the
-zero-copy view `store[:, :max(counts)]` and `*_list[b]` is `store[b, :counts[b]]`.  The per-element sizes
-live on the device (the kernels bump them); the host copy is refreshed lazily, only when a caller asks
-for a shape-dependent view.
+so a kernel touches a surfel with two (geometry) or three (+ colour) 128-bit accesses instead of ten scalar ones
+spread over four arrays.  gradslam's tensors are STRIDED VIEWS of these rows: `points_padded = geometry[:, :N, 0:3]`,
+`normals_padded = geometry[:, :N, 3:6]`, `features_padded = geometry[:, :N, 6:7]` (the confidence count),
+`colors_padded = colours[:, :N, 0:3]`; `*_list[b]` are the same views cut at `counts[b]`.  (Features with more than
+one channel are not part of the fusion path; they live in a separate dense (B, capacity, C) tensor.)  Rows >=
+counts[b] are always zero inside the padded width.  The per-element sizes live on the device (the kernels bump them);
+the host copy is refreshed lazily, only when a caller asks for a shape-dependent view.  Everything is float32: other
+floating inputs are cast on construction (the kernels read raw float32 rows).
 """
 from typing import List, Optional, Union
 
@@ -20,6 +26,11 @@ import torch
 __all__ = ["Pointclouds"]
 
 _ATTRS = ("points", "normals", "colors", "features")
+GEO_W, COL_W = 8, 4  # floats per geometry / colour row (csrc/gsx_fusion.cu)
+
+
+def _f32(t, device):
+    return t.to(device=device, dtype=torch.float32)
 
 
 class Pointclouds(object):
@@ -34,7 +45,11 @@ class Pointclouds(object):
         if points is not None and len(points) == 0:
             raise ValueError("len(points) (= 0) should be > 0")
 
-        self._store = {k: None for k in _ATTRS}  # capacity-backed tensors
+        self._geo = None  # (B, cap, 8) geometry rows
+        self._col = None  # (B, cap, 4) colour rows, or None: no colours
+        self._feat = None  # (B, cap, C) generic features (C != 1), or None
+        self._has_normals = False
+        self._has_cc = False  # single-channel features (the confidence count) live in slot 6 of the geometry rows
         self._counts_dev = None  # int32 (2, B): ping-pong; row self._cur is current
         self._cur = 0
         self._counts_host = None  # list[int] or None when stale
@@ -64,16 +79,15 @@ class Pointclouds(object):
             if not (features is None or len(set(f.shape[-1] for f in features)) == 1):
                 raise ValueError("number of features per pointcloud has to be the same")
             self._B = len(points)
-            cap = max(counts)
+            self._alloc_buffers(max(counts), normals is not None, colors is not None,
+                                0 if features is None else features[0].shape[-1])
             for key, lst in zip(_ATTRS, (points, normals, colors, features)):
                 if lst is None:
                     continue
-                C = lst[0].shape[-1]
-                st = torch.zeros((self._B, cap, C), dtype=lst[0].dtype, device=self.device)
+                dst = self._view(key)
                 for b, x in enumerate(lst):
                     if x.shape[0] > 0:
-                        st[b, : x.shape[0]] = x.to(self.device)
-                self._store[key] = st
+                        dst[b, : x.shape[0]] = _f32(x, self.device)
             self._set_counts(counts)
         elif torch.is_tensor(points):
             self.device = torch.empty(0, device=device).device if device is not None else points.device
@@ -95,11 +109,47 @@ class Pointclouds(object):
                 raise ValueError("first 2 dims of features tensor and points tensor should have same shape, but "
                                  "didn't: %r != %r" % (features.shape[:-1], points.shape[:-1]))
             self._B = points.shape[0]
+            N = points.shape[1]
+            self._alloc_buffers(N, normals is not None, colors is not None,
+                                0 if features is None else features.shape[-1])
             for key, t in zip(_ATTRS, (points, normals, colors, features)):
-                self._store[key] = None if t is None else t.to(self.device)
-            self._set_counts([points.shape[1]] * self._B)
+                if t is not None and N > 0:
+                    self._view(key)[:, :N] = _f32(t, self.device)
+            self._set_counts([N] * self._B)
         else:
             self.device = torch.empty(0, device=device).device if device is not None else torch.device("cpu")
+
+    # ------------------------------------------------------------------ packed storage
+    def _alloc_buffers(self, capacity: int, with_normals: bool, with_colors: bool, features_dim: int, zero: bool = True):
+        alloc = torch.zeros if zero else torch.empty
+        cap = max(int(capacity), 0)
+        self._geo = alloc((self._B, cap, GEO_W), dtype=torch.float32, device=self.device)
+        self._col = alloc((self._B, cap, COL_W), dtype=torch.float32, device=self.device) if with_colors else None
+        self._has_normals = bool(with_normals)
+        self._has_cc = features_dim == 1
+        self._feat = (alloc((self._B, cap, int(features_dim)), dtype=torch.float32, device=self.device)
+                      if features_dim > 1 else None)
+
+    def _buffers(self):
+        return [t for t in (self._geo, self._col, self._feat) if t is not None]
+
+    def _view(self, key):
+        """Full-capacity strided view (B, capacity, C) of one attribute, or None."""
+        if self._geo is None:
+            return None
+        if key == "points":
+            return self._geo[..., 0:3]
+        if key == "normals":
+            return self._geo[..., 3:6] if self._has_normals else None
+        if key == "colors":
+            return None if self._col is None else self._col[..., 0:3]
+        if key == "features":
+            return self._geo[..., 6:7] if self._has_cc else self._feat
+        raise KeyError(key)
+
+    def _grad_tensors(self):
+        """Tensors whose requires_grad switches the fusion / ICP ops to their differentiable mode."""
+        return self._buffers()
 
     # ------------------------------------------------------------------ size bookkeeping
     def _set_counts(self, counts: List[int]):
@@ -116,13 +166,16 @@ class Pointclouds(object):
         if self._counts_host is None:
             self._counts_host = [int(c) for c in self._counts_dev[self._cur].tolist()]
             self._bound = max(self._counts_host)
-            if self._overflow is not None and int(self._overflow.item()) != 0:
-                raise RuntimeError("gradslam_b200: surfel map capacity exceeded; points were dropped")
+            self._check_overflow()
         return self._counts_host
+
+    def _check_overflow(self):
+        if self._overflow is not None and int(self._overflow.item()) != 0:
+            raise RuntimeError("gradslam_b200: surfel map capacity exceeded; points were dropped")
 
     @property
     def capacity(self) -> int:
-        return 0 if self._store["points"] is None else int(self._store["points"].shape[1])
+        return 0 if self._geo is None else int(self._geo.shape[1])
 
     def _mark_device_updated(self, new_bound: int):
         """Called by the fusion ops after kernels wrote counts into the other ping-pong row."""
@@ -132,16 +185,13 @@ class Pointclouds(object):
         self._list_cache = {}
         self._tail_dirty = self._uninit
 
-    def _allocate(self, B: int, capacity: int, features_dim: int = 1, dtype=torch.float32, zero: bool = True):
-        """Turns an EMPTY object into B empty maps with the given capacity (used by the fusion ops).
-        zero=False skips the fill: the kernels never read rows >= counts[b]; the zero padding that the
-        `*_padded` views promise is then restored lazily, only for the ragged tail (see _padded)."""
+    def _allocate(self, B: int, capacity: int, features_dim: int = 1, zero: bool = True):
+        """Turns an EMPTY object into B empty maps (points, normals, colours [, confidence]) with the given capacity
+        (used by the fusion ops).  zero=False skips the fill: the kernels never read rows >= counts[b]; the zero
+        padding that the `*_padded` views promise is then restored lazily, only for the ragged tail (see _padded)."""
         assert not self.has_points
         self._B = int(B)
-        alloc = torch.zeros if zero else torch.empty
-        for key, C in (("points", 3), ("normals", 3), ("colors", 3), ("features", features_dim)):
-            if C > 0:
-                self._store[key] = alloc((self._B, int(capacity), C), dtype=dtype, device=self.device)
+        self._alloc_buffers(capacity, True, True, features_dim, zero)
         self._uninit = not zero
         self._set_counts([0] * self._B)
 
@@ -151,19 +201,21 @@ class Pointclouds(object):
         return self._overflow
 
     def reserve(self, capacity: int):
-        """Grows every attribute store to at least `capacity` rows (amortised doubling, zero-filled)."""
+        """Grows every buffer to at least `capacity` rows (amortised doubling, zero-filled)."""
         cap = self.capacity
         if capacity <= cap:
             return
         new_cap = max(int(capacity), 2 * cap)
-        for key in _ATTRS:
-            st = self._store[key]
+
+        def grow(st):
             if st is None:
-                continue
+                return None
             grown = torch.zeros((st.shape[0], new_cap, st.shape[2]), dtype=st.dtype, device=st.device)
             if cap > 0:
                 grown[:, :cap] = st  # (a dirty tail, if any, is copied too and stays flagged)
-            self._store[key] = grown
+            return grown
+
+        self._geo, self._col, self._feat = grow(self._geo), grow(self._col), grow(self._feat)
         self._list_cache = {}
 
     # ------------------------------------------------------------------ protocol
@@ -172,23 +224,25 @@ class Pointclouds(object):
 
     @property
     def has_points(self):
-        return self._store["points"] is not None
+        return self._geo is not None
 
     @property
     def has_normals(self):
-        return self._store["normals"] is not None
+        return self._geo is not None and self._has_normals
 
     @property
     def has_colors(self):
-        return self._store["colors"] is not None
+        return self._col is not None
 
     @property
     def has_features(self):
-        return self._store["features"] is not None
+        return self._geo is not None and (self._has_cc or self._feat is not None)
 
     @property
     def num_features(self):
-        return 0 if not self.has_features else self._store["features"].shape[-1]
+        if not self.has_features:
+            return 0
+        return 1 if self._has_cc else self._feat.shape[-1]
 
     @property
     def num_points_per_pointcloud(self):
@@ -206,39 +260,33 @@ class Pointclouds(object):
     def _N(self):
         return max(self._host_counts()) if self.has_points else 0
 
-    def _clean_tail(self):
-        """Zeroes rows [counts[b], max(counts)) of every attribute (only needed after a zero=False allocation)."""
-        if self._tail_dirty and self.has_points:
-            counts, n = self._host_counts(), self._N
-            for st in self._store.values():
-                if st is None:
-                    continue
-                for b, c in enumerate(counts):
-                    if c < n:
-                        st[b, c:n].zero_()
-            self._tail_dirty = False
-
-    def _zero_rows_upto(self, n: int):
-        """Zeroes rows [counts[b], n) of every attribute (padding contract for an externally chosen width)."""
+    def _zero_tail(self, n: int):
         counts = self._host_counts()
-        if not self._uninit:  # zero-initialised stores already satisfy the contract
-            return
-        for st in self._store.values():
-            if st is None:
-                continue
+        for st in self._buffers():
             for b, c in enumerate(counts):
                 if c < n:
                     st[b, c:n].zero_()
 
+    def _clean_tail(self):
+        """Zeroes rows [counts[b], max(counts)) of every buffer (only needed after a zero=False allocation)."""
+        if self._tail_dirty and self.has_points:
+            self._zero_tail(self._N)
+            self._tail_dirty = False
+
+    def _zero_rows_upto(self, n: int):
+        """Zeroes rows [counts[b], n) of every buffer (padding contract for an externally chosen width)."""
+        if self._uninit:  # zero-initialised stores already satisfy the contract
+            self._zero_tail(n)
+
     def _padded(self, key):
-        st = self._store[key]
+        st = self._view(key)
         if st is None:
             return None
         self._clean_tail()
         return st[:, : self._N]
 
     def _list(self, key):
-        st = self._store[key]
+        st = self._view(key)
         if st is None:
             return None
         if key not in self._list_cache:
@@ -277,20 +325,33 @@ class Pointclouds(object):
         if got != exp:
             raise ValueError("Expected value to have shape {}. Got {}".format(exp, tuple(value.shape)))
 
+    def _writable_view(self, key, channels: int):
+        """Fresh (out-of-place, autograd friendly: never mutate a tensor a caller may still hold) full-capacity view of
+        attribute `key` with `channels` channels, creating / re-shaping its buffer if needed."""
+        cap = max(self.capacity, self._N)
+        if key in ("points", "normals") or (key == "features" and channels == 1):
+            self._geo = self._geo.clone()
+            if key == "normals":
+                self._has_normals = True
+            if key == "features":
+                self._has_cc, self._feat = True, None
+        elif key == "colors":
+            self._col = (torch.zeros((self._B, cap, COL_W), dtype=torch.float32, device=self.device)
+                         if self._col is None else self._col.clone())
+        else:  # features with C != 1
+            if self._has_cc:
+                self._geo = self._geo.clone()
+                self._geo[..., 6] = 0
+                self._has_cc = False
+            self._feat = torch.zeros((self._B, cap, channels), dtype=torch.float32, device=self.device)
+        self._list_cache = {}
+        return self._view(key)
+
     def _set_padded(self, key, value, first_2=False):
         self._assert_set_padded(value, first_2)
-        st = self._store[key]
-        if st is None or st.shape[-1] != value.shape[-1] or st.dtype != value.dtype:
-            new = torch.zeros((self._B, max(self.capacity, self._N), value.shape[-1]), dtype=value.dtype,
-                              device=self.device)
-            self._store[key] = new
-            st = new
-        else:
-            # out-of-place for autograd friendliness: never mutate a tensor a caller may still hold
-            st = st.clone()
-            self._store[key] = st
-        st[:, : self._N] = value
-        self._list_cache = {}
+        n = self._N
+        dst = self._writable_view(key, value.shape[-1])
+        dst[:, :n] = _f32(value, self.device)
 
     def _assert_set_list(self, value, first_dim_only=False):
         if not isinstance(value, list):
@@ -307,12 +368,9 @@ class Pointclouds(object):
 
     def _set_list(self, key, value, first_dim_only=False):
         self._assert_set_list(value, first_dim_only)
-        C = value[0].shape[-1]
-        new = torch.zeros((self._B, max(self.capacity, self._N), C), dtype=value[0].dtype, device=self.device)
+        dst = self._writable_view(key, value[0].shape[-1])
         for b, v in enumerate(value):
-            new[b, : v.shape[0]] = v.to(self.device)
-        self._store[key] = new
-        self._list_cache = {}
+            dst[b, : v.shape[0]] = _f32(v, self.device)
 
     points_padded = points_padded.setter(lambda self, v: self._set_padded("points", v))
     normals_padded = normals_padded.setter(lambda self, v: self._set_padded("normals", v))
@@ -389,10 +447,8 @@ class Pointclouds(object):
         return self.clone().pinhole_projection_(intrinsics)
 
     def _write_padded(self, key, value):
-        st = self._store[key].clone()
-        st[:, : self._N] = value
-        self._store[key] = st
-        self._list_cache = {}
+        n = self._N
+        self._writable_view(key, value.shape[-1])[:, :n] = value
 
     def offset_(self, offset):
         if not (torch.is_tensor(offset) or isinstance(offset, (float, int))):
@@ -470,10 +526,10 @@ class Pointclouds(object):
             return other
         other._B = self._B
         keep = max(self._N, 1)  # copy the populated rows only (one sync beats cloning gigabytes of spare capacity)
-        for key in _ATTRS:
-            st = self._store[key]
-            other._store[key] = None if st is None else fn(st[:, :keep])
-        other.device = other._store["points"].device
+        cp = lambda st: None if st is None else fn(st[:, :keep])
+        other._geo, other._col, other._feat = cp(self._geo), cp(self._col), cp(self._feat)
+        other._has_normals, other._has_cc = self._has_normals, self._has_cc
+        other.device = other._geo.device
         other._counts_dev = self._counts_dev.clone().to(other.device)
         other._cur = self._cur
         other._counts_host = None if self._counts_host is None else list(self._counts_host)
@@ -518,6 +574,14 @@ class Pointclouds(object):
         return to_plotly(self, index, include_colors, max_num_points, as_figure, point_size)
 
     # ------------------------------------------------------------------ growth
+    def _adopt(self, src: "Pointclouds"):
+        self._geo, self._col, self._feat, self._B = src._geo, src._col, src._feat, src._B
+        self._has_normals, self._has_cc = src._has_normals, src._has_cc
+        self._counts_dev, self._cur = src._counts_dev, src._cur
+        self._counts_host, self._bound, self._overflow = src._counts_host, src._bound, src._overflow
+        self._uninit, self._tail_dirty = src._uninit, src._tail_dirty
+        self._list_cache = {}
+
     def append_points(self, pointclouds: "Pointclouds"):
         """Appends another batch of clouds element-wise, in place (pointclouds.py:1117-1237)."""
         if not isinstance(pointclouds, type(self)):
@@ -529,12 +593,7 @@ class Pointclouds(object):
         if not pointclouds.has_points:
             return self
         if not self.has_points:
-            src = pointclouds.clone()
-            self._store, self._B = src._store, src._B
-            self._counts_dev, self._cur = src._counts_dev, src._cur
-            self._counts_host, self._bound, self._overflow = src._counts_host, src._bound, src._overflow
-            self._uninit, self._tail_dirty = src._uninit, src._tail_dirty
-            self._list_cache = {}
+            self._adopt(pointclouds.clone())
             return self
         if len(pointclouds) != len(self):
             raise ValueError("Batch size of pointclouds to append and to be appended must match: ({0} != {1})".format(
@@ -550,8 +609,8 @@ class Pointclouds(object):
         mine, theirs = self._host_counts(), pointclouds._host_counts()
         total = [a + b for a, b in zip(mine, theirs)]
         self.reserve(max(total))
-        for key in _ATTRS:
-            dst, src = self._store[key], pointclouds._store[key]
+        for dst, src in ((self._geo, pointclouds._geo), (self._col, pointclouds._col),
+                         (self._feat, pointclouds._feat)):
             if dst is None:
                 continue
             for b in range(self._B):

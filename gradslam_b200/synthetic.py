@@ -69,3 +69,13 @@ def make_sequence(B, L, H, W, seed=0, hole_fraction=0.02, motion_scale=1.0, pin_
     torch.rand((B, L, H, W, 3), generator=gen, out=rgb)
     Kt = torch.from_numpy(K.astype(np.float32)).view(1, 1, 4, 4).repeat(B, 1, 1, 1)
     return rgb, depth, Kt, poses
+
+
+def punch_lattice_holes(depth, row_step=5, col_step=7):
+    """Zeroes depth (..., H, W, 1) on a sparse lattice (rows 2, 2+row_step, ...; columns 3, 3+col_step, ...).  No two
+    holes touch, not even diagonally, so no valid pixel has BOTH its right and its lower neighbour missing: at such
+    pixels the normal is the normalised rounding residue of a cancelling cross product (see gsx_common.cuh cross_ref) and
+    its derivative is ~1e7 - fine for parity fixtures, useless for checking gradient FORMULAS against autograd."""
+    depth = depth.clone()
+    depth[..., 2::row_step, 3::col_step, :] = 0.0
+    return depth

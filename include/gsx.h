@@ -15,11 +15,15 @@
  *   - images are channels-last: depth (B,L,H,W,1), rgb/vertex/normal (B,L,H,W,3).  Per-frame calls take
  *     a base pointer for the frame plus the element stride (`*_bstride`, in floats) between batch elements,
  *     so frame s of a (B,L,H,W,C) tensor is addressed without a copy.
- *   - the surfel map is SoA with a fixed capacity: points/normals/colors (B,cap,3), ccounts (B,cap,1),
- *     counts int32 (B,).  Rows >= counts[b] are never read.
- *   - arithmetic is IEEE fp32 with NO fused multiply-add and a fixed association order (see DESIGN.md
- *     "canonical arithmetic"), so every decision (threshold, pixel rounding, arg-min key) is bit-exact
- *     against the CPU oracle.
+ *   - the surfel map has a fixed capacity and SECTOR-PACKED rows: map_geometry (B,cap,8) float32 rows
+ *     (px,py,pz,nx,ny,nz,ccount,0) - exactly one 32-byte DRAM sector per surfel - and map_colors (B,cap,4) rows
+ *     (r,g,b,0); both 16-byte aligned, every row access is a 128-bit load / store.  counts int32 (B,).  Rows
+ *     >= counts[b] are never read.  (gradslam's padded tensors points / normals / colors / features are the
+ *     strided views [..., 0:3], [..., 3:6], colours [..., 0:3], [..., 6:7] of these two arrays.)
+ *   - arithmetic is IEEE fp32 with a fixed association order and no fused multiply-add, except the normal
+ *     estimate's cross product and length, which are fused exactly as the reference's CPU build fuses them
+ *     (see DESIGN.md "canonical arithmetic"), so every decision (threshold, pixel rounding, arg-min key) is
+ *     bit-exact against the CPU oracle.
  */
 #ifndef GSX_H_
 #define GSX_H_
@@ -30,7 +34,7 @@
 extern "C" {
 #endif
 
-#define GSX_VERSION 100 /* 0.1.0 */
+#define GSX_VERSION 200 /* 0.2.0: sector-packed map rows, per-frame records */
 
 int gsx_version(void);
 const char *gsx_last_error(void);
@@ -63,109 +67,91 @@ int gsx_backproject_normals_bwd(const float *depth, int64_t depth_bstride, const
                                 float *g_poses, void *scratch, int64_t scratch_bytes, void *stream);
 
 /* ------------------------------------------------------------------------------------------------
- * Fused PointFusion map update (K2+K3 and K4), one live frame for all B elements.
+ * Fused PointFusion map update, one live frame for all B elements: three kernels
+ *   K1r  gsx_fusion_frame_records    per pixel: world vertex, world normal, confidence weight, depth -> one
+ *                                    32-byte record; re-arms the workspace for this frame
+ *   K2   gsx_fusion_project_select   per map row: projection, tests, per-pixel 128-bit arg-min
+ *   K4   gsx_fusion_merge_append     per pixel: merge the selected row or append a new surfel
  * replaces update_map_fusion = find_active_map_points + find_similar_map_points +
  *          find_best_unique_correspondences + fuse_with_map (+ Pointclouds.append_points)
  *          gradslam/slam/fusionutils.py:198-287, 290-411, 414-546, 580-722, 761-789;
  *          gradslam/structures/pointclouds.py:526-614, 1117-1237
  *
- * Workspace: gsx_fusion_workspace_bytes(B,H,W) bytes, zero-filled ONCE by the caller before first use
- * (cudaMemset 0); the kernels leave it clean for the next frame.  `epoch` must increase by one with
- * every gsx_fusion_merge_append call on the same workspace, starting at 1.                        */
+ * Workspace: gsx_fusion_workspace_bytes(B,H,W) bytes, 16-byte aligned.  Nothing in it has to survive from one frame
+ * to the next: gsx_fusion_frame_records re-arms everything the other two kernels consume, so no zero-fill and no
+ * epoch bookkeeping is needed and an abandoned frame cannot poison the next one.  (Only the statistics below
+ * accumulate; zero them once if they are read.)                                                            */
 int64_t gsx_fusion_workspace_bytes(int B, int H, int W);
 /* byte offset inside the workspace of uint64 stats[B][2] = running totals of {map points inside the
  * live frustum ("active"), map points merged}; used for the roofline's algorithmic-byte count. */
 int64_t gsx_fusion_workspace_stats_offset(int B, int H, int W);
 
+/* K1r: frame records of the live frame.
+ * replaces, per pixel, RGBDImages.global_vertex_map / global_normal_map (gradslam/structures/rgbdimages.py:643-762)
+ *          and get_alpha on the camera-frame vertex (gradslam/slam/fusionutils.py:16-73, :657)
+ * Either evaluate everything from the depth image (gvertex = gnormal = vertex = NULL; intrinsics required; poses =
+ * camera-to-world, or NULL for "world frame == camera frame"), or pack already materialised maps: gvertex / gnormal /
+ * vertex (B,H,W,3) (outputs of gsx_backproject_normals_fwd, used by the differentiable mode; intrinsics / poses are
+ * then ignored).  Same arithmetic either way, bit for bit. */
+int gsx_fusion_frame_records(const float *depth, int64_t depth_bstride, const float *intrinsics, int64_t K_bstride,
+                             const float *poses, int64_t pose_bstride, const float *gvertex, const float *gnormal,
+                             const float *vertex, int B, int H, int W, double sigma, void *workspace, void *stream);
+
 /* K2+K3: project every map point into the live camera, keep points that are in the frustum, close to
  * the frame vertex they land on and with a similar normal, and reduce per pixel to the best candidate
  * (largest confidence count, then smallest ray distance, then smallest index) with a 128-bit atomic
- * min.  max_count = host upper bound on counts[b] (sizes the grid).
- * Frame geometry: either pass the materialised world-frame maps gvertex / gnormal (B,H,W,3) (outputs of
- * gsx_backproject_normals_fwd), or pass both as NULL and give the live depth image: the kernel then
- * evaluates vertex and normal of the pixel each point lands on directly from depth (same arithmetic, bit
- * for bit) and the maps never touch HBM. */
-int gsx_fusion_project_select(const float *map_points, const float *map_normals, const float *map_ccounts,
-                              const int32_t *counts, int64_t capacity, int64_t max_count, const float *poses,
-                              int64_t pose_bstride, const float *intrinsics, int64_t K_bstride,
-                              const float *depth, int64_t depth_bstride, const float *gvertex,
-                              const float *gnormal, int B, int H, int W, float dist_th, float dot_th,
-                              void *workspace, void *stream);
+ * min.  max_count = host upper bound on counts[b] (sizes the grid).  The frame records of the live frame must be in
+ * the workspace (gsx_fusion_frame_records). */
+int gsx_fusion_project_select(const float *map_geometry, const int32_t *counts, int64_t capacity, int64_t max_count,
+                              const float *poses, int64_t pose_bstride, const float *intrinsics, int64_t K_bstride,
+                              int B, int H, int W, float dist_th, float dot_th, void *workspace, void *stream);
 
 /* K4: per pixel, merge the selected map point with the frame sample (confidence-weighted mean) or, for
  * valid pixels without a match, append a new surfel in row-major pixel order (stable single-pass scan).
- * counts_in -> counts_out (may not alias).  map_ccounts may be NULL for maps without confidence counts
- * (ICPSLAM aggregation, gradslam/slam/fusionutils.py:725-758): then nothing is merged and every valid
- * pixel is appended.  overflow_flag (int32, device) is set to 1 if capacity was
- * exceeded (the surplus points are dropped).  Frame geometry as for gsx_fusion_project_select: pass the
- * maps to merge/append (gvertex, gnormal), or NULL for both plus the camera poses to sample depth on the
- * fly. */
-int gsx_fusion_merge_append(float *map_points, float *map_normals, float *map_colors, float *map_ccounts,
-                            const int32_t *counts_in, int32_t *counts_out, int64_t capacity,
-                            const float *depth, int64_t depth_bstride, const float *rgb, int64_t rgb_bstride,
-                            const float *intrinsics, int64_t K_bstride, const float *poses,
-                            int64_t pose_bstride, const float *gvertex, const float *gnormal, int B, int H,
-                            int W, double sigma, void *workspace, uint32_t epoch, int32_t *overflow_flag,
-                            void *stream);
+ * counts_in -> counts_out (may not alias).  with_ccounts = 0 for maps without confidence counts
+ * (ICPSLAM aggregation, gradslam/slam/fusionutils.py:725-758): then nothing is merged, every valid
+ * pixel is appended and the ccount slot of the new rows is 0.  overflow_flag (int32, device) is set to 1 if capacity
+ * was exceeded (the surplus points are dropped).  rgb: live colours (B,H,W,3), element stride rgb_bstride.
+ * assoc_out: NULL, or int32 (B,H,W) zero-filled by the caller that receives where every pixel went: +(row+1) appended
+ * as `row`, -(row+1) merged into `row`, 0 dropped (the differentiable mode's forward: the caller runs the kernel on
+ * a COPY of the map so that the pre-merge rows survive for the backward). */
+int gsx_fusion_merge_append(float *map_geometry, float *map_colors, int with_ccounts, const int32_t *counts_in,
+                            int32_t *counts_out, int64_t capacity, const float *rgb, int64_t rgb_bstride, int B, int H,
+                            int W, void *workspace, int32_t *overflow_flag, int32_t *assoc_out, void *stream);
 
-/* K4 as a differentiable op (autograd.Function forward / backward).
+/* Backward of K4 (autograd.Function backward of the differentiable mode).
  * replaces the tape PyTorch builds through fuse_with_map   gradslam/slam/fusionutils.py:654-720 (merge),
  *          :702-720 + gradslam/structures/pointclouds.py:1117-1237 (append), get_alpha :16-73
- * _fwd: same kernel as gsx_fusion_merge_append on the materialised frame maps (gvertex, gnormal), run on a COPY of
- *       the map (the caller copies; the pre-merge map must survive for the backward), and additionally records in
- *       assoc_out int32 (B,H,W), zero-filled by the caller, where every pixel went: +(row+1) appended as `row`,
- *       -(row+1) merged into `row`, 0 dropped.
- * _bwd: upstream gradients of the updated map (B,capacity_out,.) (any may be NULL = zero) -> gradients of the
- *       pre-merge map (B,capacity_in,.) (every row written; padding rows zero) and of the frame values: world vertex /
- *       normal maps, colours and - through the confidence weight alpha - the camera-frame vertex map, all (B,H,W,3).
- *       map_ccounts / d_map_ccounts are both NULL for maps without confidence counts. */
-int gsx_fusion_merge_append_fwd(float *map_points, float *map_normals, float *map_colors, float *map_ccounts,
-                                const int32_t *counts_in, int32_t *counts_out, int64_t capacity,
-                                const float *depth, int64_t depth_bstride, const float *rgb, int64_t rgb_bstride,
-                                const float *intrinsics, int64_t K_bstride, const float *gvertex,
-                                const float *gnormal, int B, int H, int W, double sigma, void *workspace,
-                                uint32_t epoch, int32_t *overflow_flag, int32_t *assoc_out, void *stream);
-int gsx_fusion_merge_append_bwd(const int32_t *assoc, const int32_t *counts_in, const float *map_points,
-                                const float *map_normals, const float *map_colors, const float *map_ccounts,
-                                int64_t capacity_in, const float *g_points, const float *g_normals,
-                                const float *g_colors, const float *g_ccounts, int64_t capacity_out,
+ * upstream gradients of the updated map in the packed row layout (B,capacity_out,8 / 4) (either may be NULL = zero)
+ * -> gradients of the pre-merge map (B,capacity_in,8 / 4) (every row written; padding rows and padding slots zero) and
+ * of the frame values: world vertex / normal maps, colours and - through the confidence weight alpha - the
+ * camera-frame vertex map, all (B,H,W,3). */
+int gsx_fusion_merge_append_bwd(const int32_t *assoc, const int32_t *counts_in, const float *map_geometry,
+                                const float *map_colors, int with_ccounts, int64_t capacity_in,
+                                const float *g_geometry, const float *g_colors, int64_t capacity_out,
                                 const float *gvertex, const float *gnormal, const float *rgb, const float *vertex,
-                                int B, int H, int W, double sigma, float *d_map_points, float *d_map_normals,
-                                float *d_map_colors, float *d_map_ccounts, float *d_gvertex, float *d_gnormal,
-                                float *d_rgb, float *d_vertex, void *stream);
+                                int B, int H, int W, double sigma, float *d_map_geometry, float *d_map_colors,
+                                float *d_gvertex, float *d_gnormal, float *d_rgb, float *d_vertex, void *stream);
 
-/* Whole-sequence driver with ground-truth poses: for s in [s_begin,s_end): K2/K3 -> K4 with the frame
- * geometry sampled on the fly from depth (no K1 launch, no frame maps in HBM), no host sync.
+/* Whole-sequence driver with ground-truth poses: for s in [s_begin,s_end): K1r -> K2/K3 -> K4, no host sync.
  * replaces ICPSLAM.forward with odom='gt' + PointFusion._map   gradslam/slam/icpslam.py:99-138,
  *          gradslam/slam/pointfusion.py:107-112
  * depth (B,L,H,W), rgb (B,L,H,W,3) dense; poses (B,L,4,4) dense; intrinsics (B,4,4) dense.
  * counts: int32 (2,B) ping-pong buffer; row (s_begin & 1) holds the current sizes on entry; on return the
  * current sizes are in row (s_end & 1).  max_count0 = host upper bound of the sizes on entry.
- * scratch_maps: unused (may be NULL); kept for ABI stability.
- * epoch0 = epoch of frame s_begin (the call consumes s_end - s_begin epochs).  Splitting a sequence
- * into several calls (s_begin..s_end chunks) lets the caller overlap host->device copies of later
- * frames with the fusion of earlier ones. */
-/* LAYOUT STUDY (not used by the Python package; prepared for the next round): the same whole-sequence
- * driver on the "geo32" map layout - map_geometry (B,capacity,8) rows (px,py,pz,nx,ny,nz,ccount,0), exactly one 32-byte
- * sector each and 16-byte aligned, plus map_colors (B,capacity,3).  K2 then reads one sector per map point with two
- * 128-bit loads and K4 gathers / rewrites two sectors per merged row instead of four.  Same arithmetic, same results
- * (scripts/geo32_experiment.py compares the two layouts bit for bit and times them). */
-int gsx_pointfusion_sequence_gt_geo32(float *map_geometry, float *map_colors, int32_t *counts, int64_t capacity,
-                                      int64_t max_count0, const float *depth, const float *rgb,
-                                      const float *intrinsics, const float *poses, int B, int L, int s_begin,
-                                      int s_end, int H, int W, float dist_th, float dot_th, double sigma,
-                                      void *workspace, uint32_t epoch0, int32_t *overflow_flag, void *stream);
-
+ * Splitting a sequence into several calls (s_begin..s_end chunks) lets the caller overlap host->device copies of
+ * later frames with the fusion of earlier ones.  On a launch failure the internal streams are still joined to
+ * `stream` before the error is returned. */
 /* number of independent batch groups gsx_pointfusion_sequence_gt runs on concurrent internal streams for a batch of
  * B (default 2, environment GSX_SEQ_GROUPS = 1..4 overrides; never more than B).  Kernel launches per call =
- * groups * (2 * frames - [map empty on entry]). */
+ * groups * (3 * frames - [map empty on entry]). */
 int gsx_pointfusion_sequence_groups(int B);
-int gsx_pointfusion_sequence_gt(float *map_points, float *map_normals, float *map_colors, float *map_ccounts,
-                                int32_t *counts, int64_t capacity, int64_t max_count0, const float *depth,
-                                const float *rgb, const float *intrinsics, const float *poses, int B, int L,
-                                int s_begin, int s_end, int H, int W, float dist_th, float dot_th,
-                                double sigma, float *scratch_maps,
-                                void *workspace, uint32_t epoch0, int32_t *overflow_flag, void *stream);
+int gsx_pointfusion_sequence_gt(float *map_geometry, float *map_colors, int32_t *counts, int64_t capacity,
+                                int64_t max_count0, const float *depth, const float *rgb, const float *intrinsics,
+                                const float *poses, int B, int L, int s_begin, int s_end, int H, int W, float dist_th,
+                                float dot_th, double sigma, void *workspace, int32_t *overflow_flag, void *stream);
+/* test hook: the next gsx_pointfusion_sequence_gt call reports a launch failure at frame s (once); -1 = off */
+void gsx_debug_fail_at_frame(int s);
 
 /* ------------------------------------------------------------------------------------------------
  * Dataset-native ingest: 8-bit colour (n_pixels,3) and 16-bit depth (n_pixels) as stored by
@@ -194,22 +180,24 @@ int gsx_compact_indices(const uint8_t *flags, int64_t n, int64_t *out_idx, int64
 
 /* per map slot (b, n < width): 1 if the point is a valid map point inside the live frustum; hw = h*W + w
  * of the pixel it rounds to.  flags, hw: (B, width). */
-int gsx_active_eval(const float *map_points, const int32_t *counts, int64_t capacity, int64_t width,
+int gsx_active_eval(const float *map_geometry, const int32_t *counts, int64_t capacity, int64_t width,
                     const float *poses, int64_t pose_bstride, const float *intrinsics, int64_t K_bstride, int B,
                     int H, int W, uint8_t *flags, int32_t *hw, void *stream);
 
 /* per table row: 1 if ||frame vertex - map point|| < dist_th and <frame normal, map normal> > dot_th. */
-int gsx_similar_eval(const int64_t *table, int64_t rows, const float *map_points, const float *map_normals,
-                     int64_t capacity, const float *gvertex, const float *gnormal, int B, int H, int W,
-                     float dist_th, float dot_th, uint8_t *flags, void *stream);
+int gsx_similar_eval(const int64_t *table, int64_t rows, const float *map_geometry, int64_t capacity,
+                     const float *gvertex, const float *gnormal, int B, int H, int W, float dist_th, float dot_th,
+                     uint8_t *flags, void *stream);
 
 /* per pixel winner among the table rows (largest ccount, then smallest ray distance, then smallest n):
- * pixel_flags (B*H*W) and pixel_n (B*H*W, -1 if none).  workspace = the fusion workspace (left clean). */
-int gsx_unique_select(const int64_t *table, int64_t rows, const float *map_points, const float *map_ccounts,
-                      int64_t capacity, const float *gvertex, int B, int H, int W, void *workspace,
-                      uint8_t *pixel_flags, int64_t *pixel_n, void *stream);
+ * pixel_flags (B*H*W) and pixel_n (B*H*W, -1 if none).  records: scratch of B*H*W 16-byte records, 16-byte
+ * aligned (cleared by the call). */
+int gsx_unique_select(const int64_t *table, int64_t rows, const float *map_geometry, int64_t capacity,
+                      const float *gvertex, int B, int H, int W, void *records, uint8_t *pixel_flags,
+                      int64_t *pixel_n, void *stream);
 
-/* stores every table row as its pixel's winner in the fusion workspace (then call gsx_fusion_merge_append). */
+/* stores every table row as its pixel's winner in the fusion workspace: call it AFTER gsx_fusion_frame_records
+ * (which re-arms the workspace) and BEFORE gsx_fusion_merge_append. */
 int gsx_records_from_table(const int64_t *table, int64_t rows, int64_t capacity, int B, int H, int W,
                            void *workspace, void *stream);
 
@@ -300,8 +288,7 @@ int gsx_icp_align(const float *src_points, const int32_t *src_count, int ns_stri
  * call on the same workspace, starting at 1. */
 int64_t gsx_icp_workspace_bytes(int B, int H, int W, int ds, int64_t map_capacity);
 int64_t gsx_icp_tgt_scratch_bytes(int B, int64_t tgt_capacity);
-int gsx_icp_localize(const float *map_points, const float *map_normals, const int32_t *counts, int64_t capacity,
-                     int64_t max_count, const float *depth, int64_t depth_bstride, const float *intrinsics,
+int gsx_icp_localize(const float *map_geometry, const int32_t *counts, int64_t capacity, int64_t max_count, const float *depth, int64_t depth_bstride, const float *intrinsics,
                      int64_t K_bstride, const float *prev_poses, int64_t prev_pose_bstride, int B, int H, int W,
                      int ds, int mode, int numiters, float damp, int use_dist_thresh, float dist_thresh,
                      float lambda_max, float Bp, float B2p, float nu, void *tgt_scratch, int64_t tgt_capacity,

@@ -3,9 +3,19 @@ implementation of the same op chain (gradslam/structures/rgbdimages.py:643-762).
 import pytest
 import torch
 
-from gradslam_b200.synthetic import make_sequence
+from gradslam_b200.synthetic import make_sequence as _make_sequence, punch_lattice_holes
 
 pytestmark = pytest.mark.gpu
+
+
+def make_sequence(*args, **kw):
+    """Inputs for checking gradient FORMULAS: sparse lattice holes instead of random ones, so that no pixel's normal is
+    the normalised residue of a cancelling cross product (derivative ~1e7; both the kernels and the reference produce
+    it, but no tolerance survives it).  Parity on the random-hole distribution is pinned by the golden fixtures
+    (tests/golden/ref_grad.npz is recorded from the reference on random holes)."""
+    kw.setdefault("hole_fraction", 0.0)
+    rgb, depth, K, poses = _make_sequence(*args, **kw)
+    return rgb, punch_lattice_holes(depth), K, poses
 DEV = "cuda:0"
 
 
@@ -40,7 +50,7 @@ def test_backproject_backward_matches_autograd(shape):
     import gradslam_b200 as gs
 
     B, L, H, W = shape
-    rgb, depth, K, poses = make_sequence(B, L, H, W, seed=21)  # no degenerate cross products
+    rgb, depth, K, poses = make_sequence(B, L, H, W, seed=21)
     g = torch.Generator().manual_seed(3)
     ups = [torch.randn(B, L, H, W, 3, generator=g).to(DEV) for _ in range(4)]
     # engine

@@ -196,3 +196,60 @@ def test_sliced_sequence_with_cached_maps():
         assert torch.equal(pc.points_list[b], ref.points_list[b])
         assert torch.equal(pc.normals_list[b], ref.normals_list[b])
         assert torch.equal(pc.features_list[b], ref.features_list[b])
+
+
+def test_sequence_driver_error_path_joins_streams_and_poisons_nothing():
+    """A launch failure in the middle of gsx_pointfusion_sequence_gt (injected at frame 2 of 4, after the batch-group
+    streams were forked and two frames were enqueued): the call returns the error as a RuntimeError, the internal streams
+    are joined to the caller's stream (a synchronize returns, nothing is left running unordered), and the next call on
+    the same cached workspace produces the bit-identical, correct map - no epoch / record state survives a failed call."""
+    import gradslam_b200 as gs
+    from gradslam_b200 import _C
+
+    B, L, H, W = 4, 4, 48, 64
+    rgb, depth, K, poses = make_sequence(B, L, H, W, seed=12)
+    frames = _frames(gs, rgb, depth, K, poses, _dev())
+    slam = gs.PointFusion(odom="gt", device=_dev())
+    good, _ = slam(frames)
+    _C.lib().gsx_debug_fail_at_frame(2)
+    with pytest.raises(RuntimeError, match="injected failure at frame 2"):
+        slam(frames)
+    torch.cuda.synchronize()
+    again, _ = slam(frames)
+    assert again.num_points_per_pointcloud.tolist() == good.num_points_per_pointcloud.tolist()
+    for b in range(B):
+        assert torch.equal(again.points_list[b], good.points_list[b])
+        assert torch.equal(again.features_list[b], good.features_list[b])
+    # and the per-frame path on the same workspace is unaffected as well
+    ref = oracle.run_slam(rgb, depth, K, poses, odom="gt")
+    _compare_maps(again, ref.map)
+
+
+def test_packed_store_views_and_input_validation():
+    """The public tensors are strided views of the packed rows (no copies), and tensors whose pointers reach a kernel
+    are validated: a CPU map or a float64 colour image raises instead of being reinterpreted."""
+    import gradslam_b200 as gs
+    from gradslam_b200.slam import fusionutils as fu
+
+    rgb, depth, K, poses = make_sequence(2, 2, 32, 40, seed=2)
+    frames = _frames(gs, rgb, depth, K, poses, _dev())
+    pc = fu.update_map_fusion(gs.Pointclouds(device=_dev()), frames[:, 0], 0.05, 0.94, 0.6)
+    assert pc._geo.shape[-1] == 8 and pc._col.shape[-1] == 4
+    assert pc.points_padded.data_ptr() == pc._geo.data_ptr()
+    assert pc.normals_padded.data_ptr() == pc._geo.data_ptr() + 12
+    assert pc.features_padded.data_ptr() == pc._geo.data_ptr() + 24
+    assert pc.colors_padded.data_ptr() == pc._col.data_ptr()
+    assert pc.points_padded.stride() == (pc.capacity * 8, 8, 1)
+    assert (pc._geo[..., 7] == 0).all() and (pc._col[..., 3] == 0).all()
+    # float64 inputs are cast to float32 rows on construction
+    p64 = torch.rand(1, 5, 3, dtype=torch.float64, device=_dev())
+    assert gs.Pointclouds(p64, p64, p64, p64[..., :1]).points_padded.dtype == torch.float32
+    # a CPU map with CUDA frames, and a float64 colour image, raise
+    cpu_map = gs.Pointclouds(torch.rand(2, 4, 3), torch.rand(2, 4, 3), torch.rand(2, 4, 3), torch.rand(2, 4, 1))
+    with pytest.raises((RuntimeError, ValueError)):
+        fu.update_map_fusion(cpu_map, frames[:, 1], 0.05, 0.94, 0.6)
+    bad = gs.RGBDImages(rgb.double().to(_dev()), depth.to(_dev()), K.to(_dev()), poses.to(_dev()))
+    with pytest.raises(TypeError):
+        fu.update_map_fusion(pc, bad[:, 1], 0.05, 0.94, 0.6)
+    with pytest.raises(ValueError, match="both have or not have features"):
+        fu.update_map_aggregate(pc, frames[:, 1])
