@@ -6,8 +6,10 @@
     torchrun ... bench.py --gpus N ...                         one rank per GPU (weak scaling: B=8 per GPU)
 
 One "step" = one whole `PointFusion(odom='gt')(frames)` call over a (B, L) batch of synthetic RGB-D
-sequences = B*L frame updates (K2/K3 project+select and K4 merge+append per frame; the frame's vertex /
-normal geometry (K1) is evaluated on the fly inside both kernels).
+sequences = B*L frame updates (per frame: K1r frame records, K2/K3 project+select, K3c per-tile append counts,
+K4 merge+append).  The timed region is EXACTLY --steps steps; because 20 steps are only ~0.1 s, the region is
+measured `--repeats` times back to back (default: enough repeats for >= 100 timed steps) and the MEDIAN region
+is reported (all of them are listed under "timed_regions_ms").
 Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement" for what each key means.
 """
 import argparse
@@ -37,7 +39,9 @@ def parse():
     ap.add_argument("--height", type=int, default=480)
     ap.add_argument("--width", type=int, default=640)
     ap.add_argument("--cpu-sample-frames", type=int, default=12, help="frames of the CPU-baseline sample (B=1)")
+    ap.add_argument("--repeats", type=int, default=0, help="timed regions of --steps steps each (0: ceil(100/steps))")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extra-configs", action="store_true", help="skip the B=1 / L=32 (config 2) line")
     ap.add_argument("--no-icp", action="store_true", help="skip the secondary ICP-odometry measurement")
     ap.add_argument("--no-raw", action="store_true", help="skip the dataset-native (uint8/uint16) ingest measurement")
     return ap.parse_args()
@@ -148,13 +152,23 @@ def run_reference(args, rank, world):
         vals.append((fps, dt))
     fps = sum(v[0] for v in vals) / len(vals)
     ms = 1e3 * sum(v[1] for v in vals) / len(vals)
-    sample = "PointFusion(odom=gt) %dx%d B=%d L=%d per step (bounded sample of the B=%d L=%d workload)" % (
-        args.width, args.height, sample_B, sample_L, args.batch, args.seqlen)
+    sample = ("PointFusion(odom=gt) %dx%d B=%d sequence x L=%d frames per step: a bounded sample of the B=%d x L=%d "
+              "workload (the CPU arm runs ~2 frames/s), timed with the thread count that is fastest for this op chain "
+              "(%d of %d cores; torch.unique(dim=0) dominates and slows down with more threads)" % (
+                  args.width, args.height, sample_B, sample_L, args.batch, args.seqlen, cores, os.cpu_count() or 1))
+    cfg = workload_config(args, 1)
+    # say what RAN: the sampled batch / length, not the workload it was sampled from
+    cfg.update({"workload": cfg["workload"].split(", %dx%d" % (args.width, args.height))[0] +
+                ", %dx%d, B=%d sequence x L=%d frames per step (bounded sample of B=%d x L=%d)" % (
+                    args.width, args.height, sample_B, sample_L, args.batch, args.seqlen),
+                "global_batch": sample_B, "seq_len": sample_L, "frames_per_step": sample_B * sample_L,
+                "parallelism": "host cores (%d threads)" % cores,
+                "sampled_from": {"global_batch": args.batch, "seq_len": args.seqlen}})
     line = {
         "impl": "reference", "metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": workload_config(args, 1),
+        "config": cfg,
         "cpu_baseline": {"value": fps, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": fps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -223,25 +237,40 @@ def main():
             dist.barrier()
         torch.cuda.synchronize(dev)
 
+    dl_stream = torch.cuda.Stream(device=dev)
+    dl_state = {"host": None, "bytes": 0}
+
+    def read_back(pc, poses):
+        """Result read-back of one step: recovered poses, map sizes and the fused map itself (packed rows, exact sizes)
+        into pinned host memory, on a side stream so that it overlaps the next step's upload and fusion."""
+        dl_stream.wait_stream(torch.cuda.current_stream(dev))
+        host = pc.download(out=dl_state["host"], stream=dl_stream)
+        dl_state["host"] = host
+        rows = sum(host._host_counts())
+        dl_state["bytes"] = rows * (32 + 16) + poses.numel() * 4 + len(host) * 8
+        return host
+
     def run_steps(frames, steps, d2h):
-        """`steps` whole-batch PointFusion calls.  N>1: the final-map all-gather of step k (NCCL, communication
-        stream) overlaps the fusion of step k+1; the last gather is awaited before returning."""
+        """`steps` whole-batch PointFusion calls.  N>1: the final-map exchange of step k (communication stream) overlaps
+        the fusion of step k+1; the last one is awaited before returning.  d2h: the result (poses + the fused map of this
+        rank) is read back to pinned host memory; the read-back of step k overlaps step k+1."""
         res = None
         pending = None  # (gather handle, poses) of the previous step
+        prev = None  # (map, poses) of the previous step, still to be read back
         for _ in range(steps):
             pc, poses = slam(frames)
             if pending is not None:  # step k-1's maps travel while step k (just enqueued) computes
-                pc_done, poses_done = parallel.gather_maps_end(pending[0], wait=False), pending[1]
-                if d2h:
-                    res = (poses_done.cpu(), pc_done.num_points_per_pointcloud.cpu())
+                parallel.gather_maps_end(pending[0], wait=False)
+            if d2h and prev is not None:
+                res = (prev[1].cpu(), read_back(*prev))
             if world > 1:
                 pending = (parallel.gather_maps_begin(pc), poses)
-            elif d2h:  # result read-back: recovered poses + per-map sizes
-                res = (poses.cpu(), pc.num_points_per_pointcloud.cpu())
+            prev = (pc, poses)
         if pending is not None:
-            pc_done = parallel.gather_maps_end(pending[0], wait=True)
-            if d2h:
-                res = (pending[1].cpu(), pc_done.num_points_per_pointcloud.cpu())
+            parallel.gather_maps_end(pending[0], wait=True)
+        if d2h:
+            res = (prev[1].cpu(), read_back(*prev))
+            torch.cuda.current_stream(dev).wait_stream(dl_stream)
         return res
 
     def timed(frames, steps, d2h):
@@ -259,16 +288,25 @@ def main():
         barrier()
         return ms, res
 
+    def timed_median(frames, steps, d2h, repeats):
+        """`repeats` timed regions of exactly `steps` steps each; returns (median ms, all ms, last result)."""
+        all_ms, res = [], None
+        for _ in range(repeats):
+            ms, res = timed(frames, steps, d2h)
+            all_ms.append(ms)
+        return sorted(all_ms)[len(all_ms) // 2], all_ms, res
+
+    repeats = args.repeats if args.repeats > 0 else max(1, -(-100 // max(1, args.steps)))
     if world > 1:  # setup, not warm-up: let the caching allocator reach its steady state (two map stores and two sets
         run_steps(frames_dev, 3, d2h=False)  # of gather buffers are alive at once in the pipelined loop)
     run_steps(frames_dev, max(args.warmup, 3), d2h=False)  # same (pipelined) code path as the timed region
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    ms_dev, _ = timed(frames_dev, args.steps, d2h=False)
+    ms_dev, all_dev, _ = timed_median(frames_dev, args.steps, False, repeats)
     clocks = sampler.stop() if rank == 0 else None
     run_steps(frames_host, 3, d2h=True)
-    ms_e2e, res = timed(frames_host, args.steps, d2h=True)
+    ms_e2e, all_e2e, res = timed_median(frames_host, args.steps, True, repeats)
 
     # extra: the same job fed in dataset-native form (uint8 colour + uint16 depth, 5 B/pixel over PCIe instead of 16)
     raw_extra = None
@@ -281,18 +319,20 @@ def main():
         dep_u16 = torch.from_numpy(np.round(depth_h.numpy()[..., 0] * 5000.0).astype(np.uint16)).pin_memory()
         raw = RawRGBD(col_u8, dep_u16, K_h, poses_h, scaling_factor=5000.0)
         run_steps(raw, 3, d2h=True)
-        ms_raw, _ = timed(raw, args.steps, d2h=True)
+        ms_raw, _, _ = timed_median(raw, args.steps, True, min(repeats, 3))
         raw_extra = {"value": B * L * world * args.steps / (ms_raw / 1e3), "unit": UNIT, "ms_per_step": ms_raw / args.steps,
                      "h2d_bytes_per_step": col_u8.numel() + dep_u16.numel() * 2 + (K_h.numel() + poses_h.numel()) * 4,
+                     "d2h_bytes_per_step": dl_state["bytes"],
                      "note": "PointFusion(odom='gt')(RawRGBD): uint8 colour + uint16 depth (TUM/ICL on-disk format, "
-                             "depth = u16/5000) uploaded from pinned memory and converted on the device"}
+                             "depth = u16/5000) uploaded from pinned memory and converted on the device; same "
+                             "read-back as e2e"}
         del raw, col_u8, dep_u16
 
     frames_per_step = B * L * world
     value = frames_per_step * args.steps / (ms_dev / 1e3)
     e2e = frames_per_step * args.steps / (ms_e2e / 1e3)
     h2d = (rgb_h.numel() + depth_h.numel() + K_h.numel() + poses_h.numel()) * 4
-    d2h = (res[0].numel() * 4 + res[1].numel() * 8) if res is not None else 0
+    d2h = dl_state["bytes"]
 
     # per-kernel timing + roofline of the dominant kernel (rank 0's GPU; every rank runs the same work)
     roofline, kernels, frames_info = None, None, None
@@ -344,6 +384,25 @@ def main():
                      "frames_per_s": B * Li / ms * 1e3, "ms_per_step": ms,
                      "max_abs_pose_error_vs_gt": float((rec.cpu() - p2).abs().max())}
 
+    # BASELINE.json configs[1]: one sequence (B=1), L=32, forward only - the launch-latency-bound end of the path
+    small_extra = None
+    if rank == 0 and not args.no_extra_configs:
+        fr1 = gs.RGBDImages(rgb_d[:1], depth_d[:1], K_d[:1], poses_d[:1])
+        for _ in range(3):
+            slam(fr1)
+        torch.cuda.synchronize(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(20):
+            pc1, _ = slam(fr1)
+        e1.record()
+        torch.cuda.synchronize(dev)
+        ms1 = e0.elapsed_time(e1) / 20
+        small_extra = {"workload": "PointFusion(odom='gt') %dx%d B=1 L=%d, 1 GPU, forward (configs[1])" % (W, H, L),
+                       "frames_per_s": L / ms1 * 1e3, "ms_per_step": ms1,
+                       "us_per_frame": 1e3 * ms1 / L,
+                       "vs_batched_per_frame": (ms1 / L) / ((ms_dev / args.steps) / (B * L))}
+
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         fps, dt, cores, _ = cpu_reference_run(1, args.cpu_sample_frames, H, W)
@@ -360,11 +419,15 @@ def main():
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": workload_config(args, world),
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "ms_per_step": ms_e2e / args.steps},
-            # K2/K3 + K4 per frame and per concurrent batch group; K2 is skipped on the empty map
-            "gpu_launches": groups * (2 * L - 1) * args.steps, "sequence_groups": groups,
+                    "ms_per_step": ms_e2e / args.steps,
+                    "result": "poses + map sizes + the fused map of this rank (packed rows, exact sizes) into pinned "
+                              "host memory, overlapped with the next step",
+                    "timed_regions_ms": all_e2e},
+            # K1r + K2/K3 + K3c + K4 per frame and per concurrent batch group; K2 is skipped on the empty map
+            "gpu_launches": groups * (4 * L - 1) * args.steps, "sequence_groups": groups,
+            "repeats": repeats, "timed_regions_ms": all_dev,
             "roofline": roofline, "cpu_baseline": cpu_baseline, "clocks": clocks, "kernels": kernels,
-            "icp_odometry": icp_extra, "e2e_raw_ingest": raw_extra,
+            "icp_odometry": icp_extra, "e2e_raw_ingest": raw_extra, "config2_b1_l32": small_extra,
             "final_map_points_per_sequence": (frames_info[-1]["map_points"] + frames_info[-1]["new"]) // B
             if frames_info else None,
         }

@@ -44,6 +44,7 @@ SIGNATURES = {
         c_int, [c_vp, c_vp, c_vp, c_vp, c_int, c_i64, c_vp, c_vp, c_i64, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int,
                 c_double, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "gsx_pointfusion_sequence_groups": (c_int, [c_int]),
+    "gsx_pointfusion_sequence_workspace_bytes": (c_i64, [c_int, c_int, c_int]),
     "gsx_pointfusion_sequence_gt": (
         c_int, [c_vp, c_vp, c_vp, c_i64, c_i64, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_int,
                 c_float, c_float, c_double, c_vp, c_vp, c_vp]),

@@ -237,6 +237,37 @@ __device__ __forceinline__ U128 cas128(U128 *addr, U128 expected, U128 desired) 
   return old;
 }
 
+// ---- L2 residency hints (createpolicy + .L2::cache_hint) -----------------------------------------------------------
+// The per-frame arg-min records are hit by scattered read-modify-writes; if their sectors have left the L2 every one of
+// them becomes a DRAM read + write-back.  Streaming data (map rows, colours) is therefore loaded evict-first and the
+// records are touched evict-last, so the records of the frame in flight stay resident.
+__device__ __forceinline__ unsigned long long l2_policy_evict_last() {
+  unsigned long long p;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ unsigned long long l2_policy_evict_first() {
+  unsigned long long p;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ float4 ldg128_hint(const float *addr, unsigned long long pol) {
+  float4 v;
+  asm volatile("ld.global.nc.L2::cache_hint.v4.f32 {%0, %1, %2, %3}, [%4], %5;"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+               : "l"(addr), "l"(pol));
+  return v;
+}
+__device__ __forceinline__ float2 ldg64_hint(const float *addr, unsigned long long pol) {
+  float2 v;
+  asm volatile("ld.global.nc.L2::cache_hint.v2.f32 {%0, %1}, [%2], %3;" : "=f"(v.x), "=f"(v.y) : "l"(addr), "l"(pol));
+  return v;
+}
+__device__ __forceinline__ void stg128_hint(float *addr, const float4 &v, unsigned long long pol) {
+  asm volatile("st.global.L2::cache_hint.v4.f32 [%0], {%1, %2, %3, %4}, %5;" ::"l"(addr), "f"(v.x), "f"(v.y), "f"(v.z),
+               "f"(v.w), "l"(pol)
+               : "memory");
+}
 __device__ __forceinline__ U128 load128_relaxed(const U128 *addr) {
   U128 v;
   asm volatile("ld.relaxed.gpu.global.v2.u64 {%0, %1}, [%2];" : "=l"(v.lo), "=l"(v.hi) : "l"(addr) : "memory");

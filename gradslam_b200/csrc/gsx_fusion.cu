@@ -631,13 +631,11 @@ __global__ void __launch_bounds__(256) k_merge_bwd_pixels(MergeBwdArgs a) {
   }
 }
 
-// One frame (K1r + K2 + K4) for the batch elements [b0, b0 + nb) of a B_total-element problem, on `st`.  All pointers are
-// the FULL-batch base pointers; batch elements are independent, so disjoint groups may run concurrently on different
-// streams (gsx_pointfusion_sequence_gt).
-int fusion_frame_group(float *geo, float *col, const int32_t *cin, int32_t *cout, int64_t cap, int64_t max_count,
-                       const float *poses, int64_t pose_bs, const float *K, int64_t K_bs, const float *depth,
-                       int64_t d_bs, const float *rgb, int64_t rgb_bs, int B_total, int b0, int nb, int H, int W,
-                       float dist_th, float dot_th, double sigma, void *workspace, int32_t *overflow, cudaStream_t st) {
+// The two halves of one frame for the batch elements [b0, b0 + nb) of a B_total-element problem, on `st`: the frame
+// records (K1r), and the map update that consumes them (K2 + K4).  All pointers are the FULL-batch base pointers; batch
+// elements are independent, so disjoint groups may run concurrently on different streams, and the records of the next
+// frame may be computed (into another workspace) while this frame's update runs (gsx_pointfusion_sequence_gt).
+static Workspace group_workspace(void *workspace, int B_total, int b0, int H, int W) {
   const int64_t P = (int64_t)H * W;
   Workspace ws = carve(workspace, B_total, H, W);
   ws.frec += (int64_t)b0 * P * kRecW;
@@ -645,22 +643,35 @@ int fusion_frame_group(float *geo, float *col, const int32_t *cin, int32_t *cout
   ws.tile_state += (int64_t)b0 * ws.tiles;
   ws.ticket += b0;
   ws.stats += 2 * b0;
+  return ws;
+}
+
+int fusion_records_group(const float *poses, int64_t pose_bs, const float *K, int64_t K_bs, const float *depth,
+                         int64_t d_bs, int B_total, int b0, int nb, int H, int W, double sigma, void *workspace,
+                         cudaStream_t st) {
+  FrameRecArgs fa{depth + (int64_t)b0 * d_bs, d_bs, K + (int64_t)b0 * K_bs, K_bs, poses + (int64_t)b0 * pose_bs, pose_bs,
+                  nullptr, nullptr, nullptr, nb, H, W, (float)(2.0 * (sigma * sigma)),
+                  group_workspace(workspace, B_total, b0, H, W)};
+  return launch_frame_records(fa, st);
+}
+
+int fusion_update_group(float *geo, float *col, const int32_t *cin, int32_t *cout, int64_t cap, int64_t max_count,
+                        const float *poses, int64_t pose_bs, const float *K, int64_t K_bs, const float *rgb,
+                        int64_t rgb_bs, int B_total, int b0, int nb, int H, int W, float dist_th, float dot_th,
+                        void *workspace, int32_t *overflow, cudaStream_t st) {
+  const Workspace ws = group_workspace(workspace, B_total, b0, H, W);
   float *ggeo = geo + (int64_t)b0 * cap * kGeoW, *gcol = col + (int64_t)b0 * cap * kColW;
-  const float *gposes = poses + (int64_t)b0 * pose_bs, *gK = K + (int64_t)b0 * K_bs;
-  const float *gdepth = depth + (int64_t)b0 * d_bs, *grgb = rgb + (int64_t)b0 * rgb_bs;
-  FrameRecArgs fa{gdepth, d_bs, gK, K_bs, gposes, pose_bs, nullptr, nullptr, nullptr, nb, H, W,
-                  (float)(2.0 * (sigma * sigma)), ws};
-  int rc = launch_frame_records(fa, st);
-  if (rc) return rc;
   if (max_count > 0) {
-    ProjectArgs pa{ggeo, cin + b0, cap, gposes, pose_bs, gK, K_bs, nb, H, W, dot_th, (float)(W - 0.999),
-                   (float)(H - 0.999), sqrt_lt_threshold(dist_th), ws.frec, ws.best, ws.stats};
-    rc = launch_project_select(pa, max_count, st);
+    ProjectArgs pa{ggeo, cin + b0, cap, poses + (int64_t)b0 * pose_bs, pose_bs, K + (int64_t)b0 * K_bs, K_bs, nb, H, W,
+                   dot_th, (float)(W - 0.999), (float)(H - 0.999), sqrt_lt_threshold(dist_th), ws.frec, ws.best, ws.stats};
+    const int rc = launch_project_select(pa, max_count, st);
     if (rc) return rc;
   }
-  MergeArgs ma{ggeo, gcol, 1, cin + b0, cout + b0, cap, grgb, rgb_bs, nb, H, W, ws, overflow, nullptr};
+  MergeArgs ma{ggeo, gcol, 1, cin + b0, cout + b0, cap, rgb + (int64_t)b0 * rgb_bs, rgb_bs, nb, H, W, ws, overflow, nullptr};
   return launch_merge_append(ma, st);
 }
+
+int64_t fusion_workspace_bytes(int B, int H, int W) { return workspace_bytes(B, H, W); }
 
 }  // namespace gsx
 

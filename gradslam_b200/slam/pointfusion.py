@@ -12,10 +12,27 @@ import torch
 from .. import _C
 from ..structures.pointclouds import Pointclouds
 from ..structures.rgbdimages import RGBDImages
-from .fusionutils import _Workspace, update_map_fusion
+from .fusionutils import update_map_fusion
 from .icpslam import ICPSLAM
 
 __all__ = ["PointFusion"]
+
+
+class _SequenceWorkspace:
+    """Scratch of gsx_pointfusion_sequence_gt (two frame workspaces used alternately), per (device, stream, B, H, W)."""
+
+    _cache = {}
+
+    def __init__(self, device, B, H, W):
+        self.buf = torch.zeros(_C.lib().gsx_pointfusion_sequence_workspace_bytes(B, H, W), dtype=torch.uint8,
+                               device=device)
+
+    @classmethod
+    def get(cls, device, B, H, W):
+        key = (str(device), torch.cuda.current_stream(device).cuda_stream, B, H, W)
+        if key not in cls._cache:
+            cls._cache[key] = cls(device, B, H, W)
+        return cls._cache[key]
 
 
 class PointFusion(ICPSLAM):
@@ -98,7 +115,7 @@ class PointFusion(ICPSLAM):
             _C.require_cuda(t, name)
         pc = Pointclouds(device=dev)
         pc._allocate(B, L * P, 1, zero=False)
-        ws = _Workspace.get(dev, B, H, W)
+        ws = _SequenceWorkspace.get(dev, B, H, W)
         main = torch.cuda.current_stream(dev)
         with torch.cuda.device(dev):
             ready = []

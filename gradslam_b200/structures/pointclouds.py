@@ -552,6 +552,35 @@ class Pointclouds(object):
         other.device = device
         return other
 
+    def download(self, out: Optional["Pointclouds"] = None, stream=None) -> "Pointclouds":
+        """Asynchronous read-back of the populated rows into PINNED host memory: returns a CPU Pointclouds (same packed
+        layout) whose buffers are filled by device-to-host copies enqueued on `stream` (default: the current stream) -
+        synchronise that stream before touching the result.  Pass the previous result as `out` to re-use its pinned
+        buffers.  One host synchronisation (the map sizes) precedes the copies."""
+        if not self.has_points:
+            return Pointclouds()
+        counts = self._host_counts()
+        n = max(max(counts), 1)
+        if out is None or out._geo is None or out._geo.shape[1] < n or out._B != self._B:
+            cap = int(n * 1.05) + 1
+            out = Pointclouds()
+            out._B = self._B
+            pin = lambda st: None if st is None else torch.zeros((st.shape[0], cap, st.shape[2]), dtype=st.dtype,
+                                                                 pin_memory=True)
+            out._geo, out._col, out._feat = pin(self._geo), pin(self._col), pin(self._feat)
+        out._has_normals, out._has_cc = self._has_normals, self._has_cc
+        ctx = torch.cuda.stream(stream) if stream is not None else torch.cuda.device(self.device)
+        with ctx:
+            for dst, src in ((out._geo, self._geo), (out._col, self._col), (out._feat, self._feat)):
+                if src is None:
+                    continue
+                for b, c in enumerate(counts):
+                    if c > 0:
+                        dst[b, :c].copy_(src[b, :c], non_blocking=True)
+        out._set_counts(counts)
+        out._uninit, out._tail_dirty = True, True  # (rows of a previous, longer download may remain beyond counts[b])
+        return out
+
     def cpu(self):
         return self.to(torch.device("cpu"))
 

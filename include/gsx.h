@@ -146,6 +146,9 @@ int gsx_fusion_merge_append_bwd(const int32_t *assoc, const int32_t *counts_in, 
  * B (default 2, environment GSX_SEQ_GROUPS = 1..4 overrides; never more than B).  Kernel launches per call =
  * groups * (3 * frames - [map empty on entry]). */
 int gsx_pointfusion_sequence_groups(int B);
+/* workspace of the sequence driver: two frame workspaces used alternately (the records of frame s+1 are computed on a
+ * side stream while frame s is fused), 16-byte aligned, no initialisation needed */
+int64_t gsx_pointfusion_sequence_workspace_bytes(int B, int H, int W);
 int gsx_pointfusion_sequence_gt(float *map_geometry, float *map_colors, int32_t *counts, int64_t capacity,
                                 int64_t max_count0, const float *depth, const float *rgb, const float *intrinsics,
                                 const float *poses, int B, int L, int s_begin, int s_end, int H, int W, float dist_th,

@@ -132,7 +132,7 @@ def test_downsample_helpers_match_oracle():
     from gradslam_b200.odometry import icputils
     from gradslam_b200.slam import fusionutils as fu
 
-    gs_, fu_, (rgb, depth, K, poses), frames, pc, smap = _scenario(False)
+    gs_, fu_, (rgb, depth, K, poses), frames, pc, smap = _scenario()
     live = frames[:, 2]
     got = icputils.downsample_rgbdimages(live, 4)
     maps = oracle.frame_maps(depth[:, 2:3], K, poses[:, 2:3])
