@@ -193,6 +193,7 @@ __device__ __forceinline__ MapRow load_map_row(const float *geo, int64_t n) {
 __global__ void __launch_bounds__(kBlock, GSX_K2_MINB) k_project_select(ProjectArgs a) {
   __shared__ Rigid s_tinv;
   __shared__ float s_k[12];
+  __shared__ unsigned int s_act[kBlock / 32];
   const int b = blockIdx.y;
   const int count = a.counts[b];
   if ((int64_t)blockIdx.x * kBlock >= count) return;
@@ -258,9 +259,17 @@ __global__ void __launch_bounds__(kBlock, GSX_K2_MINB) k_project_select(ProjectA
     }
   }
   if (pend_pix >= 0) atomic_max_rec128_finish(best + pend_pix, mine, old);
-  // bookkeeping for the roofline's algorithmic-byte count: one atomic per warp
+  // bookkeeping for the roofline's algorithmic-byte count: ONE atomic per CTA (every warp of the grid adding to the same
+  // address serialises in the L2: 9472 same-address atomics cost ~20 us when the whole grid works on one map)
   n_active = __reduce_add_sync(0xffffffffu, n_active);
-  if ((threadIdx.x & 31) == 0 && n_active) atomicAdd(a.stats + 2 * b, (unsigned long long)n_active);
+  if ((threadIdx.x & 31) == 0) s_act[threadIdx.x >> 5] = n_active;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned int t = 0;
+#pragma unroll
+    for (int i = 0; i < kBlock / 32; ++i) t += s_act[i];
+    if (t) atomicAdd(a.stats + 2 * b, (unsigned long long)t);
+  }
 }
 
 #ifndef GSX_K2_CTAS_PER_SM
@@ -337,6 +346,7 @@ template <bool kAssoc>
 __global__ void __launch_bounds__(kMB, GSX_K4_MINB) k_merge_append(MergeArgs a) {
   __shared__ int s_tile;
   __shared__ int s_warp_sums[kPix][kMB / 32];
+  __shared__ int s_matched[kMB / 32];
   __shared__ int s_excl;
   __shared__ __align__(16) float s_rgb[kTilePix * 3];
   // batch element varies fastest in the grid: CTAs resident at the same time belong to different elements, so
@@ -394,8 +404,14 @@ __global__ void __launch_bounds__(kMB, GSX_K4_MINB) k_merge_append(MergeArgs a) 
     if (lane == 0) s_warp_sums[j][warp] = __popc(ballot);
   }
   n_matched = __reduce_add_sync(0xffffffffu, n_matched);
-  if (lane == 0 && n_matched) atomicAdd(a.ws.stats + 2 * b + 1, (unsigned long long)n_matched);
+  if (lane == 0) s_matched[warp] = n_matched;
   __syncthreads();
+  if (threadIdx.x == 0) {  // bookkeeping (merged rows of this element): one atomic per CTA
+    int t = 0;
+#pragma unroll
+    for (int i = 0; i < kMB / 32; ++i) t += s_matched[i];
+    if (t) atomicAdd(a.ws.stats + 2 * b + 1, (unsigned long long)t);
+  }
   int block_total = 0;
   int block_excl[kPix];
 #pragma unroll
