@@ -5,8 +5,10 @@
 Imports the reference from /root/reference through tests/golden/ref_loader.py (four in-memory shims, see
 there) and writes
 
-  tests/golden/msrd_b2s3.npz   the reference's own golden vectors for K1 (tests/data/msrd_b2s3/*.npy:
-                               depths, intrinsics, poses -> vertex / normal / global maps), re-packed losslessly
+  tests/golden/msrd_b2s3.npz   the reference's own test data and golden vectors (tests/data/msrd_b2s3/*.npy: colors,
+                               depths, intrinsics, poses -> vertex / normal / global maps), re-packed losslessly; the
+                               inputs of the reference's hot-path tests (tests/common.py load_test_data), which
+                               tests/test_gpu_reference_twins.py restates against this package on the GPU
   tests/golden/ref_slam.npz    reference outputs on seeded synthetic sequences (gradslam_b200.synthetic, the
                                bench's own input distribution: 2 % random depth holes): PointFusion / ICPSLAM
                                final maps + poses for odom in {gt, icp, gradicp}, the frame maps (K1) of one
@@ -70,7 +72,8 @@ def main():
     # ---- the reference's own golden vectors (K1) ---------------------------------------------------------
     d = os.path.join(REFERENCE_ROOT, "tests", "data", "msrd_b2s3")
     msrd = {k: np.load(os.path.join(d, k + ".npy")) for k in
-            ("depths", "intrinsics", "poses", "vertex_map", "normal_map", "global_vertex_map", "global_normal_map")}
+            ("colors", "depths", "intrinsics", "poses", "vertex_map", "normal_map", "global_vertex_map",
+             "global_normal_map")}
     np.savez_compressed(os.path.join(HERE, "msrd_b2s3.npz"), **msrd)
 
     out = {}
