@@ -423,8 +423,8 @@ def main():
                     "result": "poses + map sizes + the fused map of this rank (packed rows, exact sizes) into pinned "
                               "host memory, overlapped with the next step",
                     "timed_regions_ms": all_e2e},
-            # K1r + K2/K3 + K3c + K4 per frame and per concurrent batch group; K2 is skipped on the empty map
-            "gpu_launches": groups * (4 * L - 1) * args.steps, "sequence_groups": groups,
+            # K1r + K2/K3 + K4 per frame and per concurrent batch group; K2 is skipped on the empty map
+            "gpu_launches": groups * (3 * L - 1) * args.steps, "sequence_groups": groups,
             "repeats": repeats, "timed_regions_ms": all_dev,
             "roofline": roofline, "cpu_baseline": cpu_baseline, "clocks": clocks, "kernels": kernels,
             "icp_odometry": icp_extra, "e2e_raw_ingest": raw_extra, "config2_b1_l32": small_extra,

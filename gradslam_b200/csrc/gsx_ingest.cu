@@ -48,7 +48,98 @@ __global__ void __launch_bounds__(256) k_ingest_raw(const uint8_t *__restrict__ 
   }
 }
 
+// The rest of the loaders' output contract that is arithmetic rather than file parsing:
+//   * intrinsics of resized frames: fx, cx *= w_ratio; fy, cy *= h_ratio in float32 (datasets/datautils.py:73-122);
+//   * poses relative to the first frame of each sequence: T_s <- compose(inverse(T_0), T_s) (datasets/icl.py:515-533 =
+//     geometryutils.relative_transformation with orthogonal_rotations=False: a GENERAL 4x4 inverse of T_0, then kornia's
+//     compose_transformations on the rotation / translation blocks, bottom row forced to 0 0 0 1).
+// One thread per matrix.  The inverse is Gauss-Jordan with partial pivoting in float32 (the reference's torch.inverse is
+// LAPACK's LU: the results agree to float32 rounding, tests/test_gpu_ingest.py holds them to 1e-5).
+__global__ void __launch_bounds__(64) k_scale_intrinsics(const float *__restrict__ K, int64_t n, int dim, float h_ratio,
+                                                         float w_ratio, float *__restrict__ out) {
+  const int64_t i = (int64_t)blockIdx.x * 64 + threadIdx.x;
+  if (i >= n) return;
+  const int sz = dim * dim;
+  for (int e = 0; e < sz; ++e) out[i * sz + e] = K[i * sz + e];
+  out[i * sz + 0] = K[i * sz + 0] * w_ratio;              // fx
+  out[i * sz + dim + 1] = K[i * sz + dim + 1] * h_ratio;  // fy
+  out[i * sz + 2] = K[i * sz + 2] * w_ratio;              // cx
+  out[i * sz + dim + 2] = K[i * sz + dim + 2] * h_ratio;  // cy
+}
+
+__device__ inline bool invert4x4(const float *a, float *inv) {
+  float m[4][8];
+  for (int r = 0; r < 4; ++r)
+    for (int c = 0; c < 4; ++c) {
+      m[r][c] = a[r * 4 + c];
+      m[r][4 + c] = (r == c) ? 1.0f : 0.0f;
+    }
+  for (int col = 0; col < 4; ++col) {
+    int piv = col;
+    for (int r = col + 1; r < 4; ++r)
+      if (fabsf(m[r][col]) > fabsf(m[piv][col])) piv = r;
+    if (m[piv][col] == 0.0f) return false;
+    if (piv != col)
+      for (int c = 0; c < 8; ++c) {
+        const float t = m[col][c];
+        m[col][c] = m[piv][c];
+        m[piv][c] = t;
+      }
+    const float d = 1.0f / m[col][col];
+    for (int c = 0; c < 8; ++c) m[col][c] *= d;
+    for (int r = 0; r < 4; ++r)
+      if (r != col) {
+        const float f = m[r][col];
+        for (int c = 0; c < 8; ++c) m[r][c] -= f * m[col][c];
+      }
+  }
+  for (int r = 0; r < 4; ++r)
+    for (int c = 0; c < 4; ++c) inv[r * 4 + c] = m[r][4 + c];
+  return true;
+}
+
+__global__ void __launch_bounds__(64) k_poses_relative(const float *__restrict__ poses, int B, int L,
+                                                       float *__restrict__ out, int32_t *singular) {
+  const int i = blockIdx.x * 64 + threadIdx.x;
+  if (i >= B * L) return;
+  const int b = i / L;
+  float t0[16], inv[16];
+  for (int e = 0; e < 16; ++e) t0[e] = poses[(int64_t)b * L * 16 + e];
+  if (!invert4x4(t0, inv)) {
+    if (singular) *singular = 1;
+    for (int e = 0; e < 16; ++e) out[(int64_t)i * 16 + e] = nanf("");
+    return;
+  }
+  const float *t = poses + (int64_t)i * 16;
+  float *o = out + (int64_t)i * 16;
+  for (int r = 0; r < 3; ++r) {
+    for (int c = 0; c < 3; ++c)
+      o[r * 4 + c] = (inv[r * 4 + 0] * t[0 * 4 + c] + inv[r * 4 + 1] * t[1 * 4 + c]) + inv[r * 4 + 2] * t[2 * 4 + c];
+    o[r * 4 + 3] = ((inv[r * 4 + 0] * t[3] + inv[r * 4 + 1] * t[7]) + inv[r * 4 + 2] * t[11]) + inv[r * 4 + 3];
+  }
+  o[12] = o[13] = o[14] = 0.0f;
+  o[15] = 1.0f;
+}
+
 }  // namespace gsx
+
+extern "C" int gsx_ingest_calibration(const float *intrinsics, int64_t n_intrinsics, int intrinsics_dim, double h_ratio,
+                                      double w_ratio, float *intrinsics_out, const float *poses, int B, int L,
+                                      float *poses_out, int32_t *singular_flag, void *stream) {
+  cudaStream_t s = (cudaStream_t)stream;
+  if (intrinsics_out && n_intrinsics > 0) {
+    GSX_CHECK_ARG(intrinsics && (intrinsics_dim == 3 || intrinsics_dim == 4), "gsx_ingest_calibration: bad intrinsics");
+    gsx::k_scale_intrinsics<<<(unsigned)((n_intrinsics + 63) / 64), 64, 0, s>>>(intrinsics, n_intrinsics, intrinsics_dim,
+                                                                               (float)h_ratio, (float)w_ratio,
+                                                                               intrinsics_out);
+  }
+  if (poses_out && B > 0 && L > 0) {
+    GSX_CHECK_ARG(poses && poses != poses_out, "gsx_ingest_calibration: poses must be given and must not alias the output");
+    gsx::k_poses_relative<<<(unsigned)((B * L + 63) / 64), 64, 0, s>>>(poses, B, L, poses_out, singular_flag);
+  }
+  GSX_CHECK_LAUNCH("gsx_ingest_calibration");
+  return 0;
+}
 
 extern "C" int gsx_ingest_raw(const uint8_t *rgb_u8, const uint16_t *depth_u16, int64_t n_pixels,
                               double depth_scaling_factor, int normalize_color, float *rgb_out, float *depth_out,

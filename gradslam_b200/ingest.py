@@ -13,7 +13,7 @@ import torch
 from . import _C
 from .structures.rgbdimages import RGBDImages
 
-__all__ = ["scale_intrinsics", "raw_to_float", "rgbdimages_from_raw", "RawRGBD"]
+__all__ = ["scale_intrinsics", "relative_poses", "raw_to_float", "rgbdimages_from_raw", "RawRGBD"]
 
 
 def scale_intrinsics(intrinsics: torch.Tensor, h_ratio: Union[float, int], w_ratio: Union[float, int]) -> torch.Tensor:
@@ -23,11 +23,40 @@ def scale_intrinsics(intrinsics: torch.Tensor, h_ratio: Union[float, int], w_rat
     if not (intrinsics.shape[-2:] == (3, 3) or intrinsics.shape[-2:] == (4, 4)):
         raise ValueError("intrinsics must have shape (*, 3, 3) or (*, 4, 4), but had shape {} instead".format(
             intrinsics.shape))
+    if intrinsics.is_cuda:  # on the device, next to the raw-frame conversion (csrc/gsx_ingest.cu); same float32 products
+        K = intrinsics.to(torch.float).contiguous()
+        out = torch.empty_like(K)
+        n = K.numel() // (K.shape[-1] * K.shape[-1])
+        with torch.cuda.device(K.device):
+            rc = _C.lib().gsx_ingest_calibration(_C.ptr(K), n, K.shape[-1], float(h_ratio), float(w_ratio), _C.ptr(out),
+                                                 None, 0, 0, None, None, _C.stream_ptr(K.device))
+        _C.check(rc, "gsx_ingest_calibration")
+        return out
     out = intrinsics.to(torch.float).clone()
     out[..., 0, 0] *= w_ratio
     out[..., 1, 1] *= h_ratio
     out[..., 0, 2] *= w_ratio
     out[..., 1, 2] *= h_ratio
+    return out
+
+
+def relative_poses(poses: torch.Tensor) -> torch.Tensor:
+    """Poses (B, L, 4, 4) or (L, 4, 4) made relative to the first frame of each sequence, as the reference's loaders
+    deliver them (gradslam/datasets/icl.py:515-533: relative_transformation(T_0, T_s) with a general inverse of T_0).
+    Runs on the device (csrc/gsx_ingest.cu); CUDA float32 input."""
+    if not torch.is_tensor(poses):
+        raise TypeError("Input poses type is not a torch.Tensor. Got {}".format(type(poses)))
+    if poses.dim() not in (3, 4) or poses.shape[-2:] != (4, 4):
+        raise ValueError("poses must have shape (B, L, 4, 4) or (L, 4, 4). Got {}".format(tuple(poses.shape)))
+    _C.require_cuda(poses, "poses")
+    p = poses.contiguous()
+    B, L = (1, p.shape[0]) if p.dim() == 3 else p.shape[:2]
+    out = torch.empty_like(p)
+    flag = torch.zeros(1, dtype=torch.int32, device=p.device)
+    with torch.cuda.device(p.device):
+        rc = _C.lib().gsx_ingest_calibration(None, 0, 4, 1.0, 1.0, None, _C.ptr(p), B, L, _C.ptr(out), _C.ptr(flag),
+                                             _C.stream_ptr(p.device))
+    _C.check(rc, "gsx_ingest_calibration")
     return out
 
 
@@ -77,11 +106,21 @@ class RawRGBD(object):
 
 
 def rgbdimages_from_raw(colors_u8, depths_u16, intrinsics, poses=None, *, scaling_factor: float = 5000.0,
-                        normalize_color: bool = False, device: Union[torch.device, str] = "cuda") -> RGBDImages:
+                        normalize_color: bool = False, device: Union[torch.device, str] = "cuda",
+                        resized_from=None, relative_to_first: bool = False) -> RGBDImages:
     """Uploads raw frames (B,L,H,W,3) uint8 / (B,L,H,W) uint16 and returns the float32 RGBDImages the reference's loaders
-    would have produced (same bits), resident on `device`."""
+    would have produced (same bits), resident on `device`.  resized_from=(H_orig, W_orig): the frames were resized from
+    that size, so the intrinsics are scaled accordingly; relative_to_first: absolute poses (as stored on disk) are made
+    relative to the first frame of each sequence (both on the device, as the loaders do on the host)."""
     colors_u8, depths_u16 = _check_raw(colors_u8, depths_u16)
     dev = torch.device(device)
     rgb, depth = raw_to_float(colors_u8.to(dev, non_blocking=True), depths_u16.to(dev, non_blocking=True),
                               scaling_factor, normalize_color)
-    return RGBDImages(rgb, depth, intrinsics.to(dev), None if poses is None else poses.to(dev))
+    K = intrinsics.to(dev)
+    if resized_from is not None:
+        H, W = colors_u8.shape[-3], colors_u8.shape[-2]
+        K = scale_intrinsics(K, H / float(resized_from[0]), W / float(resized_from[1]))
+    P = None if poses is None else poses.to(dev)
+    if P is not None and relative_to_first:
+        P = relative_poses(P.to(torch.float32))
+    return RGBDImages(rgb, depth, K, P)

@@ -165,6 +165,17 @@ void gsx_debug_fail_at_frame(int s);
 int gsx_ingest_raw(const uint8_t *rgb_u8, const uint16_t *depth_u16, int64_t n_pixels, double depth_scaling_factor,
                    int normalize_color, float *rgb_out, float *depth_out, void *stream);
 
+/* The arithmetic part of the loaders' calibration contract, on the device (either half may be skipped with NULL outputs):
+ *   intrinsics_out[i] = intrinsics[i] with fx, cx scaled by w_ratio and fy, cy by h_ratio, in float32
+ *                       (gradslam/datasets/datautils.py:73-122 scale_intrinsics; n_intrinsics matrices of
+ *                       intrinsics_dim x intrinsics_dim, 3 or 4);
+ *   poses_out[b][l]   = compose(inverse(poses[b][0]), poses[b][l]) with the bottom row forced to 0 0 0 1
+ *                       (gradslam/datasets/icl.py:515-533 _preprocess_poses = geometryutils.relative_transformation with
+ *                       a general 4x4 inverse); *singular_flag (int32, may be NULL) is set to 1 if a first pose is singular. */
+int gsx_ingest_calibration(const float *intrinsics, int64_t n_intrinsics, int intrinsics_dim, double h_ratio,
+                           double w_ratio, float *intrinsics_out, const float *poses, int B, int L, float *poses_out,
+                           int32_t *singular_flag, void *stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Table-returning association steps (API parity with gradslam's module-level helpers; the fused path
  * above never materialises these tables).  Tables are int64 (rows,4) with rows [b, n, h, w].

@@ -150,6 +150,39 @@ def main():
     print("icp err", (T_icp @ T_true - torch.eye(4)).abs().max().item(),
           (T_grad @ T_true - torch.eye(4)).abs().max().item())
 
+    # ---- loader calibration contract (datasets/datautils.py:73 scale_intrinsics; icl.py:515-533 _preprocess_poses) ------
+    import importlib.util
+
+    # (gradslam.datasets imports imageio / cv2, which are not installed: load the one module the contract lives in)
+    spec = importlib.util.spec_from_file_location("ref_datautils",
+                                                  os.path.join(REFERENCE_ROOT, "gradslam", "datasets", "datautils.py"))
+    ref_datautils = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ref_datautils)
+    scale_intrinsics = ref_datautils.scale_intrinsics
+    from gradslam.geometry.geometryutils import relative_transformation
+
+    g = torch.Generator().manual_seed(7)
+    K_in = torch.eye(4).repeat(3, 1, 1)
+    K_in[:, 0, 0] = 481.2 + torch.rand(3, generator=g)
+    K_in[:, 1, 1] = -480.0 + torch.rand(3, generator=g)
+    K_in[:, 0, 2] = 319.5
+    K_in[:, 1, 2] = 239.5
+    out["f2/K_in"] = K_in.numpy()
+    out["f2/ratios"] = np.array([120.0 / 480.0, 160.0 / 640.0])
+    out["f2/K_scaled"] = scale_intrinsics(K_in, 120.0 / 480.0, 160.0 / 640.0).numpy()
+    out["f2/K3_scaled"] = scale_intrinsics(K_in[:, :3, :3].contiguous(), 0.5, 0.75).numpy()
+    Bp, Lp = 2, 5
+    poses_abs = torch.eye(4).repeat(Bp, Lp, 1, 1)
+    for b in range(Bp):
+        for l in range(Lp):
+            xi = torch.randn(6, generator=g) * torch.tensor([0.5, 0.5, 0.5, 0.8, 0.8, 0.8])
+            poses_abs[b, l] = se3_exp(xi)
+    poses_abs[:, :, :3, :3] += 1e-3 * torch.randn(Bp, Lp, 3, 3, generator=g)  # (loader poses are not exactly orthogonal)
+    out["f2/poses_abs"] = poses_abs.numpy()
+    out["f2/poses_rel"] = torch.stack([
+        relative_transformation(poses_abs[b, 0].unsqueeze(0).repeat(Lp, 1, 1), poses_abs[b], orthogonal_rotations=False)
+        for b in range(Bp)]).numpy()
+
     np.savez_compressed(os.path.join(HERE, "ref_slam.npz"), **out)
     for f in ("msrd_b2s3.npz", "ref_slam.npz"):
         print(f, os.path.getsize(os.path.join(HERE, f)) // 1024, "KiB")

@@ -55,3 +55,31 @@ def test_pointfusion_on_raw_input_equals_float_input():
         gs.PointFusion(odom="gradicp", device=DEV)(raw)
     with pytest.raises(TypeError):
         ingest.RawRGBD(torch.zeros(1, 1, 4, 4, 3), torch.zeros(1, 1, 4, 4, dtype=torch.int16), K, poses)
+
+
+def test_calibration_contract_matches_frozen_reference():
+    """scale_intrinsics (datasets/datautils.py:73-122) and frame-0-relative poses (datasets/icl.py:515-533) on the device
+    against values frozen from the reference (tests/golden/make_golden.py, `f2/*`): the intrinsics are float32 products
+    and must be bit-identical; the relative poses go through a general 4x4 inverse (LAPACK LU in the reference,
+    Gauss-Jordan here) and are held to 1e-5."""
+    import os
+
+    import numpy as np
+
+    from gradslam_b200 import ingest
+
+    ref = np.load(os.path.join(os.path.dirname(__file__), "golden", "ref_slam.npz"))
+    K = torch.from_numpy(ref["f2/K_in"]).to(DEV)
+    hr, wr = (float(x) for x in ref["f2/ratios"])
+    assert torch.equal(ingest.scale_intrinsics(K, hr, wr).cpu(), torch.from_numpy(ref["f2/K_scaled"]))
+    assert torch.equal(ingest.scale_intrinsics(K[:, :3, :3].contiguous(), 0.5, 0.75).cpu(),
+                       torch.from_numpy(ref["f2/K3_scaled"]))
+    # the host mirror gives the same bits
+    assert torch.equal(ingest.scale_intrinsics(K.cpu(), hr, wr), torch.from_numpy(ref["f2/K_scaled"]))
+    poses = torch.from_numpy(ref["f2/poses_abs"]).to(DEV)
+    rel = ingest.relative_poses(poses)
+    torch.testing.assert_close(rel.cpu(), torch.from_numpy(ref["f2/poses_rel"]), rtol=1e-5, atol=1e-5)
+    assert torch.equal(rel[:, 0, 3].cpu(), torch.tensor([[0.0, 0.0, 0.0, 1.0]] * 2))
+    torch.testing.assert_close(rel[:, 0].cpu(), torch.eye(4).repeat(2, 1, 1), rtol=0, atol=1e-5)
+    torch.testing.assert_close(ingest.relative_poses(poses[0]).cpu(), torch.from_numpy(ref["f2/poses_rel"][0]),
+                               rtol=1e-5, atol=1e-5)
