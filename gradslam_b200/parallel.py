@@ -102,10 +102,11 @@ def gather_maps_end(h: "_GatherHandle", wait: bool = True) -> Pointclouds:
 
         ctx = contextlib.nullcontext()
     with ctx:
-        # zero-filled so that rows >= counts stay zero (the padding contract of the *_padded views); the fill is a
-        # memset on the communication stream, not a kernel competing with the next step's fusion
+        # not zero-filled (that would be a multi-GB memset per step at 8 GPUs): the zero padding the *_padded views
+        # promise is restored lazily, only for the ragged tails and only if such a view is asked for (Pointclouds._padded)
         out._alloc_buffers(nmax, pc._has_normals, pc._col is not None,
-                           pc.num_features if pc.has_features else 0)
+                           pc.num_features if pc.has_features else 0, zero=False)
+        out._uninit = True
         ops, keep = [], []
         for src, dst in ((pc._geo, out._geo), (pc._col, out._col), (pc._feat, out._feat)):
             if src is None:
