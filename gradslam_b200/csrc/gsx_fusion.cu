@@ -11,6 +11,8 @@
 // Map rows are sector-packed: geometry rows (px,py,pz,nx,ny,nz,ccount,0) of exactly one 32-byte
 // sector, colour rows (r,g,b,0) of 16 bytes; every row access is a 128-bit load / store.
 // Reference op chains: gradslam/slam/fusionutils.py:198-722 (see include/gsx.h).
+#include <cuda.h>  // CUtensorMap (the encoder is fetched with cudaGetDriverEntryPoint: no link against libcuda)
+
 #include "gsx_common.cuh"
 #include "gsx_exp.cuh"
 #include "gsx_thresholds.h"
@@ -140,10 +142,122 @@ __global__ void __launch_bounds__(kRecTW *kRecTH) k_frame_records(FrameRecArgs a
   a.ws.best[(int64_t)b * P + pix] = U128{0ull, 0ull};
 }
 
+// The same kernel with the depth tile staged by the TMA unit: the frame is a regular grid, so the (32 + halo) x (8 + halo)
+// depth tile a CTA needs (each pixel reads its right and lower neighbour) is ONE 3-D tensor-map box {36, 9, 1} of the
+// (W, H, element) depth tensor, copied into shared memory by cp.async.bulk.tensor (SASS: UTMALDG) and signalled on an
+// mbarrier, while the CTA fetches its constants.  Elements of the box beyond the image are zero-filled by the unit; they
+// are never used (edge pixels take the difference of the previous column / row, which lies inside the box).  The arithmetic
+// is frame_sample_from(): bit-identical to frame_sample<true>() of the plain kernel.
+constexpr int kRecBoxW = kRecTW + 4, kRecBoxH = kRecTH + 1;  // box width: 36 floats = 144 bytes (a multiple of 16)
+
+__device__ __forceinline__ unsigned int smem_u32(const void *p) { return (unsigned int)__cvta_generic_to_shared(p); }
+
+__global__ void __launch_bounds__(kRecTW *kRecTH) k_frame_records_tma(const __grid_constant__ CUtensorMap tmap,
+                                                                       FrameRecArgs a) {
+  __shared__ __align__(128) float s_d[kRecBoxH][kRecBoxW];
+  __shared__ __align__(8) unsigned long long s_bar;
+  __shared__ Rigid s_pose;
+  __shared__ KInv s_k;
+  const int b = blockIdx.z;
+  const int tid = threadIdx.y * kRecTW + threadIdx.x;
+  const int w0 = blockIdx.x * kRecTW, h0 = blockIdx.y * kRecTH;
+  if (tid == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&s_bar)));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (tid == 0) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&s_bar)),
+                 "r"((unsigned int)(kRecBoxH * kRecBoxW * 4))
+                 : "memory");
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(
+            smem_u32(&s_d[0][0])),
+        "l"(&tmap), "r"(smem_u32(&s_bar)), "r"(w0), "r"(h0), "r"(b)
+        : "memory");
+  }
+  // constants and the scan state of the frame's K4 while the tile is in flight
+  if (tid == 32) s_k = load_kinv(a.K + b * a.K_bstride);
+  if (tid == 64 && a.poses) s_pose = load_rigid(a.poses + b * a.pose_bstride);
+  const int lin = (blockIdx.y * gridDim.x + blockIdx.x) * (kRecTW * kRecTH) + tid;
+  if (lin < a.ws.tiles) a.ws.tile_state[(int64_t)b * a.ws.tiles + lin] = 0ull;
+  if (lin == 0) a.ws.ticket[b] = 0u;
+  __syncthreads();
+  {  // wait for the tile (phase 0 of the barrier)
+    unsigned int done = 0;
+    while (!done)
+      asm volatile(
+          "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+          : "=r"(done)
+          : "r"(smem_u32(&s_bar))
+          : "memory");
+  }
+  const int w = w0 + threadIdx.x, h = h0 + threadIdx.y;
+  if (w >= a.W || h >= a.H) return;
+  const int P = a.H * a.W;
+  const int pix = h * a.W + w;
+  const int wa = (w < a.W - 1) ? w : w - 1, ha = (h < a.H - 1) ? h : h - 1;
+  DepthStencil t;
+  t.c = s_d[threadIdx.y][threadIdx.x];
+  t.l = s_d[threadIdx.y][wa - w0];
+  t.r = s_d[threadIdx.y][wa - w0 + 1];
+  t.u = s_d[ha - h0][threadIdx.x];
+  t.d = s_d[ha - h0 + 1][threadIdx.x];
+  const FrameSample f = frame_sample_from(t, s_k, a.poses ? &s_pose : nullptr, h, w, a.H, a.W);
+  // alpha from the LOCAL vertex (fusionutils.py:657, 69-72)
+  const float s = (f.v.x * f.v.x + f.v.y * f.v.y) + f.v.z * f.v.z;
+  float4 *rec = reinterpret_cast<float4 *>(a.ws.frec + ((int64_t)b * P + pix) * kRecW);
+  rec[0] = make_float4(f.gv.x, f.gv.y, f.gv.z, f.gn.x);
+  rec[1] = make_float4(f.gn.y, f.gn.z, confidence_alpha(s, a.two_sigma_sq), f.d);
+  a.ws.best[(int64_t)b * P + pix] = U128{0ull, 0ull};
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn tensor_map_encoder() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void *p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+    cudaGetLastError();  // (a failed query must not poison the next launch check)
+  }
+  return fn;
+}
+
+// depth (nb, H, W) with element stride depth_bstride as a 3-D tensor map; false if the layout does not qualify
+static bool depth_tensor_map(const FrameRecArgs &a, CUtensorMap *tm) {
+  if (getenv("GSX_NO_TMA")) return false;
+  const EncodeTiledFn enc = tensor_map_encoder();
+  if (!enc) return false;
+  // strides must be multiples of 16 bytes, the base 16-byte aligned; a last column / row that starts a tile of its own
+  // would need a halo on the other side
+  if (a.W % 4 || a.depth_bstride % 4 || (reinterpret_cast<uintptr_t>(a.depth) & 15)) return false;
+  if ((a.W - 1) % kRecTW == 0 || (a.H - 1) % kRecTH == 0 || a.W < 2 || a.H < 2) return false;
+  const cuuint64_t dims[3] = {(cuuint64_t)a.W, (cuuint64_t)a.H, (cuuint64_t)a.B};
+  const cuuint64_t strides[2] = {(cuuint64_t)a.W * 4, (cuuint64_t)a.depth_bstride * 4};
+  const cuuint32_t box[3] = {(cuuint32_t)kRecBoxW, (cuuint32_t)kRecBoxH, 1};
+  const cuuint32_t estr[3] = {1, 1, 1};
+  return enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float *>(a.depth), dims, strides, box, estr,
+             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 int launch_frame_records(const FrameRecArgs &a, cudaStream_t stream) {
   if (a.B == 0) return 0;
   const dim3 grid((unsigned)((a.W + kRecTW - 1) / kRecTW), (unsigned)((a.H + kRecTH - 1) / kRecTH), (unsigned)a.B);
   const dim3 block(kRecTW, kRecTH);
+  CUtensorMap tm;
+  if (!a.gv && depth_tensor_map(a, &tm)) {
+    k_frame_records_tma<<<grid, block, 0, stream>>>(tm, a);
+    GSX_CHECK_LAUNCH("gsx_fusion_frame_records(tma)");
+    return 0;
+  }
   if (a.gv)
     k_frame_records<true><<<grid, block, 0, stream>>>(a);
   else
