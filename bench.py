@@ -364,10 +364,15 @@ def main():
             roofline["traffic"] = json.load(open(tpath)).get(dom)
 
     # secondary measurement: the same PointFusion with its default ICP odometry (gradLM, 20 iterations, dsratio 4),
-    # on a corner-facing variant of the scene (yaw0=0.6) where point-to-plane ICP is well conditioned
+    # on a corner-facing variant of the scene (yaw0=0.6) where point-to-plane ICP is well conditioned; plus the
+    # localisation call alone (K5 exact 1-NN + K6 rows / normal equations + K7 solve, 2 searches per iteration) with its
+    # work in SURVEY.md §8(d)'s units and the CPU port of the same call beside it
     icp_extra = None
     if rank == 0 and not args.no_icp:
-        Li = 8
+        from gradslam_b200.odometry.icputils import downsample_pointclouds, localize_against_map
+        from gradslam_b200.slam.fusionutils import find_active_map_points
+
+        Li, ds, iters = 8, 4, 20
         r2, d2, K2, p2 = make_sequence(B, Li, H, W, seed=100 + rank, yaw0=0.6)
         fr2 = gs.RGBDImages(r2.to(dev), d2.to(dev), K2.to(dev), p2.to(dev))
         slam2 = gs.PointFusion(odom="gradicp", device=dev)
@@ -383,6 +388,52 @@ def main():
         icp_extra = {"workload": "PointFusion(odom='gradicp', numiters=20, dsratio=4) %dx%d B=%d L=%d, 1 GPU" % (W, H, B, Li),
                      "frames_per_s": B * Li / ms * 1e3, "ms_per_step": ms,
                      "max_abs_pose_error_vs_gt": float((rec.cpu() - p2).abs().max())}
+        # the localisation of the last frame against the map of the first Li-1 frames, alone
+        slam_gt = gs.PointFusion(odom="gt", device=dev)
+        pc_map, _ = slam_gt(fr2[:, : Li - 1])
+        live, prev = fr2[:, Li - 1], fr2[:, Li - 2]
+        live.poses = prev.poses
+        localize_against_map(pc_map, live, prev, ds, slam2.odomprov)
+        torch.cuda.synchronize(dev)
+        e0.record()
+        for _ in range(5):
+            pose_dev = localize_against_map(pc_map, live, prev, ds, slam2.odomprov)
+        e1.record()
+        torch.cuda.synchronize(dev)
+        ms_loc = e0.elapsed_time(e1) / 5
+        ns = (d2[:, Li - 1, ::ds, ::ds, 0] > 0).flatten(1).sum(1).tolist()
+        tgt = downsample_pointclouds(pc_map, find_active_map_points(pc_map, prev), ds)
+        nt = [int(c) for c in tgt.num_points_per_pointcloud.tolist()]
+        searches = 2 * iters
+        flop = sum(a * b for a, b in zip(ns, nt)) * 8.0 * searches  # brute-force-equivalent pair evaluations
+        k6_bytes = sum(ns) * 36.0 * searches
+        icp_extra["localize"] = {
+            "ms_per_call": ms_loc, "source_points": ns, "target_points": nt, "searches_per_call": searches,
+            "K5_brute_force_equivalent_TFLOP_per_s": flop / (ms_loc * 1e-3) / 1e12,
+            "K5_note": "SURVEY 8(d) unit: Ns*Nt pairs x 8 flop per search over the WHOLE call time (K5+K6+K7 and the two "
+                       "gathers); targets > 4096 points are searched through an exact uniform grid (~1e2 distance "
+                       "evaluations per query), so this is work AVOIDED, not FP32 throughput",
+            "K6_algorithmic_GB_per_s": k6_bytes / (ms_loc * 1e-3) / 1e9,
+            "K6_note": "36 B per source point per search (SURVEY 8(d)) over the whole call time: a lower bound",
+        }
+        if not args.no_cpu_baseline:
+            sys.path.insert(0, os.path.join(ROOT, "oracle"))
+            import gsx_oracle as oracle
+
+            torch.set_num_threads(best_thread_count(H, W))
+            ref_run = oracle.run_slam(r2[:1, : Li - 1], d2[:1, : Li - 1], K2[:1], p2[:1, : Li - 1], odom="gt")
+            at_prev = oracle.frame_maps(d2[:1, Li - 1: Li], K2[:1], p2[:1, Li - 2: Li - 1])
+            t0 = time.perf_counter()
+            pose_cpu = oracle.odometry(ref_run.map, at_prev, p2[:1, Li - 2], K2[:1, 0], H, W, "gradicp", ds,
+                                       dict(numiters=iters, damp=1e-8, dist_thresh=None, lambda_max=2.0, B=1.0, B2=1.0,
+                                            nu=200.0))
+            dt = time.perf_counter() - t0
+            icp_extra["localize"]["cpu_port"] = {
+                "seconds_per_call_B1": dt, "cores": os.cpu_count(),
+                "kind": "oracle.odometry: torch-CPU restatement of ICPSLAM._localize with the brute-force KNN "
+                        "restatement (oracle/knn1.c, OpenMP on all cores) in place of chamferdist",
+                "gpu_over_cpu_per_sequence": dt / (ms_loc * 1e-3 / B),
+                "max_abs_pose_diff_vs_cuda": float((pose_cpu[0] - pose_dev[0, 0].cpu()).abs().max())}
 
     # BASELINE.json configs[1]: one sequence (B=1), L=32, forward only - the launch-latency-bound end of the path
     small_extra = None

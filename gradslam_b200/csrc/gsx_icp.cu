@@ -594,10 +594,18 @@ __global__ void __launch_bounds__(kIcpBlock) k_icp_knn_linearize(KnnArgs a) {
 // ---------------------------------------------------------------------------------------------------------
 // normal equations for a GIVEN association (the differentiable op of the taped ICP): forward + backward
 // ---------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kIcpBlock) k_icp_linearize_idx(const float *src, int ns, const float *tp,
-                                                                 const float *tn, const int64_t *idx,
-                                                                 float *partials) {
+// (batched: element b = blockIdx.y lives at b * ns_stride / b * nt_stride rows; counts may be null = ns_stride rows each)
+__global__ void __launch_bounds__(kIcpBlock) k_icp_linearize_idx(const float *src, int ns_stride, const int32_t *counts,
+                                                                 const float *tp, const float *tn, int nt_stride,
+                                                                 const int64_t *idx, float *partials) {
   __shared__ float s_red[kIcpBlock / 32][kNumSums];
+  const int b = blockIdx.y;
+  const int ns = counts ? counts[b] : ns_stride;
+  src += (int64_t)b * ns_stride * 3;
+  tp += (int64_t)b * nt_stride * 3;
+  tn += (int64_t)b * nt_stride * 3;
+  idx += (int64_t)b * ns_stride;
+  partials += (int64_t)b * gridDim.x * kNumSums;
   const int i = blockIdx.x * kIcpBlock + threadIdx.x;
   float acc[kNumSums];
 #pragma unroll
@@ -610,6 +618,8 @@ __global__ void __launch_bounds__(kIcpBlock) k_icp_linearize_idx(const float *sr
 }
 
 __global__ void k_icp_reduce_partials(const float *partials, int nblocks, float *sums) {
+  partials += (int64_t)blockIdx.x * nblocks * kNumSums;  // (one block per batch element)
+  sums += (int64_t)blockIdx.x * kNumSums;
   if (threadIdx.x < kNumSums) {
     float v = 0.0f;
     for (int j = 0; j < nblocks; ++j) v += partials[(int64_t)j * kNumSums + threadIdx.x];
@@ -620,14 +630,30 @@ __global__ void k_icp_reduce_partials(const float *partials, int nblocks, float 
 // d(loss)/d(source point), d/d(associated target point), d/d(associated target normal) from d(loss)/d(28 sums).
 // One thread per source point; the target gradients are written per SOURCE row (the caller scatters them with the
 // association), so there are no atomics.
-__global__ void __launch_bounds__(kIcpBlock) k_icp_linearize_bwd(const float *src, int ns, const float *tp,
-                                                                 const float *tn, const int64_t *idx, const float *g,
-                                                                 float *g_src, float *g_tp, float *g_tn) {
+__global__ void __launch_bounds__(kIcpBlock) k_icp_linearize_bwd(const float *src, int ns_stride, const int32_t *counts,
+                                                                 const float *tp, const float *tn, int nt_stride,
+                                                                 const int64_t *idx, const float *g, float *g_src,
+                                                                 float *g_tp, float *g_tn) {
   __shared__ float s_g[kNumSums];
+  const int b = blockIdx.y;
+  const int ns = counts ? counts[b] : ns_stride;
+  src += (int64_t)b * ns_stride * 3;
+  tp += (int64_t)b * nt_stride * 3;
+  tn += (int64_t)b * nt_stride * 3;
+  idx += (int64_t)b * ns_stride;
+  g += (int64_t)b * kNumSums;
+  g_src += (int64_t)b * ns_stride * 3;
+  g_tp += (int64_t)b * ns_stride * 3;
+  g_tn += (int64_t)b * ns_stride * 3;
   if (threadIdx.x < kNumSums) s_g[threadIdx.x] = g[threadIdx.x];
   __syncthreads();
   const int i = blockIdx.x * kIcpBlock + threadIdx.x;
-  if (i >= ns) return;
+  if (i >= ns_stride) return;
+  if (i >= ns) {  // padding rows of a batched call: zero gradients
+#pragma unroll
+    for (int c = 0; c < 3; ++c) g_src[(int64_t)i * 3 + c] = g_tp[(int64_t)i * 3 + c] = g_tn[(int64_t)i * 3 + c] = 0.0f;
+    return;
+  }
   float gs[3] = {0.f, 0.f, 0.f}, gp[3] = {0.f, 0.f, 0.f}, gn[3] = {0.f, 0.f, 0.f};
   const int64_t j = idx[i];
   if (j >= 0) {
@@ -1106,6 +1132,41 @@ extern "C" int64_t gsx_icp_normal_eq_scratch_bytes(int ns) {
   return (int64_t)((ns + kIcpBlock - 1) / kIcpBlock) * kNumSums * 4;
 }
 
+extern "C" int gsx_icp_normal_eq_batched_fwd(const float *src_points, const int32_t *src_count, int ns_stride,
+                                             const float *tgt_points, const float *tgt_normals, int nt_stride, int B,
+                                             const int64_t *nn_idx, float *sums_out, void *scratch, int64_t scratch_bytes,
+                                             void *stream) {
+  GSX_CHECK_ARG(src_points && tgt_points && tgt_normals && nn_idx && sums_out && scratch,
+                "gsx_icp_normal_eq_batched_fwd: null pointer");
+  GSX_CHECK_ARG(B >= 1 && ns_stride >= 1 && nt_stride >= 1 &&
+                    scratch_bytes >= (int64_t)B * gsx_icp_normal_eq_scratch_bytes(ns_stride),
+                "gsx_icp_normal_eq_batched_fwd: bad sizes");
+  const int nblk = (ns_stride + kIcpBlock - 1) / kIcpBlock;
+  cudaStream_t s = (cudaStream_t)stream;
+  k_icp_linearize_idx<<<dim3((unsigned)nblk, (unsigned)B), kIcpBlock, 0, s>>>(src_points, ns_stride, src_count, tgt_points,
+                                                                            tgt_normals, nt_stride, nn_idx,
+                                                                            (float *)scratch);
+  k_icp_reduce_partials<<<B, 32, 0, s>>>((const float *)scratch, nblk, sums_out);
+  GSX_CHECK_LAUNCH("gsx_icp_normal_eq_batched_fwd");
+  return 0;
+}
+
+extern "C" int gsx_icp_normal_eq_batched_bwd(const float *src_points, const int32_t *src_count, int ns_stride,
+                                             const float *tgt_points, const float *tgt_normals, int nt_stride, int B,
+                                             const int64_t *nn_idx, const float *g_sums, float *g_src,
+                                             float *g_tgt_points_rows, float *g_tgt_normals_rows, void *stream) {
+  GSX_CHECK_ARG(src_points && tgt_points && tgt_normals && nn_idx && g_sums && g_src && g_tgt_points_rows &&
+                    g_tgt_normals_rows,
+                "gsx_icp_normal_eq_batched_bwd: null pointer");
+  GSX_CHECK_ARG(B >= 1 && ns_stride >= 1 && nt_stride >= 1, "gsx_icp_normal_eq_batched_bwd: bad sizes");
+  const int nblk = (ns_stride + kIcpBlock - 1) / kIcpBlock;
+  k_icp_linearize_bwd<<<dim3((unsigned)nblk, (unsigned)B), kIcpBlock, 0, (cudaStream_t)stream>>>(
+      src_points, ns_stride, src_count, tgt_points, tgt_normals, nt_stride, nn_idx, g_sums, g_src, g_tgt_points_rows,
+      g_tgt_normals_rows);
+  GSX_CHECK_LAUNCH("gsx_icp_normal_eq_batched_bwd");
+  return 0;
+}
+
 extern "C" int gsx_icp_normal_eq_fwd(const float *src_points, int ns, const float *tgt_points,
                                      const float *tgt_normals, const int64_t *nn_idx, float *sums_out, void *scratch,
                                      int64_t scratch_bytes, void *stream) {
@@ -1114,7 +1175,8 @@ extern "C" int gsx_icp_normal_eq_fwd(const float *src_points, int ns, const floa
   GSX_CHECK_ARG(ns >= 1 && scratch_bytes >= gsx_icp_normal_eq_scratch_bytes(ns), "gsx_icp_normal_eq_fwd: bad sizes");
   const int nblk = (ns + kIcpBlock - 1) / kIcpBlock;
   cudaStream_t s = (cudaStream_t)stream;
-  k_icp_linearize_idx<<<nblk, kIcpBlock, 0, s>>>(src_points, ns, tgt_points, tgt_normals, nn_idx, (float *)scratch);
+  k_icp_linearize_idx<<<nblk, kIcpBlock, 0, s>>>(src_points, ns, nullptr, tgt_points, tgt_normals, 0, nn_idx,
+                                                 (float *)scratch);
   k_icp_reduce_partials<<<1, 32, 0, s>>>((const float *)scratch, nblk, sums_out);
   GSX_CHECK_LAUNCH("gsx_icp_normal_eq_fwd");
   return 0;
@@ -1129,8 +1191,8 @@ extern "C" int gsx_icp_normal_eq_bwd(const float *src_points, int ns, const floa
                 "gsx_icp_normal_eq_bwd: null pointer");
   GSX_CHECK_ARG(ns >= 1, "gsx_icp_normal_eq_bwd: bad sizes");
   const int nblk = (ns + kIcpBlock - 1) / kIcpBlock;
-  k_icp_linearize_bwd<<<nblk, kIcpBlock, 0, (cudaStream_t)stream>>>(src_points, ns, tgt_points, tgt_normals, nn_idx,
-                                                                    g_sums, g_src, g_tgt_points_rows,
+  k_icp_linearize_bwd<<<nblk, kIcpBlock, 0, (cudaStream_t)stream>>>(src_points, ns, nullptr, tgt_points, tgt_normals, 0,
+                                                                    nn_idx, g_sums, g_src, g_tgt_points_rows,
                                                                     g_tgt_normals_rows);
   GSX_CHECK_LAUNCH("gsx_icp_normal_eq_bwd");
   return 0;

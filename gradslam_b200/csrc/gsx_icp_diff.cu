@@ -94,12 +94,23 @@ __global__ void __launch_bounds__(32) k_update_bwd(const float *xi, const float 
 
 // ---- rigid transform of a cloud: out = R p + t (geometryutils.py:737-794), canonical left-to-right sums ------------
 constexpr int kRtBlock = 256;
-__global__ void __launch_bounds__(kRtBlock) k_rigid_fwd(const float *src, int64_t n, const float *T, float *out) {
+// (batched: element b = blockIdx.y owns `stride` rows and T + 16 b; counts may be null = `stride` rows each.  Padding rows
+//  of a batched call are written as zeros, so the padded cloud stays a valid zero-padded tensor.)
+__global__ void __launch_bounds__(kRtBlock) k_rigid_fwd(const float *src, int64_t stride, const int32_t *counts,
+                                                        const float *T, float *out) {
   __shared__ Rigid s_T;
-  if (threadIdx.x == 0) s_T = load_rigid(T);
+  const int b = blockIdx.y;
+  const int64_t n = counts ? counts[b] : stride;
+  src += (int64_t)b * stride * 3;
+  out += (int64_t)b * stride * 3;
+  if (threadIdx.x == 0) s_T = load_rigid(T + b * 16);
   __syncthreads();
   const int64_t i = (int64_t)blockIdx.x * kRtBlock + threadIdx.x;
-  if (i >= n) return;
+  if (i >= stride) return;
+  if (i >= n) {
+    out[i * 3] = out[i * 3 + 1] = out[i * 3 + 2] = 0.0f;
+    return;
+  }
   const float3 q = rigid_apply(s_T, src[i * 3], src[i * 3 + 1], src[i * 3 + 2]);
   out[i * 3] = q.x;
   out[i * 3 + 1] = q.y;
@@ -107,13 +118,21 @@ __global__ void __launch_bounds__(kRtBlock) k_rigid_fwd(const float *src, int64_
 }
 
 // g_src = R^T g; per-block partial sums of g (x) [p; 1] (12 numbers) in a fixed order, reduced by k_rigid_bwd_reduce
-__global__ void __launch_bounds__(kRtBlock) k_rigid_bwd(const float *src, int64_t n, const float *T, const float *g_out,
-                                                        float *g_src, float *partials) {
+__global__ void __launch_bounds__(kRtBlock) k_rigid_bwd(const float *src, int64_t stride, const int32_t *counts,
+                                                        const float *T, const float *g_out, float *g_src,
+                                                        float *partials) {
   __shared__ Rigid s_T;
   __shared__ float s_red[kRtBlock / 32][12];
-  if (threadIdx.x == 0) s_T = load_rigid(T);
+  const int b = blockIdx.y;
+  const int64_t n = counts ? counts[b] : stride;
+  src += (int64_t)b * stride * 3;
+  g_out += (int64_t)b * stride * 3;
+  g_src += (int64_t)b * stride * 3;
+  partials += (int64_t)b * gridDim.x * 12;
+  if (threadIdx.x == 0) s_T = load_rigid(T + b * 16);
   __syncthreads();
   const int64_t i = (int64_t)blockIdx.x * kRtBlock + threadIdx.x;
+  if (i >= n && i < stride) g_src[i * 3] = g_src[i * 3 + 1] = g_src[i * 3 + 2] = 0.0f;
   float acc[12];
 #pragma unroll
   for (int k = 0; k < 12; ++k) acc[k] = 0.0f;
@@ -154,6 +173,8 @@ __global__ void __launch_bounds__(kRtBlock) k_rigid_bwd(const float *src, int64_
 }
 
 __global__ void k_rigid_bwd_reduce(const float *partials, int nblocks, float *g_T) {
+  partials += (int64_t)blockIdx.x * nblocks * 12;  // (one block per batch element)
+  g_T += (int64_t)blockIdx.x * 16;
   const int k = threadIdx.x;
   if (k < 12) {
     float v = 0.0f;
@@ -227,8 +248,34 @@ extern "C" int gsx_rigid_transform_fwd(const float *points, int64_t n, const flo
   GSX_CHECK_ARG(n >= 0, "gsx_rigid_transform_fwd: negative count");
   if (n == 0) return 0;
   GSX_CHECK_ARG(points && T && out, "gsx_rigid_transform_fwd: null pointer");
-  k_rigid_fwd<<<(unsigned)((n + kRtBlock - 1) / kRtBlock), kRtBlock, 0, (cudaStream_t)stream>>>(points, n, T, out);
+  k_rigid_fwd<<<(unsigned)((n + kRtBlock - 1) / kRtBlock), kRtBlock, 0, (cudaStream_t)stream>>>(points, n, nullptr, T, out);
   GSX_CHECK_LAUNCH("gsx_rigid_transform_fwd");
+  return 0;
+}
+
+extern "C" int gsx_rigid_transform_batched_fwd(const float *points, const int32_t *counts, int64_t stride, int B,
+                                               const float *T, float *out, void *stream) {
+  GSX_CHECK_ARG(B >= 1 && stride >= 1, "gsx_rigid_transform_batched_fwd: bad sizes");
+  GSX_CHECK_ARG(points && T && out, "gsx_rigid_transform_batched_fwd: null pointer");
+  k_rigid_fwd<<<dim3((unsigned)((stride + kRtBlock - 1) / kRtBlock), (unsigned)B), kRtBlock, 0, (cudaStream_t)stream>>>(
+      points, stride, counts, T, out);
+  GSX_CHECK_LAUNCH("gsx_rigid_transform_batched_fwd");
+  return 0;
+}
+
+extern "C" int gsx_rigid_transform_batched_bwd(const float *points, const int32_t *counts, int64_t stride, int B,
+                                               const float *T, const float *g_out, float *g_points, float *g_T,
+                                               void *scratch, int64_t scratch_bytes, void *stream) {
+  GSX_CHECK_ARG(B >= 1 && stride >= 1, "gsx_rigid_transform_batched_bwd: bad sizes");
+  GSX_CHECK_ARG(points && T && g_out && g_points && g_T && scratch, "gsx_rigid_transform_batched_bwd: null pointer");
+  GSX_CHECK_ARG(scratch_bytes >= (int64_t)B * gsx_rigid_transform_bwd_scratch_bytes(stride),
+                "gsx_rigid_transform_batched_bwd: scratch too small");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int nblk = (int)((stride + kRtBlock - 1) / kRtBlock);
+  k_rigid_bwd<<<dim3((unsigned)nblk, (unsigned)B), kRtBlock, 0, st>>>(points, stride, counts, T, g_out, g_points,
+                                                                      (float *)scratch);
+  k_rigid_bwd_reduce<<<B, 32, 0, st>>>((const float *)scratch, nblk, g_T);
+  GSX_CHECK_LAUNCH("gsx_rigid_transform_batched_bwd");
   return 0;
 }
 
@@ -247,7 +294,7 @@ extern "C" int gsx_rigid_transform_bwd(const float *points, int64_t n, const flo
   if (n > 0) {
     GSX_CHECK_ARG(points && g_out && g_points && scratch, "gsx_rigid_transform_bwd: null pointer");
     GSX_CHECK_ARG(scratch_bytes >= gsx_rigid_transform_bwd_scratch_bytes(n), "gsx_rigid_transform_bwd: scratch too small");
-    k_rigid_bwd<<<nblk, kRtBlock, 0, st>>>(points, n, T, g_out, g_points, (float *)scratch);
+    k_rigid_bwd<<<nblk, kRtBlock, 0, st>>>(points, n, nullptr, T, g_out, g_points, (float *)scratch);
   }
   k_rigid_bwd_reduce<<<1, 32, 0, st>>>((const float *)scratch, nblk, g_T);
   GSX_CHECK_LAUNCH("gsx_rigid_transform_bwd");

@@ -6,7 +6,7 @@ import torch
 
 from ..structures.pointclouds import Pointclouds
 from .base import OdometryProvider
-from .icputils import _taped_icp, _wants_grad, icp_align
+from .icputils import _taped_icp_batched, _wants_grad, icp_align
 
 __all__ = ["ICPOdometryProvider"]
 
@@ -29,11 +29,12 @@ def _provide(prov, maps_pc, frames_pc, mode):
     kw = dict(lambda_max=getattr(prov, "lambda_max", 2.0), B=getattr(prov, "B", 1.0), B2=getattr(prov, "B2", 1.0),
               nu=getattr(prov, "nu", 200.0))
     if _wants_grad(*frames_pc._grad_tensors(), *maps_pc._grad_tensors()):
-        # differentiable mode: per-element taped loop, like the reference's providers (odometry/icp.py:84-97)
-        Ts = [_taped_icp(frames_pc.points_list[b].unsqueeze(0), maps_pc.points_list[b].unsqueeze(0),
-                         maps_pc.normals_list[b].unsqueeze(0), None, mode, prov.numiters, prov.damp,
-                         prov.dist_thresh, **kw)[0] for b in range(len(maps_pc))]
-        return torch.stack(Ts).unsqueeze(1)
+        # differentiable mode: ONE chain of batched autograd ops for all elements (the reference's providers loop over
+        # the batch in Python, odometry/icp.py:84-97)
+        T, _ = _taped_icp_batched(frames_pc.points_padded, frames_pc._counts_dev[frames_pc._cur], maps_pc.points_padded,
+                                  maps_pc.normals_padded, maps_pc._counts_dev[maps_pc._cur], None, mode, prov.numiters,
+                                  prov.damp, prov.dist_thresh, **kw)
+        return T.unsqueeze(1)
     # (the padded views are strided slices of the packed rows; the ICP kernels take dense (B,N,3) clouds)
     src = frames_pc.points_padded.contiguous()
     tgt, tgt_n = maps_pc.points_padded.contiguous(), maps_pc.normals_padded.contiguous()

@@ -67,9 +67,10 @@ def _counts(n, B, device):
     return torch.full((B,), n, dtype=torch.int32, device=device)
 
 
-def knn1(src: torch.Tensor, tgt: torch.Tensor):
-    """Exact 1-NN of every row of src (B,Ns,3) in tgt (B,Nt,3).  Returns (squared distances (B,Ns), idx int64 (B,Ns));
-    ties resolve to the lowest target index.  CUDA kernel k_icp_knn_linearize."""
+def knn1(src: torch.Tensor, tgt: torch.Tensor, src_counts=None, tgt_counts=None):
+    """Exact 1-NN of every row of src (B,Ns,3) in tgt (B,Nt,3) (padded clouds: optional int32 sizes (B,); rows beyond a
+    source size get idx -1).  Returns (squared distances (B,Ns), idx int64 (B,Ns)); ties resolve to the lowest target
+    index.  CUDA kernel k_icp_knn_linearize."""
     _C.require_cuda(src, "src")
     _C.require_cuda(tgt, "tgt")
     src, tgt = src.contiguous(), tgt.contiguous()
@@ -78,7 +79,8 @@ def knn1(src: torch.Tensor, tgt: torch.Tensor):
     idx = torch.empty((B, Ns), dtype=torch.int64, device=src.device)
     d2 = torch.empty((B, Ns), dtype=torch.float32, device=src.device)
     scratch = torch.empty(_C.lib().gsx_knn1_scratch_bytes(B, Ns, Nt), dtype=torch.uint8, device=src.device)
-    ns_t, nt_t = _counts(Ns, B, src.device), _counts(Nt, B, src.device)  # keep alive across the call
+    ns_t = _counts(Ns, B, src.device) if src_counts is None else src_counts  # (kept alive across the call)
+    nt_t = _counts(Nt, B, src.device) if tgt_counts is None else tgt_counts
     with torch.cuda.device(src.device):
         rc = _C.lib().gsx_knn1(_C.ptr(src), _C.ptr(ns_t), Ns, _C.ptr(tgt), _C.ptr(nt_t), Nt, B, _C.ptr(idx),
                                _C.ptr(d2), _C.ptr(scratch), scratch.numel(), _C.stream_ptr(src.device))
@@ -285,6 +287,171 @@ class _RigidTransformFn(torch.autograd.Function):
                                              _C.ptr(scratch), nbytes, _C.stream_ptr(dev))
         _C.check(rc, "gsx_rigid_transform_bwd")
         return g_p, g_T
+
+
+# ------------------------------------------------------------------------------------------------ batched variants
+# The same four ops for a padded batch (B, N, 3) with int32 sizes: ONE op chain records the differentiable ICP of all
+# batch elements (the reference's providers, and round 1 here, ran one chain per element: odometry/icp.py:84-97).  Every
+# kernel takes the batch index from blockIdx.y; values per element are bit-identical to the per-element ops (padding rows
+# contribute exact zeros to the fixed-order sums).
+class _NormalEqBatchedFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, src, tgt, tgt_n, idx, src_counts):
+        src_c, tgt_c, tn_c = (t.detach().contiguous().float() for t in (src, tgt, tgt_n))
+        idx_c = idx.contiguous()
+        _C.require_cuda(src_c, "src")
+        Bn, Ns, _ = src_c.shape
+        Nt, dev = tgt_c.shape[1], src_c.device
+        sums = torch.empty((Bn, 28), dtype=torch.float32, device=dev)
+        lib = _C.lib()
+        nbytes = Bn * lib.gsx_icp_normal_eq_scratch_bytes(Ns)
+        scratch = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        with torch.cuda.device(dev):
+            rc = lib.gsx_icp_normal_eq_batched_fwd(_C.ptr(src_c), _C.ptr(src_counts), Ns, _C.ptr(tgt_c), _C.ptr(tn_c), Nt,
+                                                   Bn, _C.ptr(idx_c), _C.ptr(sums), _C.ptr(scratch), nbytes,
+                                                   _C.stream_ptr(dev))
+        _C.check(rc, "gsx_icp_normal_eq_batched_fwd")
+        ctx.saved = (src_c, tgt_c, tn_c, idx_c, src_counts)
+        return sums
+
+    @staticmethod
+    def backward(ctx, g):
+        src_c, tgt_c, tn_c, idx_c, src_counts = ctx.saved
+        Bn, Ns, _ = src_c.shape
+        Nt, dev = tgt_c.shape[1], src_c.device
+        g = g.contiguous().float()
+        g_src = torch.empty_like(src_c)
+        rows_p, rows_n = torch.empty_like(src_c), torch.empty_like(src_c)
+        with torch.cuda.device(dev):
+            rc = _C.lib().gsx_icp_normal_eq_batched_bwd(_C.ptr(src_c), _C.ptr(src_counts), Ns, _C.ptr(tgt_c),
+                                                        _C.ptr(tn_c), Nt, Bn, _C.ptr(idx_c), _C.ptr(g), _C.ptr(g_src),
+                                                        _C.ptr(rows_p), _C.ptr(rows_n), _C.stream_ptr(dev))
+        _C.check(rc, "gsx_icp_normal_eq_batched_bwd")
+        # rows with idx < 0 carry zero gradients; scatter the per-source-row target gradients with the association
+        flat = (idx_c.clamp(min=0) + torch.arange(Bn, device=dev).view(Bn, 1) * Nt).view(-1)
+        g_tgt = torch.zeros((Bn * Nt, 3), dtype=torch.float32, device=dev).index_add_(0, flat, rows_p.view(-1, 3))
+        g_tn = torch.zeros((Bn * Nt, 3), dtype=torch.float32, device=dev).index_add_(0, flat, rows_n.view(-1, 3))
+        return g_src, g_tgt.view(Bn, Nt, 3), g_tn.view(Bn, Nt, 3), None, None
+
+
+class _SolveBatchedFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, sums, damp):
+        s, d = sums.detach().contiguous().float(), damp.detach().contiguous().float()
+        _C.require_cuda(s, "sums")
+        Bn, dev = s.shape[0], s.device
+        xi = torch.empty((Bn, 6), dtype=torch.float32, device=dev)
+        dT = torch.empty((Bn, 4, 4), dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            rc = _C.lib().gsx_icp_solve_fwd(_C.ptr(s), _C.ptr(d), Bn, _C.ptr(xi), _C.ptr(dT), _C.stream_ptr(dev))
+        _C.check(rc, "gsx_icp_solve_fwd")
+        ctx.saved = (s, d)
+        return xi, dT
+
+    @staticmethod
+    def backward(ctx, g_xi, g_dT):
+        s, d = ctx.saved
+        dev = s.device
+        g_xi = None if g_xi is None else g_xi.contiguous().float()
+        g_dT = None if g_dT is None else g_dT.contiguous().float()
+        g_s, g_d = torch.empty_like(s), torch.empty_like(d)
+        with torch.cuda.device(dev):
+            rc = _C.lib().gsx_icp_solve_bwd(_C.ptr(s), _C.ptr(d), s.shape[0], _C.ptr(g_xi), _C.ptr(g_dT), _C.ptr(g_s),
+                                            _C.ptr(g_d), _C.stream_ptr(dev))
+        _C.check(rc, "gsx_icp_solve_bwd")
+        return g_s, g_d
+
+
+class _UpdateBatchedFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, xi, err, new_err, damp, T, mode, lambda_max, B, B2, nu):
+        dev = xi.device
+        ins = [t.detach().contiguous().float() for t in (xi, err, new_err, damp, T)]
+        _C.require_cuda(ins[0], "xi")
+        Bn = ins[0].shape[0]
+        damp_out = torch.empty(Bn, dtype=torch.float32, device=dev)
+        dT = torch.empty((Bn, 4, 4), dtype=torch.float32, device=dev)
+        Tn = torch.empty((Bn, 4, 4), dtype=torch.float32, device=dev)
+        par = (int(mode), float(lambda_max), float(B), float(B2), float(nu))
+        with torch.cuda.device(dev):
+            rc = _C.lib().gsx_icp_update_fwd(*[_C.ptr(t) for t in ins], Bn, *par, _C.ptr(damp_out), _C.ptr(dT),
+                                             _C.ptr(Tn), _C.stream_ptr(dev))
+        _C.check(rc, "gsx_icp_update_fwd")
+        ctx.saved = (ins, par)
+        return damp_out, dT, Tn
+
+    @staticmethod
+    def backward(ctx, g_damp, g_dT, g_T):
+        ins, par = ctx.saved
+        dev = ins[0].device
+        gs = [None if g is None else g.contiguous().float() for g in (g_damp, g_dT, g_T)]
+        outs = [torch.empty_like(t) for t in ins]
+        with torch.cuda.device(dev):
+            rc = _C.lib().gsx_icp_update_bwd(*[_C.ptr(t) for t in ins], ins[0].shape[0], *par, *[_C.ptr(g) for g in gs],
+                                             *[_C.ptr(o) for o in outs], _C.stream_ptr(dev))
+        _C.check(rc, "gsx_icp_update_bwd")
+        return tuple(outs) + (None,) * 5
+
+
+class _RigidTransformBatchedFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, points, T, counts):
+        p, Tc = points.detach().contiguous().float(), T.detach().contiguous().float()
+        _C.require_cuda(p, "points")
+        dev = p.device
+        out = torch.empty_like(p)
+        with torch.cuda.device(dev):
+            rc = _C.lib().gsx_rigid_transform_batched_fwd(_C.ptr(p), _C.ptr(counts), p.shape[1], p.shape[0], _C.ptr(Tc),
+                                                          _C.ptr(out), _C.stream_ptr(dev))
+        _C.check(rc, "gsx_rigid_transform_batched_fwd")
+        ctx.saved = (p, Tc, counts)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        p, Tc, counts = ctx.saved
+        dev = p.device
+        Bn, n = p.shape[0], p.shape[1]
+        g = g.contiguous().float()
+        g_p, g_T = torch.empty_like(p), torch.empty_like(Tc)
+        lib = _C.lib()
+        nbytes = Bn * lib.gsx_rigid_transform_bwd_scratch_bytes(n)
+        scratch = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        with torch.cuda.device(dev):
+            rc = lib.gsx_rigid_transform_batched_bwd(_C.ptr(p), _C.ptr(counts), n, Bn, _C.ptr(Tc), _C.ptr(g), _C.ptr(g_p),
+                                                     _C.ptr(g_T), _C.ptr(scratch), nbytes, _C.stream_ptr(dev))
+        _C.check(rc, "gsx_rigid_transform_batched_bwd")
+        return g_p, g_T, None
+
+
+def _normal_equations_batched(src, src_counts, tgt, tgt_n, tgt_counts, dist_thresh):
+    d2, idx = knn1(src.detach(), tgt.detach(), src_counts, tgt_counts)
+    if dist_thresh is not None:
+        idx = torch.where(d2 < dist_thresh, idx, torch.full_like(idx, -1))
+    return _NormalEqBatchedFn.apply(src, tgt, tgt_n, idx, src_counts), idx
+
+
+def _taped_icp_batched(src, src_counts, tgt, tgt_n, tgt_counts, T0, mode, numiters, damp, dist_thresh, lambda_max=2.0,
+                       B=1.0, B2=1.0, nu=200.0):
+    """The differentiable ICP / gradICP loop of `_taped_icp` for a padded batch: src (Bn,Ns,3), tgt / tgt_n (Bn,Nt,3),
+    int32 sizes (Bn,).  One chain of batched ops for all elements; returns (T (Bn,4,4), last nn idx (Bn,Ns), -1 = none).
+    Per element the values are bit-identical to the per-element chain and to the fused no-grad loop."""
+    dev = src.device
+    Bn = src.shape[0]
+    dampt = torch.full((Bn,), float(damp), dtype=torch.float32, device=dev)
+    T = (torch.eye(4, dtype=torch.float32, device=dev).repeat(Bn, 1, 1) if T0 is None
+         else T0.to(torch.float32).expand(Bn, 4, 4).contiguous())
+    cur = _RigidTransformBatchedFn.apply(src, T, src_counts)
+    idx = None
+    for _ in range(numiters):
+        sums, idx = _normal_equations_batched(cur, src_counts, tgt, tgt_n, tgt_counts, dist_thresh)
+        xi, dT = _SolveBatchedFn.apply(sums, dampt)
+        one_step = _RigidTransformBatchedFn.apply(cur, dT, src_counts)
+        sums_next, _ = _normal_equations_batched(one_step, src_counts, tgt, tgt_n, tgt_counts, dist_thresh)
+        dampt, dT_applied, T = _UpdateBatchedFn.apply(xi, sums[:, 27], sums_next[:, 27], dampt, T, mode, lambda_max, B,
+                                                      B2, nu)
+        cur = _RigidTransformBatchedFn.apply(cur, dT_applied, src_counts)
+    return T, idx
 
 
 def _normal_equations(src, tgt, tgt_n, dist_thresh):

@@ -262,6 +262,18 @@ int gsx_icp_normal_eq_bwd(const float *src_points, int ns, const float *tgt_poin
  *          se3_exp(xi / (1 + exp(-B2 diff))^(1/nu)).  Outputs: new damp (n), applied step (n,16), T_out = step * T (n,16).
  * The backward entries take the forward inputs again plus the upstream gradients (any may be NULL = zero) and write
  * the gradient of every forward input (same arithmetic evaluated on dual numbers, one lane per input). */
+/* the same two ops for a padded batch (B, stride, 3) with int32 sizes (NULL = all rows): one launch for all elements
+ * (the differentiable mode's op chain is recorded ONCE for the batch instead of once per element, which is what the
+ * reference's providers do, odometry/icp.py:84-97).  sums (B,28); nn_idx (B, ns_stride), -1 = no neighbour; the target
+ * gradients come back per SOURCE row (B, ns_stride, 3).  Padding rows get zero outputs / zero gradients. */
+int gsx_icp_normal_eq_batched_fwd(const float *src_points, const int32_t *src_count, int ns_stride,
+                                  const float *tgt_points, const float *tgt_normals, int nt_stride, int B,
+                                  const int64_t *nn_idx, float *sums_out, void *scratch, int64_t scratch_bytes,
+                                  void *stream);
+int gsx_icp_normal_eq_batched_bwd(const float *src_points, const int32_t *src_count, int ns_stride,
+                                  const float *tgt_points, const float *tgt_normals, int nt_stride, int B,
+                                  const int64_t *nn_idx, const float *g_sums, float *g_src, float *g_tgt_points_rows,
+                                  float *g_tgt_normals_rows, void *stream);
 int gsx_icp_solve_fwd(const float *sums, const float *damp, int n, float *xi_out, float *dT_out, void *stream);
 int gsx_icp_solve_bwd(const float *sums, const float *damp, int n, const float *g_xi, const float *g_dT,
                       float *g_sums, float *g_damp, void *stream);
@@ -277,6 +289,12 @@ int gsx_icp_update_bwd(const float *xi, const float *err, const float *new_err, 
  * reduction; bottom row zero).     replaces transform_pointcloud   gradslam/geometry/geometryutils.py:737-794 */
 int gsx_rigid_transform_fwd(const float *points, int64_t n, const float *T, float *out, void *stream);
 int64_t gsx_rigid_transform_bwd_scratch_bytes(int64_t n);
+/* batched: points (B, stride, 3), T (B,4,4); scratch B * gsx_rigid_transform_bwd_scratch_bytes(stride) bytes */
+int gsx_rigid_transform_batched_fwd(const float *points, const int32_t *counts, int64_t stride, int B, const float *T,
+                                    float *out, void *stream);
+int gsx_rigid_transform_batched_bwd(const float *points, const int32_t *counts, int64_t stride, int B, const float *T,
+                                    const float *g_out, float *g_points, float *g_T, void *scratch,
+                                    int64_t scratch_bytes, void *stream);
 int gsx_rigid_transform_bwd(const float *points, int64_t n, const float *T, const float *g_out, float *g_points,
                             float *g_T, void *scratch, int64_t scratch_bytes, void *stream);
 

@@ -360,3 +360,58 @@ def test_normal_equation_op_forward_and_backward():
     for x, y in zip(b_, a):
         scale = y.grad.abs().max().item()
         torch.testing.assert_close(x.grad.cpu().double(), y.grad, rtol=1e-3, atol=1e-4 * scale)
+
+
+def test_batched_differentiable_icp_equals_per_element_chain():
+    """The batched op chain (one set of autograd ops for all elements, ragged sizes) against the per-element chain of
+    round 1: transforms bit-identical, association identical, gradients w.r.t. the source clouds, the target clouds and
+    the target normals equal to float32 rounding; and the providers use it (ICPSLAM-style call with B=3)."""
+    import gradslam_b200 as gs
+    from gradslam_b200.odometry import icputils as iu
+    from gradslam_b200.odometry.gradicp import GradICPOdometryProvider
+
+    g = torch.Generator().manual_seed(5)
+    Bn, sizes_s, sizes_t = 3, [700, 512, 655], [900, 1024, 640]
+    Ns, Nt = max(sizes_s), max(sizes_t)
+    rgb, depth, K, poses = make_sequence(1, 1, 40, 56, seed=7, hole_fraction=0.0, yaw0=0.6)
+    fr = gs.RGBDImages(rgb.to(DEV), depth.to(DEV), K.to(DEV), poses.to(DEV))
+    base_p = fr.global_vertex_map[0, 0].reshape(-1, 3)
+    base_n = fr.global_normal_map[0, 0].reshape(-1, 3)
+    T_true = [torch.tensor([[1, 0, 0, 0.01 * (b + 1)], [0, 1, 0, -0.005], [0, 0, 1, 0.004 * b], [0, 0, 0, 1.0]],
+                           device=DEV) for b in range(Bn)]
+    src = torch.zeros(Bn, Ns, 3, device=DEV)
+    tgt = torch.zeros(Bn, Nt, 3, device=DEV)
+    tgt_n = torch.zeros(Bn, Nt, 3, device=DEV)
+    for b in range(Bn):
+        pick_t = torch.randperm(base_p.shape[0], generator=g)[: sizes_t[b]].to(DEV)
+        pick_s = torch.randperm(base_p.shape[0], generator=g)[: sizes_s[b]].to(DEV)
+        tgt[b, : sizes_t[b]] = base_p[pick_t]
+        tgt_n[b, : sizes_t[b]] = base_n[pick_t]
+        src[b, : sizes_s[b]] = base_p[pick_s] @ T_true[b][:3, :3].t() + T_true[b][:3, 3]
+    cs = torch.tensor(sizes_s, dtype=torch.int32, device=DEV)
+    ct = torch.tensor(sizes_t, dtype=torch.int32, device=DEV)
+    w = torch.randn(Bn, 4, 4, generator=g).to(DEV)
+    leaves = [t.clone().requires_grad_(True) for t in (src, tgt, tgt_n)]
+    T_b, idx_b = iu._taped_icp_batched(leaves[0], cs, leaves[1], leaves[2], ct, None, 1, 4, 1e-8, None)
+    (T_b * w).sum().backward()
+    for b in range(Bn):
+        l1 = [src[b:b + 1, : sizes_s[b]].clone().requires_grad_(True), tgt[b:b + 1, : sizes_t[b]].clone().requires_grad_(True),
+              tgt_n[b:b + 1, : sizes_t[b]].clone().requires_grad_(True)]
+        T_1, idx_1 = iu._taped_icp(l1[0], l1[1], l1[2], None, 1, 4, 1e-8, None)
+        (T_1 * w[b]).sum().backward()
+        assert torch.equal(T_1, T_b[b])
+        assert torch.equal(idx_1, idx_b[b, : sizes_s[b]][idx_b[b, : sizes_s[b]] >= 0])
+        for got, want, n in ((leaves[0].grad[b], l1[0].grad[0], sizes_s[b]), (leaves[1].grad[b], l1[1].grad[0], sizes_t[b]),
+                             (leaves[2].grad[b], l1[2].grad[0], sizes_t[b])):
+            scale = want.abs().max().item()
+            torch.testing.assert_close(got[:n], want, rtol=1e-4, atol=1e-5 * scale)
+            assert got[n:].abs().max() == 0  # padding rows carry no gradient
+    # the providers run the batched chain when a gradient is requested
+    maps = gs.Pointclouds([tgt[b, : sizes_t[b]] for b in range(Bn)], [tgt_n[b, : sizes_t[b]] for b in range(Bn)])
+    s_req = [src[b, : sizes_s[b]].clone().requires_grad_(True) for b in range(Bn)]
+    out = GradICPOdometryProvider(numiters=4).provide(maps, gs.Pointclouds(s_req))
+    assert out.shape == (Bn, 1, 4, 4) and torch.equal(out[:, 0], T_b.detach())
+    (out[:, 0] * w).sum().backward()
+    for b in range(Bn):
+        scale = leaves[0].grad[b].abs().max().item()
+        torch.testing.assert_close(s_req[b].grad, leaves[0].grad[b, : sizes_s[b]], rtol=1e-4, atol=1e-5 * scale)
