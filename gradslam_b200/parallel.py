@@ -4,10 +4,10 @@ Sequences are independent (each batch element owns its map and pose chain), so a
 contiguous blocks of B_total / world sequences per rank, one process per GPU, and NO traffic crosses GPUs
 while the L frames are fused.  The only exchange is at the end: an all-gather of the per-sequence sizes
 followed by a variable-length all-gather of the fused maps, after which every rank holds all B_total maps.  The maps
-travel as they are stored - packed geometry rows (8 floats) and colour rows (4 floats) - in EXACT sizes: every rank
-sends rows [0, counts[b]) of each of its elements straight out of the store to every peer, which receives them in place
-in the output store (one grouped batch of point-to-point transfers: no staging copy, no padding to the longest map, no
-zero fill of the send side).
+travel as they are stored - packed geometry rows (8 floats) and colour rows (4 floats): two collectives (round 1: four
+attribute tensors), received in place in the output store, no zero fill on either side.  An exact-size point-to-point
+variant (rows [0, counts[b]) straight out of the store, no staging, no padding) is kept behind GSX_MAP_EXCHANGE=p2p; it
+measured slower at 2 GPUs (see _exchange_mode).
 """
 from typing import Optional
 
@@ -107,31 +107,10 @@ def gather_maps_end(h: "_GatherHandle", wait: bool = True) -> Pointclouds:
         out._alloc_buffers(nmax, pc._has_normals, pc._col is not None,
                            pc.num_features if pc.has_features else 0, zero=False)
         out._uninit = True
-        ops, keep = [], []
-        for src, dst in ((pc._geo, out._geo), (pc._col, out._col), (pc._feat, out._feat)):
-            if src is None:
-                continue
-            for b in range(B):
-                c = counts[rank * B + b]
-                if c > 0:
-                    dst[rank * B + b, :c].copy_(src[b, :c])  # own rows: local copy
-            for peer in range(world):
-                if peer == rank:
-                    continue
-                g_peer = peer if group is None else dist.get_global_rank(group, peer)
-                for b in range(B):
-                    c = counts[rank * B + b]
-                    if c > 0:
-                        ops.append(dist.P2POp(dist.isend, src[b, :c], g_peer, group))
-                    c = counts[peer * B + b]
-                    if c > 0:
-                        ops.append(dist.P2POp(dist.irecv, dst[peer * B + b, :c], g_peer, group))
-        if ops:
-            for req in dist.batch_isend_irecv(ops):
-                if h.stream is None:
-                    req.wait()
-                else:
-                    keep.append(req)
+        if _exchange_mode() == "p2p":
+            _exchange_p2p(pc, out, counts, rank, world, B, group, h.stream is None)
+        else:
+            _exchange_all_gather(pc, out, nmax, group, h.stream)
         for t in out._buffers():
             if h.stream is not None:
                 t.record_stream(torch.cuda.current_stream(dev))
@@ -139,6 +118,61 @@ def gather_maps_end(h: "_GatherHandle", wait: bool = True) -> Pointclouds:
     if h.stream is not None and wait:
         torch.cuda.current_stream(dev).wait_stream(h.stream)
     return out
+
+
+def _exchange_mode():
+    """GSX_MAP_EXCHANGE = all_gather (default) | p2p.  Measured at 2 x B200 (bench.py, B=8 x L=32 per GPU, 388 MB of map
+    rows per rank per step): the grouped exact-size point-to-point batch (32 NCCL send / recv operations) 7.70 ms per
+    step against 6.53 ms on one GPU; the collective's numbers are in DESIGN.md section 7."""
+    import os
+
+    return os.environ.get("GSX_MAP_EXCHANGE", "all_gather")
+
+
+def _exchange_all_gather(pc, out, nmax, group, stream):
+    """One all-gather per row array (geometry rows, colour rows [, extra features]): 2 collectives where round 1 sent
+    four attribute tensors.  The send side is the `[:, :nmax]` block of the capacity-backed store (one device-to-device
+    staging copy on the communication stream: the store's row stride is its capacity); the receive side IS the output
+    store, (world * B, nmax, C) rank-major."""
+    for src, dst in ((pc._geo, out._geo), (pc._col, out._col), (pc._feat, out._feat)):
+        if src is None:
+            continue
+        if nmax <= src.shape[1]:
+            send = src[:, :nmax].contiguous()
+        else:  # a peer's map is longer than this rank's capacity: pad a temporary (never re-allocate the live map here)
+            send = src.new_zeros((src.shape[0], nmax, src.shape[2]))
+            send[:, : src.shape[1]] = src
+        _all_gather(dst, send, group)
+        if stream is not None:
+            send.record_stream(stream)
+
+
+def _exchange_p2p(pc, out, counts, rank, world, B, group, blocking):
+    """Exact-size rows straight out of the store: one grouped batch of point-to-point transfers (no staging copy, no
+    padding to the longest map)."""
+    ops = []
+    for src, dst in ((pc._geo, out._geo), (pc._col, out._col), (pc._feat, out._feat)):
+        if src is None:
+            continue
+        for b in range(B):
+            c = counts[rank * B + b]
+            if c > 0:
+                dst[rank * B + b, :c].copy_(src[b, :c])  # own rows: local copy
+        for peer in range(world):
+            if peer == rank:
+                continue
+            g_peer = peer if group is None else dist.get_global_rank(group, peer)
+            for b in range(B):
+                c = counts[rank * B + b]
+                if c > 0:
+                    ops.append(dist.P2POp(dist.isend, src[b, :c], g_peer, group))
+                c = counts[peer * B + b]
+                if c > 0:
+                    ops.append(dist.P2POp(dist.irecv, dst[peer * B + b, :c], g_peer, group))
+    if ops:
+        for req in dist.batch_isend_irecv(ops):
+            if blocking:
+                req.wait()
 
 
 def comm_stream(device):
