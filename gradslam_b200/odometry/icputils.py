@@ -76,8 +76,9 @@ def knn1(src: torch.Tensor, tgt: torch.Tensor, src_counts=None, tgt_counts=None)
     src, tgt = src.contiguous(), tgt.contiguous()
     B, Ns, _ = src.shape
     Nt = tgt.shape[1]
-    idx = torch.empty((B, Ns), dtype=torch.int64, device=src.device)
-    d2 = torch.empty((B, Ns), dtype=torch.float32, device=src.device)
+    # (the kernel writes the rows below each source size; the padding rows keep -1 / inf)
+    idx = torch.full((B, Ns), -1, dtype=torch.int64, device=src.device)
+    d2 = torch.full((B, Ns), float("inf"), dtype=torch.float32, device=src.device)
     scratch = torch.empty(_C.lib().gsx_knn1_scratch_bytes(B, Ns, Nt), dtype=torch.uint8, device=src.device)
     ns_t = _counts(Ns, B, src.device) if src_counts is None else src_counts  # (kept alive across the call)
     nt_t = _counts(Nt, B, src.device) if tgt_counts is None else tgt_counts
