@@ -405,7 +405,7 @@ def test_batched_differentiable_icp_equals_per_element_chain():
                              (leaves[2].grad[b], l1[2].grad[0], sizes_t[b])):
             scale = want.abs().max().item()
             torch.testing.assert_close(got[:n], want, rtol=1e-4, atol=1e-5 * scale)
-            assert got[n:].abs().max() == 0  # padding rows carry no gradient
+            assert got[n:].numel() == 0 or got[n:].abs().max() == 0  # padding rows carry no gradient
     # the providers run the batched chain when a gradient is requested
     maps = gs.Pointclouds([tgt[b, : sizes_t[b]] for b in range(Bn)], [tgt_n[b, : sizes_t[b]] for b in range(Bn)])
     s_req = [src[b, : sizes_s[b]].clone().requires_grad_(True) for b in range(Bn)]
