@@ -183,6 +183,7 @@ def workload_config(args, world):
                         args.width, args.height, args.batch, args.seqlen),
         "global_batch": args.batch * world, "seq_len": args.seqlen, "height": args.height, "width": args.width,
         "frames_per_step": args.batch * world * args.seqlen, "parallelism": "batch-sharded x%d" % world,
+        "map_exchange": None if world == 1 else os.environ.get("GSX_MAP_EXCHANGE", "peer"),
         "l2_policy": "inputs (%.0f MB depth+rgb per GPU per step) exceed the 126 MB L2" % (
             args.batch * args.seqlen * args.height * args.width * 16 / 1e6),
     }
@@ -208,6 +209,8 @@ def main():
     assert torch.cuda.is_available(), "bench.py (impl gsx) needs a GPU; there is no CPU fallback"
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    # host buffers of this rank in the memory of its GPU's NUMA node (matters for the e2e leg at N > 1)
+    host_cpus = parallel.bind_host_to_gpu(dev) if world > 1 else None
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         # NCCL prints its version banner on stdout when the communicator is created; stdout must carry exactly
@@ -473,7 +476,7 @@ def main():
                     "ms_per_step": ms_e2e / args.steps,
                     "result": "poses + map sizes + the fused map of this rank (packed rows, exact sizes) into pinned "
                               "host memory, overlapped with the next step",
-                    "timed_regions_ms": all_e2e},
+                    "host_cpus": host_cpus, "timed_regions_ms": all_e2e},
             # K1r + K2/K3 + K4 per frame and per concurrent batch group; K2 is skipped on the empty map
             "gpu_launches": groups * (3 * L - 1) * args.steps, "sequence_groups": groups,
             "repeats": repeats, "timed_regions_ms": all_dev,

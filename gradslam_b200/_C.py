@@ -49,6 +49,10 @@ SIGNATURES = {
         c_int, [c_vp, c_vp, c_vp, c_i64, c_i64, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_int,
                 c_float, c_float, c_double, c_vp, c_vp, c_vp]),
     "gsx_debug_fail_at_frame": (None, [c_int]),
+    "gsx_peer_export": (c_int, [c_vp, c_vp, c_vp, c_vp]),
+    "gsx_peer_open": (c_int, [c_vp, c_i64, c_vp]),
+    "gsx_peer_close_all": (c_int, []),
+    "gsx_peer_copy_rows": (c_int, [c_vp, c_i64, c_vp, c_i64, c_i64, c_i64, c_vp]),
     "gsx_ingest_raw": (c_int, [c_vp, c_vp, c_i64, c_double, c_int, c_vp, c_vp, c_vp]),
     "gsx_ingest_calibration": (c_int, [c_vp, c_i64, c_int, c_double, c_double, c_vp, c_vp, c_int, c_int, c_vp, c_vp,
                                        c_vp]),

@@ -4,10 +4,15 @@ Sequences are independent (each batch element owns its map and pose chain), so a
 contiguous blocks of B_total / world sequences per rank, one process per GPU, and NO traffic crosses GPUs
 while the L frames are fused.  The only exchange is at the end: an all-gather of the per-sequence sizes
 followed by a variable-length all-gather of the fused maps, after which every rank holds all B_total maps.  The maps
-travel as they are stored - packed geometry rows (8 floats) and colour rows (4 floats): two collectives (round 1: four
-attribute tensors), received in place in the output store, no zero fill on either side.  An exact-size point-to-point
-variant (rows [0, counts[b]) straight out of the store, no staging, no padding) is kept behind GSX_MAP_EXCHANGE=p2p; it
-measured slower at 2 GPUs (see _exchange_mode).
+travel as they are stored - packed geometry rows (8 floats) and colour rows (4 floats) - and are received in place in the
+output store, no zero fill on either side.  Three transports (see _exchange_mode):
+
+  peer        each rank PULLS its peers' rows out of their stores (CUDA IPC mappings) with one pitched copy per peer and
+              row array, executed by the copy engines over NVLink: no communication kernel on any SM, no staging copy
+              (csrc/gsx_peer.cu).  The size all-gather before the pulls orders them after the owners' fusion; a one-word
+              all-reduce after them releases the owners' stores.
+  all_gather  one NCCL all-gather per row array on `[:, :nmax]` staging copies (also the CPU / gloo path of the tests).
+  p2p         grouped exact-size NCCL send / recv straight out of the stores.
 """
 from typing import Optional
 
@@ -16,7 +21,34 @@ import torch.distributed as dist
 
 from .structures.pointclouds import Pointclouds
 
-__all__ = ["shard_batch", "gather_maps", "gather_maps_begin", "gather_maps_end", "comm_stream"]
+__all__ = ["shard_batch", "gather_maps", "gather_maps_begin", "gather_maps_end", "comm_stream", "bind_host_to_gpu"]
+
+
+def bind_host_to_gpu(device) -> Optional[str]:
+    """Pins this process (one process per GPU) to the CPU cores of the NUMA node the GPU hangs off, so that the pinned
+    host buffers it allocates afterwards - the upload source and the map read-back target - are placed in that node's
+    memory and the PCIe traffic of the ranks does not cross the socket interconnect.  Returns the core list that was
+    applied, or None if the topology is not exposed (the affinity is then left alone)."""
+    import os
+
+    try:
+        prop = torch.cuda.get_device_properties(torch.device(device))
+        bdf = "%04x:%02x:%02x.0" % (prop.pci_domain_id, prop.pci_bus_id, prop.pci_device_id)
+        with open("/sys/bus/pci/devices/%s/local_cpulist" % bdf) as f:
+            text = f.read().strip()
+        cpus = set()
+        for part in text.split(","):
+            if not part:
+                continue
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return text
+    except (OSError, ValueError, AttributeError, RuntimeError):
+        return None
 
 
 def shard_batch(total: int, rank: Optional[int] = None, world: Optional[int] = None):
@@ -41,7 +73,30 @@ def _comm_stream(device):
 
 
 class _GatherHandle:
-    __slots__ = ("pc", "group", "world", "counts_host", "ready", "stream")
+    __slots__ = ("pc", "group", "world", "counts_host", "ready", "stream", "mode", "meta_len")
+
+
+_META_PER_ARRAY = 10  # present, offset, 8 words of IPC handle
+
+
+def _export_stores(pc):
+    """Host int64 words describing where this rank's row arrays live: capacity, then per array (geometry, colour, extra
+    features) a present flag, the offset inside its allocation and the allocation's CUDA IPC handle (gsx_peer_export)."""
+    import ctypes
+    import struct
+
+    from . import _C
+
+    words = [pc.capacity]
+    for t in (pc._geo, pc._col, pc._feat):
+        if t is None:
+            words += [0] * _META_PER_ARRAY
+            continue
+        handle = (ctypes.c_ubyte * 64)()
+        off = ctypes.c_int64(0)
+        _C.check(_C.lib().gsx_peer_export(_C.ptr(t), handle, ctypes.byref(off), None), "gsx_peer_export")
+        words += [1, off.value] + list(struct.unpack("8q", bytes(handle)))
+    return words
 
 
 def gather_maps_begin(pointclouds: Pointclouds, group=None) -> "_GatherHandle":
@@ -61,11 +116,21 @@ def gather_maps_begin(pointclouds: Pointclouds, group=None) -> "_GatherHandle":
         import contextlib
 
         ctx = contextlib.nullcontext()
+    h.mode = _exchange_mode(dev)
+    h.meta_len = 0
+    meta = None
+    if h.mode == "peer":
+        words = _export_stores(pointclouds)
+        h.meta_len = len(words)
+        meta = torch.tensor(words, dtype=torch.int64).pin_memory()
     with ctx:
-        all_counts = torch.empty(h.world * B, dtype=torch.int64, device=dev)
-        _all_gather(all_counts, local.to(torch.int64).contiguous(), group)
+        send = local.to(torch.int64).contiguous()
+        if meta is not None:  # sizes and store descriptors travel in the same small all-gather
+            send = torch.cat([send, meta.to(dev, non_blocking=True)])
+        all_counts = torch.empty(h.world * (B + h.meta_len), dtype=torch.int64, device=dev)
+        _all_gather(all_counts, send, group)
         if h.stream is not None:
-            h.counts_host = torch.empty(h.world * B, dtype=torch.int64, pin_memory=True)
+            h.counts_host = torch.empty(h.world * (B + h.meta_len), dtype=torch.int64, pin_memory=True)
             h.counts_host.copy_(all_counts, non_blocking=True)
             h.ready = torch.cuda.Event()
             h.ready.record(h.stream)
@@ -87,7 +152,8 @@ def gather_maps_end(h: "_GatherHandle", wait: bool = True) -> Pointclouds:
     B = len(pc)
     if h.ready is not None:
         h.ready.synchronize()
-    counts = [int(c) for c in h.counts_host.tolist()]
+    blob = h.counts_host.view(world, B + h.meta_len)
+    counts = [int(c) for c in blob[:, :B].reshape(-1).tolist()]
     nmax = max(max(counts), 1)
     rank = dist.get_rank(group)
     if pc._counts_host is None:  # (also raises if the local map overflowed its capacity)
@@ -107,7 +173,9 @@ def gather_maps_end(h: "_GatherHandle", wait: bool = True) -> Pointclouds:
         out._alloc_buffers(nmax, pc._has_normals, pc._col is not None,
                            pc.num_features if pc.has_features else 0, zero=False)
         out._uninit = True
-        if _exchange_mode() == "p2p":
+        if h.mode == "peer":
+            _exchange_peer(pc, out, counts, blob[:, B:], rank, world, B, nmax, group, h.stream)
+        elif h.mode == "p2p":
             _exchange_p2p(pc, out, counts, rank, world, B, group, h.stream is None)
         else:
             _exchange_all_gather(pc, out, nmax, group, h.stream)
@@ -120,13 +188,56 @@ def gather_maps_end(h: "_GatherHandle", wait: bool = True) -> Pointclouds:
     return out
 
 
-def _exchange_mode():
-    """GSX_MAP_EXCHANGE = all_gather (default) | p2p.  Measured at 2 x B200 (bench.py, B=8 x L=32 per GPU, 388 MB of map
-    rows per rank per step): the grouped exact-size point-to-point batch (32 NCCL send / recv operations) 7.70 ms per
-    step against 6.53 ms on one GPU; the collective's numbers are in DESIGN.md section 7."""
+def _exchange_mode(device=None):
+    """GSX_MAP_EXCHANGE = peer | all_gather | p2p.  On CUDA the default is `peer` (copy-engine pulls through IPC mappings);
+    CPU tensors (the gloo tests) always use all_gather.  Measured numbers: DESIGN.md section 7."""
     import os
 
-    return os.environ.get("GSX_MAP_EXCHANGE", "all_gather")
+    if device is not None and torch.device(device).type != "cuda":
+        return "all_gather"
+    mode = os.environ.get("GSX_MAP_EXCHANGE", "peer")
+    if mode not in ("peer", "all_gather", "p2p"):
+        raise ValueError("GSX_MAP_EXCHANGE must be peer, all_gather or p2p (got %r)" % mode)
+    return mode
+
+
+def _exchange_peer(pc, out, counts, meta, rank, world, B, nmax, group, stream):
+    """Every rank pulls: per peer and row array ONE pitched copy (B blocks of max(counts of that peer) rows) from the
+    peer's store - mapped into this process through its IPC handle - into this rank's output store.  No kernel runs; the
+    trailing one-word all-reduce completes on a rank only when every peer has issued and finished its pulls, which is
+    what allows that rank's store to be reused."""
+    import ctypes
+    import struct
+
+    from . import _C
+
+    lib = _C.lib()
+    dev = pc.device
+    sp = ctypes.c_void_p(stream.cuda_stream)
+    with torch.cuda.device(dev):
+        for q in range(world):
+            nq = max(counts[q * B:(q + 1) * B])
+            if nq == 0:
+                continue
+            cap_q = int(meta[q, 0])
+            for k, (src, dst) in enumerate(((pc._geo, out._geo), (pc._col, out._col), (pc._feat, out._feat))):
+                if dst is None:
+                    continue
+                row = dst.shape[2] * 4
+                words = meta[q, 1 + k * _META_PER_ARRAY: 1 + (k + 1) * _META_PER_ARRAY].tolist()
+                if not words[0]:
+                    raise RuntimeError("gather_maps: rank %d has no array %d but rank %d does" % (q, k, rank))
+                if q == rank:
+                    sptr = ctypes.c_void_p(src.data_ptr())
+                else:
+                    sptr = ctypes.c_void_p()
+                    handle = (ctypes.c_ubyte * 64).from_buffer_copy(struct.pack("8q", *words[2:]))
+                    _C.check(lib.gsx_peer_open(handle, words[1], ctypes.byref(sptr)), "gsx_peer_open")
+                _C.check(lib.gsx_peer_copy_rows(ctypes.c_void_p(dst.data_ptr() + q * B * nmax * row), nmax * row, sptr,
+                                                cap_q * row, nq * row, B, sp), "gsx_peer_copy_rows")
+    token = torch.zeros(1, dtype=torch.int32, device=dev)
+    dist.all_reduce(token, group=group)
+    token.record_stream(stream)
 
 
 def _exchange_all_gather(pc, out, nmax, group, stream):

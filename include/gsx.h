@@ -157,6 +157,22 @@ int gsx_pointfusion_sequence_gt(float *map_geometry, float *map_colors, int32_t 
 void gsx_debug_fail_at_frame(int s);
 
 /* ------------------------------------------------------------------------------------------------
+ * Map exchange between the GPUs of a node through peer memory (SURVEY.md section 8e "Collective": the variable-length
+ * all-gather of the finished maps; the reference has no multi-GPU code - this is the exchange its DataParallel-style
+ * use would need).  One process per GPU.  The owner exports the allocation behind a store pointer as a CUDA IPC handle,
+ * peers open it (mappings are cached per process; gsx_peer_close_all drops them - call it before the owners free their
+ * allocations back to the driver) and pull row blocks with pitched device-to-device copies on the copy engines:
+ * block b of n_blocks moves width_bytes from src + b*src_pitch_bytes to dst + b*dst_pitch_bytes.  Ordering between the
+ * processes is the caller's (gradslam_b200/parallel.py).  Return 0, or non-zero with gsx_last_error(). */
+#define GSX_IPC_HANDLE_BYTES 64
+int gsx_peer_export(const void *ptr, unsigned char *handle /* [GSX_IPC_HANDLE_BYTES] */, int64_t *offset,
+                    int64_t *allocation_bytes /* optional */);
+int gsx_peer_open(const unsigned char *handle, int64_t offset, void **ptr_out);
+int gsx_peer_close_all(void);
+int gsx_peer_copy_rows(void *dst, int64_t dst_pitch_bytes, const void *src, int64_t src_pitch_bytes,
+                       int64_t width_bytes, int64_t n_blocks, void *stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Dataset-native ingest: 8-bit colour (n_pixels,3) and 16-bit depth (n_pixels) as stored by
  * ICL-NUIM / TUM / ScanNet -> float32 colour and depth on the device, bit-identical to the reference loaders'
  * host-side conversion: colour = float(u8) [/ 255 if normalize_color], depth = float32(float64(u16) /
