@@ -176,6 +176,11 @@ def run_reference(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
+# GSX_BENCH_EXCHANGE: diagnostic only.  overlap (default, the product path): the maps of step k travel while step k+1 is
+# fused;  serial: exchange, then the next step;  none: no exchange (NOT the metric - the line says so in config).
+EXCHANGE_SCHEDULE = os.environ.get("GSX_BENCH_EXCHANGE", "overlap")
+
+
 def workload_config(args, world):
     return {
         "workload": "PointFusion(odom='gt', dist_th=0.05, angle_th=20, sigma=0.6) forward over synthetic box-room "
@@ -183,7 +188,8 @@ def workload_config(args, world):
                         args.width, args.height, args.batch, args.seqlen),
         "global_batch": args.batch * world, "seq_len": args.seqlen, "height": args.height, "width": args.width,
         "frames_per_step": args.batch * world * args.seqlen, "parallelism": "batch-sharded x%d" % world,
-        "map_exchange": None if world == 1 else os.environ.get("GSX_MAP_EXCHANGE", "peer"),
+        "map_exchange": None if world == 1 else "%s (%s)" % (os.environ.get("GSX_MAP_EXCHANGE", "peer"),
+                                                               EXCHANGE_SCHEDULE),
         "l2_policy": "inputs (%.0f MB depth+rgb per GPU per step) exceed the 126 MB L2" % (
             args.batch * args.seqlen * args.height * args.width * 16 / 1e6),
     }
@@ -253,6 +259,13 @@ def main():
         dl_state["bytes"] = rows * (32 + 16) + poses.numel() * 4 + len(host) * 8
         return host
 
+    # N > 1: two job-wide stores used alternately; each rank fuses its sequences straight into its block of one of them
+    # and pulls the peers' rows into the other blocks (GSX_BENCH_STORE=fresh: a fresh local map and a fresh gathered
+    # store per step, own rows copied - the round-1 behaviour, for comparison)
+    stores = []
+    if world > 1 and os.environ.get("GSX_BENCH_STORE", "shared") == "shared":
+        stores = [parallel.GatheredMaps(B, L * H * W, dev) for _ in range(2)]
+
     def run_steps(frames, steps, d2h):
         """`steps` whole-batch PointFusion calls.  N>1: the final-map exchange of step k (communication stream) overlaps
         the fusion of step k+1; the last one is awaited before returning.  d2h: the result (poses + the fused map of this
@@ -260,14 +273,22 @@ def main():
         res = None
         pending = None  # (gather handle, poses) of the previous step
         prev = None  # (map, poses) of the previous step, still to be read back
-        for _ in range(steps):
-            pc, poses = slam(frames)
+        for i in range(steps):
+            store = stores[i % len(stores)] if stores else None
+            if store is not None:
+                # the block is reused every other step: wait (on the device) for its last exchange and read-back
+                torch.cuda.current_stream(dev).wait_stream(dl_stream)
+                pc, poses = slam(frames, out=store.reset())
+            else:
+                pc, poses = slam(frames)
             if pending is not None:  # step k-1's maps travel while step k (just enqueued) computes
                 parallel.gather_maps_end(pending[0], wait=False)
             if d2h and prev is not None:
                 res = (prev[1].cpu(), read_back(*prev))
-            if world > 1:
-                pending = (parallel.gather_maps_begin(pc), poses)
+            if world > 1 and EXCHANGE_SCHEDULE == "serial":  # diagnostic: the exchange alone on the GPU, then the next step
+                parallel.gather_maps(pc, into=store)
+            elif world > 1 and EXCHANGE_SCHEDULE != "none":
+                pending = (parallel.gather_maps_begin(pc, into=store), poses)
             prev = (pc, poses)
         if pending is not None:
             parallel.gather_maps_end(pending[0], wait=True)

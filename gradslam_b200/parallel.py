@@ -21,7 +21,8 @@ import torch.distributed as dist
 
 from .structures.pointclouds import Pointclouds
 
-__all__ = ["shard_batch", "gather_maps", "gather_maps_begin", "gather_maps_end", "comm_stream", "bind_host_to_gpu"]
+__all__ = ["shard_batch", "gather_maps", "gather_maps_begin", "gather_maps_end", "comm_stream", "bind_host_to_gpu",
+           "GatheredMaps"]
 
 
 def bind_host_to_gpu(device) -> Optional[str]:
@@ -73,7 +74,42 @@ def _comm_stream(device):
 
 
 class _GatherHandle:
-    __slots__ = ("pc", "group", "world", "counts_host", "ready", "stream", "mode", "meta_len")
+    __slots__ = ("pc", "group", "world", "counts_host", "ready", "stream", "mode", "meta_len", "into")
+
+
+class GatheredMaps:
+    """A job-wide map store: row arrays for world * B maps of `capacity` rows on every rank.  This rank's sequences are
+    fused IN PLACE into its block (`PointFusion(...)(frames, out=store.local)`); `gather_maps*(store.local, into=store)`
+    then only moves the peers' rows - into their blocks of this store - and returns `store.all`.  Compared with gathering
+    into a fresh store this saves the allocation and the local copy of this rank's own rows (as many bytes again as one
+    peer sends).  `reset()` empties the local block for the next job."""
+
+    def __init__(self, batch_size: int, capacity: int, device, group=None):
+        from .structures.pointclouds import COL_W, GEO_W
+
+        self.group = group
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        self.batch_size = int(batch_size)
+        device = torch.device(device)
+        total = self.world * self.batch_size
+        geo = torch.empty((total, int(capacity), GEO_W), dtype=torch.float32, device=device)
+        col = torch.empty((total, int(capacity), COL_W), dtype=torch.float32, device=device)
+        self.all = Pointclouds(device=device)
+        self.all._attach(geo, col)
+        lo = self.rank * self.batch_size
+        self.local = Pointclouds(device=device)
+        self.local._attach(geo[lo: lo + self.batch_size], col[lo: lo + self.batch_size])
+        self._done = None  # event on the communication stream: the last exchange of this store has completed
+
+    def reset(self) -> Pointclouds:
+        """Empties this rank's block for the next job and returns it.  The current stream is made to wait for the last
+        exchange of this store (peers may still be reading the block until then)."""
+        if self._done is not None:
+            torch.cuda.current_stream(self.local.device).wait_event(self._done)
+        for pc in (self.local, self.all):
+            pc._overflow = None
+            pc._set_counts([0] * len(pc))
+        return self.local
 
 
 _META_PER_ARRAY = 10  # present, offset, 8 words of IPC handle
@@ -99,12 +135,21 @@ def _export_stores(pc):
     return words
 
 
-def gather_maps_begin(pointclouds: Pointclouds, group=None) -> "_GatherHandle":
+def gather_maps_begin(pointclouds: Pointclouds, group=None, into: Optional[GatheredMaps] = None) -> "_GatherHandle":
     """First half of the map all-gather: exchanges the per-sequence sizes on a side (communication) stream and
     starts their copy to pinned host memory.  Does NOT block the host, so the caller can enqueue the next batch of
-    sequences before calling `gather_maps_end` — the exchange then overlaps that compute."""
+    sequences before calling `gather_maps_end` — the exchange then overlaps that compute.
+    into: the GatheredMaps store whose `local` block `pointclouds` is (see there)."""
     h = _GatherHandle()
     h.pc, h.group, h.world = pointclouds, group, dist.get_world_size(group)
+    h.into = into
+    if into is not None:
+        if pointclouds is not into.local or pointclouds._geo.data_ptr() != into.all._geo[
+                into.rank * into.batch_size].data_ptr():
+            raise ValueError("gather_maps(into=store): `pointclouds` must be store.local, still living in the store "
+                             "(a map that outgrew its capacity is re-allocated elsewhere)")
+        if into.group is not group:
+            raise ValueError("gather_maps(into=store): the store was created for another process group")
     dev = pointclouds.device
     B = len(pointclouds)
     h.stream = _comm_stream(dev)
@@ -159,8 +204,15 @@ def gather_maps_end(h: "_GatherHandle", wait: bool = True) -> Pointclouds:
     if pc._counts_host is None:  # (also raises if the local map overflowed its capacity)
         pc._counts_host = counts[rank * B: (rank + 1) * B]
         pc._check_overflow()
-    out = Pointclouds(device=dev)
-    out._B = world * B
+    in_place = h.into is not None
+    if in_place:
+        out = h.into.all
+        if nmax > out.capacity:
+            raise RuntimeError("gather_maps(into=store): a peer's map has %d rows, the store's capacity is %d" % (
+                nmax, out.capacity))
+    else:
+        out = Pointclouds(device=dev)
+        out._B = world * B
     if h.stream is not None:
         ctx = torch.cuda.stream(h.stream)
     else:
@@ -170,19 +222,23 @@ def gather_maps_end(h: "_GatherHandle", wait: bool = True) -> Pointclouds:
     with ctx:
         # not zero-filled (that would be a multi-GB memset per step at 8 GPUs): the zero padding the *_padded views
         # promise is restored lazily, only for the ragged tails and only if such a view is asked for (Pointclouds._padded)
-        out._alloc_buffers(nmax, pc._has_normals, pc._col is not None,
-                           pc.num_features if pc.has_features else 0, zero=False)
-        out._uninit = True
+        if not in_place:
+            out._alloc_buffers(nmax, pc._has_normals, pc._col is not None,
+                               pc.num_features if pc.has_features else 0, zero=False)
+            out._uninit = True
         if h.mode == "peer":
-            _exchange_peer(pc, out, counts, blob[:, B:], rank, world, B, nmax, group, h.stream)
-        elif h.mode == "p2p":
-            _exchange_p2p(pc, out, counts, rank, world, B, group, h.stream is None)
+            _exchange_peer(pc, out, counts, blob[:, B:], rank, world, B, group, h.stream, skip_own=in_place)
+        elif h.mode == "p2p" or in_place:
+            _exchange_p2p(pc, out, counts, rank, world, B, group, h.stream is None, skip_own=in_place)
         else:
             _exchange_all_gather(pc, out, nmax, group, h.stream)
         for t in out._buffers():
             if h.stream is not None:
                 t.record_stream(torch.cuda.current_stream(dev))
         out._set_counts(counts)
+        if in_place and h.stream is not None:
+            h.into._done = torch.cuda.Event()
+            h.into._done.record(h.stream)
     if h.stream is not None and wait:
         torch.cuda.current_stream(dev).wait_stream(h.stream)
     return out
@@ -201,7 +257,7 @@ def _exchange_mode(device=None):
     return mode
 
 
-def _exchange_peer(pc, out, counts, meta, rank, world, B, nmax, group, stream):
+def _exchange_peer(pc, out, counts, meta, rank, world, B, group, stream, skip_own=False):
     """Every rank pulls: per peer and row array ONE pitched copy (B blocks of max(counts of that peer) rows) from the
     peer's store - mapped into this process through its IPC handle - into this rank's output store.  No kernel runs; the
     trailing one-word all-reduce completes on a rank only when every peer has issued and finished its pulls, which is
@@ -214,10 +270,11 @@ def _exchange_peer(pc, out, counts, meta, rank, world, B, nmax, group, stream):
     lib = _C.lib()
     dev = pc.device
     sp = ctypes.c_void_p(stream.cuda_stream)
+    pitch_rows = out.capacity  # row stride of the receiving store's elements
     with torch.cuda.device(dev):
         for q in range(world):
             nq = max(counts[q * B:(q + 1) * B])
-            if nq == 0:
+            if nq == 0 or (skip_own and q == rank):
                 continue
             cap_q = int(meta[q, 0])
             for k, (src, dst) in enumerate(((pc._geo, out._geo), (pc._col, out._col), (pc._feat, out._feat))):
@@ -233,8 +290,9 @@ def _exchange_peer(pc, out, counts, meta, rank, world, B, nmax, group, stream):
                     sptr = ctypes.c_void_p()
                     handle = (ctypes.c_ubyte * 64).from_buffer_copy(struct.pack("8q", *words[2:]))
                     _C.check(lib.gsx_peer_open(handle, words[1], ctypes.byref(sptr)), "gsx_peer_open")
-                _C.check(lib.gsx_peer_copy_rows(ctypes.c_void_p(dst.data_ptr() + q * B * nmax * row), nmax * row, sptr,
-                                                cap_q * row, nq * row, B, sp), "gsx_peer_copy_rows")
+                _C.check(lib.gsx_peer_copy_rows(ctypes.c_void_p(dst.data_ptr() + q * B * pitch_rows * row),
+                                                pitch_rows * row, sptr, cap_q * row, nq * row, B, sp),
+                         "gsx_peer_copy_rows")
     token = torch.zeros(1, dtype=torch.int32, device=dev)
     dist.all_reduce(token, group=group)
     token.record_stream(stream)
@@ -258,7 +316,7 @@ def _exchange_all_gather(pc, out, nmax, group, stream):
             send.record_stream(stream)
 
 
-def _exchange_p2p(pc, out, counts, rank, world, B, group, blocking):
+def _exchange_p2p(pc, out, counts, rank, world, B, group, blocking, skip_own=False):
     """Exact-size rows straight out of the store: one grouped batch of point-to-point transfers (no staging copy, no
     padding to the longest map)."""
     ops = []
@@ -267,7 +325,7 @@ def _exchange_p2p(pc, out, counts, rank, world, B, group, blocking):
             continue
         for b in range(B):
             c = counts[rank * B + b]
-            if c > 0:
+            if c > 0 and not skip_own:
                 dst[rank * B + b, :c].copy_(src[b, :c])  # own rows: local copy
         for peer in range(world):
             if peer == rank:
@@ -291,13 +349,13 @@ def comm_stream(device):
     return _comm_stream(torch.device(device))
 
 
-def gather_maps(pointclouds: Pointclouds, group=None) -> Pointclouds:
+def gather_maps(pointclouds: Pointclouds, group=None, into: Optional[GatheredMaps] = None) -> Pointclouds:
     """All-gathers the maps of every rank (equal local batch size).  Returns a Pointclouds with world*B maps,
     ordered by rank.  Works on NCCL (CUDA tensors) and on gloo (CPU tensors, used by the CPU tests).
     Blocking convenience wrapper around gather_maps_begin / gather_maps_end."""
-    if dist.get_world_size(group) == 1:
+    if dist.get_world_size(group) == 1 and into is None:
         return pointclouds
-    return gather_maps_end(gather_maps_begin(pointclouds, group), wait=True)
+    return gather_maps_end(gather_maps_begin(pointclouds, group, into), wait=True)
 
 
 def _all_gather(recv, send, group):

@@ -51,13 +51,17 @@ class ICPSLAM(nn.Module):
         self.device = _normalize_device(device if device is not None else "cuda")
 
     # ------------------------------------------------------------------ sequence driver
-    def forward(self, frames: RGBDImages):
-        """Builds the maps from a (B, L) batch of sequences.  Returns (Pointclouds, poses (B,L,4,4))."""
+    def forward(self, frames: RGBDImages, out: Optional[Pointclouds] = None):
+        """Builds the maps from a (B, L) batch of sequences.  Returns (Pointclouds, poses (B,L,4,4)).
+        out (extension): EMPTY maps with pre-allocated row storage that receive the result in place - e.g. this rank's
+        block of a job-wide store, `parallel.GatheredMaps(...).local`.  Give it room for L*H*W rows per sequence: a map
+        that outgrows its storage is re-allocated elsewhere (step loop) or reports the overflow (sequence call)."""
         if not isinstance(frames, RGBDImages):
             raise TypeError("Expected frames to be of type gradslam.RGBDImages. Got {0}.".format(type(frames)))
-        pointclouds = Pointclouds(device=self.device)
         batch_size, seq_len = frames.shape[:2]
-        fast = self._forward_sequence(frames)
+        self._check_out(out, batch_size)
+        pointclouds = out if out is not None else Pointclouds(device=self.device)
+        fast = self._forward_sequence(frames, out=out)
         if fast is not None:
             return fast
         recovered_poses = torch.empty(batch_size, seq_len, 4, 4, device=self.device)
@@ -72,7 +76,17 @@ class ICPSLAM(nn.Module):
             recovered_poses[:, s] = live_frame.poses[:, 0]
         return pointclouds, recovered_poses
 
-    def _forward_sequence(self, frames):
+    def _check_out(self, out, batch_size):
+        if out is None:
+            return
+        if not isinstance(out, Pointclouds):
+            raise TypeError("Expected out to be of type gradslam.Pointclouds. Got {0}.".format(type(out)))
+        if out.device != self.device or not out.has_points or len(out) != batch_size:
+            raise ValueError("out must hold %d pre-allocated maps on %s" % (batch_size, self.device))
+        if any(out._host_counts()):
+            raise ValueError("out must be empty (the maps are built from scratch)")
+
+    def _forward_sequence(self, frames, out=None):
         """Hook for single-call whole-sequence drivers (PointFusion with odom='gt'); None = use the step loop."""
         return None
 

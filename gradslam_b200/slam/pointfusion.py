@@ -60,7 +60,7 @@ class PointFusion(ICPSLAM):
     def _map(self, pointclouds: Pointclouds, live_frame: RGBDImages, inplace: bool = False):
         return update_map_fusion(pointclouds, live_frame, self.dist_th, self.dot_th, self.sigma, inplace)
 
-    def forward(self, frames):
+    def forward(self, frames, out=None):
         """As ICPSLAM.forward; additionally accepts a `gradslam_b200.ingest.RawRGBD` batch (uint8 colour + uint16 depth)
         when odom='gt': the raw frames are uploaded and converted on the device, overlapped with the fusion."""
         from ..ingest import RawRGBD
@@ -69,10 +69,11 @@ class PointFusion(ICPSLAM):
             if self.odom != "gt" or frames.poses is None:
                 raise ValueError("RawRGBD input is supported for odom='gt' with poses; convert with "
                                  "ingest.rgbdimages_from_raw for the other odometry modes")
-            return self._forward_sequence(frames, raw=True)
-        return super().forward(frames)
+            self._check_out(out, frames.shape[0])
+            return self._forward_sequence(frames, raw=True, out=out)
+        return super().forward(frames, out)
 
-    def _forward_sequence(self, frames, chunk: int = 4, raw: bool = False):
+    def _forward_sequence(self, frames, chunk: int = 4, raw: bool = False, out=None):
         """odom='gt': the whole (B, L) sequence runs as C calls chaining K1 -> K2/K3 -> K4 per frame with no
         host synchronisation.  Frames that live in HOST memory are uploaded `chunk` frames at a time on a side
         stream, so the copy of chunk i+1 overlaps the fusion of chunk i (pin the host tensors for this)."""
@@ -87,7 +88,7 @@ class PointFusion(ICPSLAM):
 
                 rgb_f, depth_f = raw_to_float(src_rgb, src_depth, frames.scaling_factor, frames.normalize_color)
                 return self._forward_sequence(RGBDImages(rgb_f, depth_f, frames.intrinsics.to(dev),
-                                                         frames.poses.to(dev)))
+                                                         frames.poses.to(dev)), out=out)
             on_device = False
         else:
             if torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in (
@@ -113,8 +114,14 @@ class PointFusion(ICPSLAM):
                 raw_rgb = torch.empty((B, L, H, W, 3), dtype=torch.uint8, device=dev)
         for t, name in ((depth, "depth_image"), (rgb, "rgb_image"), (K, "intrinsics"), (poses, "poses")):
             _C.require_cuda(t, name)
-        pc = Pointclouds(device=dev)
-        pc._allocate(B, L * P, 1, zero=False)
+        if out is not None:  # caller-provided storage (validated by forward: empty, B maps, this device)
+            if not (out.has_normals and out.has_colors and out._has_cc):
+                raise ValueError("out must have normals, colours and a confidence count per point for map fusion")
+            pc = out
+            pc._cur = 0
+        else:
+            pc = Pointclouds(device=dev)
+            pc._allocate(B, L * P, 1, zero=False)
         ws = _SequenceWorkspace.get(dev, B, H, W)
         main = torch.cuda.current_stream(dev)
         with torch.cuda.device(dev):

@@ -155,7 +155,11 @@ class Pointclouds(object):
     def _set_counts(self, counts: List[int]):
         self._counts_host = [int(c) for c in counts]
         self._bound = max(self._counts_host) if self._counts_host else 0
-        t = torch.tensor([self._counts_host, self._counts_host], dtype=torch.int32, device=self.device)
+        t = torch.tensor([self._counts_host, self._counts_host], dtype=torch.int32)
+        if self.device.type == "cuda":
+            # from pinned memory, asynchronously: a pageable source would synchronise the current stream, i.e. make the
+            # host wait for all fusion work enqueued so far every time a map is (re)started
+            t = t.pin_memory().to(self.device, non_blocking=True)
         self._counts_dev = t
         self._cur = 0
         self._list_cache = {}
@@ -193,6 +197,22 @@ class Pointclouds(object):
         self._B = int(B)
         self._alloc_buffers(capacity, True, True, features_dim, zero)
         self._uninit = not zero
+        self._set_counts([0] * self._B)
+
+    def _attach(self, geo: torch.Tensor, col: torch.Tensor, uninit: bool = True):
+        """Turns an EMPTY object into B empty maps that live in caller-provided row arrays - geometry rows (B, cap, 8)
+        and colour rows (B, cap, 4), dense float32 - e.g. one rank's block of a job-wide store (parallel.GatheredMaps)."""
+        assert not self.has_points
+        if geo.shape[:2] != col.shape[:2] or geo.shape[2] != GEO_W or col.shape[2] != COL_W:
+            raise ValueError("row arrays must be (B, cap, %d) and (B, cap, %d); got %r and %r" % (
+                GEO_W, COL_W, tuple(geo.shape), tuple(col.shape)))
+        if not (geo.is_contiguous() and col.is_contiguous() and geo.dtype == col.dtype == torch.float32):
+            raise ValueError("row arrays must be dense float32")
+        self.device = geo.device
+        self._B = int(geo.shape[0])
+        self._geo, self._col, self._feat = geo, col, None
+        self._has_normals = self._has_cc = True
+        self._uninit = bool(uninit)
         self._set_counts([0] * self._B)
 
     def _overflow_flag(self):

@@ -46,9 +46,22 @@ def _worker(rank, world, port, q):
                       torch.equal(allpc.features_list[rank * B + b], pc.features_list[b]) for b in range(B))
             got[mode] = (counts, own, [t.cpu() for t in allpc.points_list], [t.cpu() for t in allpc.normals_list],
                          [t.cpu() for t in allpc.colors_list], allpc.points_padded.cpu())
+        # job-wide store: the sequences are fused in place into this rank's block, only the peers' rows travel
+        os.environ["GSX_MAP_EXCHANGE"] = "peer"
+        P = H * W
+        store = parallel.GatheredMaps(B, 5 * P, dev)  # room for the longer of the two ranks' sequences
+        for rep in range(2):
+            pc, _ = slam(gs.RGBDImages(rgb.to(dev), depth.to(dev), K.to(dev), poses.to(dev)), out=store.reset())
+            assert pc is store.local
+            allpc = parallel.gather_maps(pc, into=store)
+            torch.cuda.synchronize(dev)
+        assert allpc is store.all
+        got["in_place"] = (allpc.num_points_per_pointcloud.tolist(), True, [t.cpu() for t in allpc.points_list],
+                           [t.cpu() for t in allpc.normals_list], [t.cpu() for t in allpc.colors_list],
+                           allpc.points_padded.cpu())
         ref = got["all_gather"]
         ok = True
-        for mode in ("peer", "p2p"):
+        for mode in ("peer", "p2p", "in_place"):
             g = got[mode]
             ok = ok and g[0] == ref[0] and g[1] and ref[1]
             for k in (2, 3, 4):

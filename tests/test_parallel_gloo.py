@@ -34,6 +34,19 @@ def _worker(rank, world, port, q):
         ok = ok and torch.equal(allpc.points_list[2 * rank], keep[0]) and torch.equal(allpc.points_list[2 * rank + 1], keep[1])
         pad = allpc.points_padded
         ok = ok and pad.shape == (4, 7, 3) and float(pad[0, 3:].abs().sum()) == 0.0
+        # the same maps built inside a job-wide store: only the peer's rows move, the result is the store itself
+        store = parallel.GatheredMaps(2, 9, "cpu")
+        loc = store.reset()
+        for b, n in enumerate(sizes):
+            loc._geo[b, :n] = pc._geo[b, :n]
+            loc._col[b, :n] = pc._col[b, :n]
+        loc._set_counts(sizes)
+        allpc2 = parallel.gather_maps(loc, into=store)
+        ok = ok and allpc2 is store.all and allpc2.num_points_per_pointcloud.tolist() == counts
+        for i in range(4):
+            for name in ("points_list", "normals_list", "colors_list", "features_list"):
+                ok = ok and torch.equal(getattr(allpc2, name)[i], getattr(allpc, name)[i])
+        ok = ok and torch.equal(allpc2.points_padded, pad)
         lo, hi = parallel.shard_batch(5)
         ok = ok and (lo, hi) == ((0, 3) if rank == 0 else (3, 5))
         q.put((rank, bool(ok), counts))
