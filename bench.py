@@ -249,15 +249,21 @@ def main():
     dl_stream = torch.cuda.Stream(device=dev)
     dl_state = {"host": None, "bytes": 0}
 
-    def read_back(pc, poses):
+    def read_back(pc, poses, fused):
         """Result read-back of one step: recovered poses, map sizes and the fused map itself (packed rows, exact sizes)
-        into pinned host memory, on a side stream so that it overlaps the next step's upload and fusion."""
-        dl_stream.wait_stream(torch.cuda.current_stream(dev))
+        into pinned host memory, on a side stream so that it overlaps the next step's upload and fusion.  `fused`: event
+        recorded when that step's fusion had been enqueued (the copies wait for it, not for the step enqueued since)."""
+        dl_stream.wait_event(fused)
+        if dl_state.get("poses") is None:
+            dl_state["poses"] = torch.empty(poses.shape, dtype=poses.dtype, pin_memory=True)
+        with torch.cuda.stream(dl_stream):
+            dl_state["poses"].copy_(poses, non_blocking=True)
+        poses.record_stream(dl_stream)
         host = pc.download(out=dl_state["host"], stream=dl_stream)
         dl_state["host"] = host
         rows = sum(host._host_counts())
         dl_state["bytes"] = rows * (32 + 16) + poses.numel() * 4 + len(host) * 8
-        return host
+        return dl_state["poses"], host
 
     # N > 1: two job-wide stores used alternately; each rank fuses its sequences straight into its block of one of them
     # and pulls the peers' rows into the other blocks (GSX_BENCH_STORE=fresh: a fresh local map and a fresh gathered
@@ -281,19 +287,21 @@ def main():
                 pc, poses = slam(frames, out=store.reset())
             else:
                 pc, poses = slam(frames)
+            fused = torch.cuda.Event()
+            fused.record()
             if pending is not None:  # step k-1's maps travel while step k (just enqueued) computes
                 parallel.gather_maps_end(pending[0], wait=False)
             if d2h and prev is not None:
-                res = (prev[1].cpu(), read_back(*prev))
+                res = read_back(*prev)
             if world > 1 and EXCHANGE_SCHEDULE == "serial":  # diagnostic: the exchange alone on the GPU, then the next step
                 parallel.gather_maps(pc, into=store)
             elif world > 1 and EXCHANGE_SCHEDULE != "none":
                 pending = (parallel.gather_maps_begin(pc, into=store), poses)
-            prev = (pc, poses)
+            prev = (pc, poses, fused)
         if pending is not None:
             parallel.gather_maps_end(pending[0], wait=True)
         if d2h:
-            res = (prev[1].cpu(), read_back(*prev))
+            res = read_back(*prev)
             torch.cuda.current_stream(dev).wait_stream(dl_stream)
         return res
 

@@ -1100,7 +1100,7 @@ extern "C" int64_t gsx_knn1_scratch_bytes(int B, int ns_stride, int nt_stride) {
 
 extern "C" int gsx_knn1(const float *src_points, const int32_t *src_count, int ns_stride, const float *tgt_points,
                         const int32_t *tgt_count, int nt_stride, int B, int64_t *idx_out, float *d2_out,
-                        void *scratch, int64_t scratch_bytes, void *stream) {
+                        void *scratch, int64_t scratch_bytes, int build_grid, void *stream) {
   GSX_CHECK_ARG(src_points && src_count && tgt_points && tgt_count && idx_out && scratch, "gsx_knn1: null pointer");
   GSX_CHECK_ARG(B >= 1 && ns_stride >= 1 && nt_stride >= 1, "gsx_knn1: bad extents");
   const int nblk = (ns_stride + kIcpBlock - 1) / kIcpBlock;
@@ -1113,12 +1113,14 @@ extern "C" int gsx_knn1(const float *src_points, const int32_t *src_count, int n
   const dim3 grid((unsigned)nblk, (unsigned)B);
   if (nt_stride > kGridThreshold) {
     ka.grid = grid_carve((char *)scratch + part, B, nt_stride);
-    const unsigned nb = (unsigned)((nt_stride + 255) / 256);
-    k_grid_bbox<<<B, 256, 0, s>>>(tgt_points, tgt_count, nt_stride, ka.grid);
-    k_grid_clear<<<(unsigned)(((int64_t)B * kGridMaxCells + 255) / 256), 256, 0, s>>>(ka.grid, B);
-    k_grid_count<<<dim3(nb, (unsigned)B), 256, 0, s>>>(tgt_points, tgt_count, nt_stride, ka.grid);
-    k_grid_scan<<<B, 1024, 0, s>>>(ka.grid);
-    k_grid_scatter<<<dim3(nb, (unsigned)B), 256, 0, s>>>(tgt_points, tgt_count, nt_stride, ka.grid);
+    if (build_grid) {  // (0: `scratch` still holds the grid a previous call built for this very target)
+      const unsigned nb = (unsigned)((nt_stride + 255) / 256);
+      k_grid_bbox<<<B, 256, 0, s>>>(tgt_points, tgt_count, nt_stride, ka.grid);
+      k_grid_clear<<<(unsigned)(((int64_t)B * kGridMaxCells + 255) / 256), 256, 0, s>>>(ka.grid, B);
+      k_grid_count<<<dim3(nb, (unsigned)B), 256, 0, s>>>(tgt_points, tgt_count, nt_stride, ka.grid);
+      k_grid_scan<<<B, 1024, 0, s>>>(ka.grid);
+      k_grid_scatter<<<dim3(nb, (unsigned)B), 256, 0, s>>>(tgt_points, tgt_count, nt_stride, ka.grid);
+    }
     k_icp_knn_linearize<true><<<grid, kIcpBlock, 0, s>>>(ka);
   } else {
     k_icp_knn_linearize<false><<<grid, kIcpBlock, 0, s>>>(ka);

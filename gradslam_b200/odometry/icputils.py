@@ -67,24 +67,35 @@ def _counts(n, B, device):
     return torch.full((B,), n, dtype=torch.int32, device=device)
 
 
-def knn1(src: torch.Tensor, tgt: torch.Tensor, src_counts=None, tgt_counts=None):
+def knn1(src: torch.Tensor, tgt: torch.Tensor, src_counts=None, tgt_counts=None, target_cache: Optional[dict] = None):
     """Exact 1-NN of every row of src (B,Ns,3) in tgt (B,Nt,3) (padded clouds: optional int32 sizes (B,); rows beyond a
     source size get idx -1).  Returns (squared distances (B,Ns), idx int64 (B,Ns)); ties resolve to the lowest target
-    index.  CUDA kernel k_icp_knn_linearize."""
+    index.  CUDA kernel k_icp_knn_linearize.
+    target_cache: a dict the caller keeps while it queries the SAME, unmodified target repeatedly (the ICP loop): the
+    search grid of the target is then built by the first call only."""
     _C.require_cuda(src, "src")
     _C.require_cuda(tgt, "tgt")
-    src, tgt = src.contiguous(), tgt.contiguous()
+    src = src.contiguous()
     B, Ns, _ = src.shape
     Nt = tgt.shape[1]
+    key = (tgt.data_ptr(), tuple(tgt.shape), tuple(tgt.stride()), tgt._version, Ns)
+    hit = target_cache is not None and target_cache.get("key") == key
+    if hit:
+        tgt_c, scratch, nt_t = target_cache["tgt"], target_cache["scratch"], target_cache["nt"]
+    else:
+        tgt_c = tgt.contiguous()
+        scratch = torch.empty(_C.lib().gsx_knn1_scratch_bytes(B, Ns, Nt), dtype=torch.uint8, device=src.device)
+        nt_t = _counts(Nt, B, src.device) if tgt_counts is None else tgt_counts
+        if target_cache is not None:
+            target_cache.update(key=key, tgt=tgt_c, scratch=scratch, nt=nt_t)
     # (the kernel writes the rows below each source size; the padding rows keep -1 / inf)
     idx = torch.full((B, Ns), -1, dtype=torch.int64, device=src.device)
     d2 = torch.full((B, Ns), float("inf"), dtype=torch.float32, device=src.device)
-    scratch = torch.empty(_C.lib().gsx_knn1_scratch_bytes(B, Ns, Nt), dtype=torch.uint8, device=src.device)
     ns_t = _counts(Ns, B, src.device) if src_counts is None else src_counts  # (kept alive across the call)
-    nt_t = _counts(Nt, B, src.device) if tgt_counts is None else tgt_counts
     with torch.cuda.device(src.device):
-        rc = _C.lib().gsx_knn1(_C.ptr(src), _C.ptr(ns_t), Ns, _C.ptr(tgt), _C.ptr(nt_t), Nt, B, _C.ptr(idx),
-                               _C.ptr(d2), _C.ptr(scratch), scratch.numel(), _C.stream_ptr(src.device))
+        rc = _C.lib().gsx_knn1(_C.ptr(src), _C.ptr(ns_t), Ns, _C.ptr(tgt_c), _C.ptr(nt_t), Nt, B, _C.ptr(idx),
+                               _C.ptr(d2), _C.ptr(scratch), scratch.numel(), 0 if hit else 1,
+                               _C.stream_ptr(src.device))
     _C.check(rc, "gsx_knn1")
     return d2, idx
 
@@ -425,8 +436,8 @@ class _RigidTransformBatchedFn(torch.autograd.Function):
         return g_p, g_T, None
 
 
-def _normal_equations_batched(src, src_counts, tgt, tgt_n, tgt_counts, dist_thresh):
-    d2, idx = knn1(src.detach(), tgt.detach(), src_counts, tgt_counts)
+def _normal_equations_batched(src, src_counts, tgt, tgt_n, tgt_counts, dist_thresh, target_cache=None):
+    d2, idx = knn1(src.detach(), tgt.detach(), src_counts, tgt_counts, target_cache)
     if dist_thresh is not None:
         idx = torch.where(d2 < dist_thresh, idx, torch.full_like(idx, -1))
     return _NormalEqBatchedFn.apply(src, tgt, tgt_n, idx, src_counts), idx
@@ -442,13 +453,15 @@ def _taped_icp_batched(src, src_counts, tgt, tgt_n, tgt_counts, T0, mode, numite
     dampt = torch.full((Bn,), float(damp), dtype=torch.float32, device=dev)
     T = (torch.eye(4, dtype=torch.float32, device=dev).repeat(Bn, 1, 1) if T0 is None
          else T0.to(torch.float32).expand(Bn, 4, 4).contiguous())
+    tgt, tgt_n = tgt.contiguous(), tgt_n.contiguous()  # once (strided views of packed map rows), not per iteration
     cur = _RigidTransformBatchedFn.apply(src, T, src_counts)
     idx = None
+    grid = {}  # the target's search grid: built by the first of the 2 * numiters associations
     for _ in range(numiters):
-        sums, idx = _normal_equations_batched(cur, src_counts, tgt, tgt_n, tgt_counts, dist_thresh)
+        sums, idx = _normal_equations_batched(cur, src_counts, tgt, tgt_n, tgt_counts, dist_thresh, grid)
         xi, dT = _SolveBatchedFn.apply(sums, dampt)
         one_step = _RigidTransformBatchedFn.apply(cur, dT, src_counts)
-        sums_next, _ = _normal_equations_batched(one_step, src_counts, tgt, tgt_n, tgt_counts, dist_thresh)
+        sums_next, _ = _normal_equations_batched(one_step, src_counts, tgt, tgt_n, tgt_counts, dist_thresh, grid)
         dampt, dT_applied, T = _UpdateBatchedFn.apply(xi, sums[:, 27], sums_next[:, 27], dampt, T, mode, lambda_max, B,
                                                       B2, nu)
         cur = _RigidTransformBatchedFn.apply(cur, dT_applied, src_counts)
@@ -533,11 +546,47 @@ def downsample_pointclouds(pointclouds: Pointclouds, pc2im_bnhw: torch.Tensor, d
         raise ValueError("Expected pc2im_bnhw to have ndim=2. Got {0}.".format(pc2im_bnhw.ndim))
     if pc2im_bnhw.shape[1] != 4:
         raise ValueError("pc2im_bnhw.shape[1] must be 4, but was {0}.".format(pc2im_bnhw.shape[1]))
+    B = len(pointclouds)
+    dev = pc2im_bnhw.device
     t = pc2im_bnhw[(pc2im_bnhw[:, 2] % ds_ratio == 0) & (pc2im_bnhw[:, 3] % ds_ratio == 0)]
-    rows = [t[t[:, 0] == b][:, 1] for b in range(len(pointclouds))]
-    pick = lambda lst: None if lst is None else [lst[b][rows[b]] for b in range(len(pointclouds))]
-    return Pointclouds(points=pick(pointclouds.points_list), normals=pick(pointclouds.normals_list),
-                       colors=pick(pointclouds.colors_list))
+    # all elements at once (the reference loops over b, icputils.py:604-617): element b keeps its rows in table order
+    order = torch.sort(t[:, 0], stable=True).indices
+    b_of, n_of = t[order, 0], t[order, 1]
+    counts_t = torch.bincount(b_of, minlength=B)[:B]
+    counts = [int(c) for c in counts_t.tolist()]  # (the one host synchronisation: the ragged sizes)
+    nmax = max(counts) if counts else 0
+    starts = torch.cumsum(counts_t, 0) - counts_t
+    pos = torch.arange(b_of.numel(), device=dev) - starts[b_of]
+    idx = torch.zeros((B, nmax), dtype=torch.int64, device=dev)
+    idx[b_of, pos] = n_of
+    keep = (torch.arange(nmax, device=dev).unsqueeze(0) < counts_t.unsqueeze(1)).unsqueeze(-1)
+
+    def pick(padded):
+        if padded is None:
+            return None
+        g = torch.gather(padded, 1, idx.unsqueeze(-1).expand(-1, -1, padded.shape[-1]))
+        return torch.where(keep, g, torch.zeros((), dtype=g.dtype, device=g.device))
+
+    out = Pointclouds(points=pick(pointclouds.points_padded), normals=pick(pointclouds.normals_padded),
+                      colors=pick(pointclouds.colors_padded))
+    out._set_counts(counts)
+    return out
+
+
+def _compact_rows(mask: torch.Tensor, values):
+    """mask (B, n) bool, values: tensors (B, n, C).  Per element the selected rows, in their original order, moved to
+    the front of a (B, max count, C) tensor, zeros behind them; returns (tensors, sizes as a host list)."""
+    B, n = mask.shape
+    counts_t = mask.sum(1)
+    counts = [int(c) for c in counts_t.tolist()]  # (the one host synchronisation: the ragged sizes)
+    nmax = max(counts) if counts else 0
+    order = torch.sort((~mask).to(torch.uint8), dim=1, stable=True).indices[:, :nmax]  # selected rows first, in order
+    keep = (torch.arange(nmax, device=mask.device).unsqueeze(0) < counts_t.unsqueeze(1)).unsqueeze(-1)
+    outs = []
+    for v in values:
+        g = torch.gather(v, 1, order.unsqueeze(-1).expand(-1, -1, v.shape[-1]))
+        outs.append(torch.where(keep, g, torch.zeros((), dtype=g.dtype, device=g.device)))
+    return outs, counts
 
 
 def downsample_rgbdimages(rgbdimages: RGBDImages, ds_ratio: int) -> Pointclouds:
@@ -550,9 +599,14 @@ def downsample_rgbdimages(rgbdimages: RGBDImages, ds_ratio: int) -> Pointclouds:
         raise ValueError("Sequence length of rgbdimages must be 1, but was {0}.".format(rgbdimages.shape[1]))
     fr = rgbdimages.to_channels_last()
     B = len(fr)
-    mask = fr.valid_depth_mask.squeeze(-1)[:, 0, ::ds_ratio, ::ds_ratio]
-    sub = lambda m: [m[b, 0, ::ds_ratio, ::ds_ratio][mask[b]] for b in range(B)]
-    return Pointclouds(points=sub(fr.global_vertex_map), normals=sub(fr.global_normal_map), colors=sub(fr.rgb_image))
+    mask = fr.valid_depth_mask.squeeze(-1)[:, 0, ::ds_ratio, ::ds_ratio].reshape(B, -1)
+    sub = lambda m: m[:, 0, ::ds_ratio, ::ds_ratio].reshape(B, -1, m.shape[-1])
+    # all elements at once (the reference indexes element by element, icputils.py:655-667)
+    (pts, nrm, col), counts = _compact_rows(mask, [sub(fr.global_vertex_map), sub(fr.global_normal_map),
+                                                    sub(fr.rgb_image)])
+    out = Pointclouds(points=pts, normals=nrm, colors=col)
+    out._set_counts(counts)
+    return out
 
 
 # --------------------------------------------------------------------------------------------- fused localisation

@@ -14,6 +14,7 @@ output store, no zero fill on either side.  Three transports (see _exchange_mode
   all_gather  one NCCL all-gather per row array on `[:, :nmax]` staging copies (also the CPU / gloo path of the tests).
   p2p         grouped exact-size NCCL send / recv straight out of the stores.
 """
+import os
 from typing import Optional
 
 import torch
@@ -30,7 +31,6 @@ def bind_host_to_gpu(device) -> Optional[str]:
     host buffers it allocates afterwards - the upload source and the map read-back target - are placed in that node's
     memory and the PCIe traffic of the ranks does not cross the socket interconnect.  Returns the core list that was
     applied, or None if the topology is not exposed (the affinity is then left alone)."""
-    import os
 
     try:
         prop = torch.cuda.get_device_properties(torch.device(device))
@@ -62,6 +62,7 @@ def shard_batch(total: int, rank: Optional[int] = None, world: Optional[int] = N
 
 
 _COMM_STREAMS = {}
+_CONTROL_GROUPS = {}
 
 
 def _comm_stream(device):
@@ -69,8 +70,28 @@ def _comm_stream(device):
         return None
     key = str(device)
     if key not in _COMM_STREAMS:
-        _COMM_STREAMS[key] = torch.cuda.Stream(device=device)
+        _COMM_STREAMS[key] = torch.cuda.Stream(device=device, priority=-1)
     return _COMM_STREAMS[key]
+
+
+def _control_group(group, device):
+    """The process group the exchange's two tiny collectives (sizes + store descriptors before the pulls, the one-word
+    release after them) run on: the same ranks as `group`, but a communicator whose kernels are launched on a
+    HIGH-PRIORITY stream.  On an ordinary stream a NCCL kernel queues behind the thousands of thread blocks the two
+    fusion streams keep pending and only gets onto an SM when a step drains - measured at 2 GPUs: the size all-gather of
+    step k completed at the END of step k+1, the host (waiting for the sizes) enqueued step k+2 late, and the GPU idled
+    0.8 ms per step.  Created once per group (a collective call: every rank reaches gather_maps_begin)."""
+    if device.type != "cuda" or os.environ.get("GSX_EXCHANGE_PRIORITY", "high") != "high":
+        return group
+    key = (id(group) if group is not None else None, str(device))
+    if key not in _CONTROL_GROUPS:
+        from torch.distributed import ProcessGroupNCCL
+
+        opts = ProcessGroupNCCL.Options()
+        opts.is_high_priority_stream = True
+        ranks = None if group is None else dist.get_process_group_ranks(group)
+        _CONTROL_GROUPS[key] = dist.new_group(ranks=ranks, backend="nccl", pg_options=opts, device_id=device)
+    return _CONTROL_GROUPS[key]
 
 
 class _GatherHandle:
@@ -173,7 +194,7 @@ def gather_maps_begin(pointclouds: Pointclouds, group=None, into: Optional[Gathe
         if meta is not None:  # sizes and store descriptors travel in the same small all-gather
             send = torch.cat([send, meta.to(dev, non_blocking=True)])
         all_counts = torch.empty(h.world * (B + h.meta_len), dtype=torch.int64, device=dev)
-        _all_gather(all_counts, send, group)
+        _all_gather(all_counts, send, _control_group(group, dev))
         if h.stream is not None:
             h.counts_host = torch.empty(h.world * (B + h.meta_len), dtype=torch.int64, pin_memory=True)
             h.counts_host.copy_(all_counts, non_blocking=True)
@@ -247,7 +268,6 @@ def gather_maps_end(h: "_GatherHandle", wait: bool = True) -> Pointclouds:
 def _exchange_mode(device=None):
     """GSX_MAP_EXCHANGE = peer | all_gather | p2p.  On CUDA the default is `peer` (copy-engine pulls through IPC mappings);
     CPU tensors (the gloo tests) always use all_gather.  Measured numbers: DESIGN.md section 7."""
-    import os
 
     if device is not None and torch.device(device).type != "cuda":
         return "all_gather"
@@ -290,11 +310,20 @@ def _exchange_peer(pc, out, counts, meta, rank, world, B, group, stream, skip_ow
                     sptr = ctypes.c_void_p()
                     handle = (ctypes.c_ubyte * 64).from_buffer_copy(struct.pack("8q", *words[2:]))
                     _C.check(lib.gsx_peer_open(handle, words[1], ctypes.byref(sptr)), "gsx_peer_open")
-                _C.check(lib.gsx_peer_copy_rows(ctypes.c_void_p(dst.data_ptr() + q * B * pitch_rows * row),
-                                                pitch_rows * row, sptr, cap_q * row, nq * row, B, sp),
-                         "gsx_peer_copy_rows")
+                how = os.environ.get("GSX_PEER_COPY", "2d")  # diagnostic: 2d (one pitched copy) | 1d (per element) | none
+                if how == "2d":
+                    _C.check(lib.gsx_peer_copy_rows(ctypes.c_void_p(dst.data_ptr() + q * B * pitch_rows * row),
+                                                    pitch_rows * row, sptr, cap_q * row, nq * row, B, sp),
+                             "gsx_peer_copy_rows")
+                elif how == "1d":
+                    for b in range(B):
+                        c = counts[q * B + b]
+                        _C.check(lib.gsx_peer_copy_rows(
+                            ctypes.c_void_p(dst.data_ptr() + (q * B + b) * pitch_rows * row), pitch_rows * row,
+                            ctypes.c_void_p(sptr.value + b * cap_q * row), cap_q * row, c * row, 1, sp),
+                            "gsx_peer_copy_rows")
     token = torch.zeros(1, dtype=torch.int32, device=dev)
-    dist.all_reduce(token, group=group)
+    dist.all_reduce(token, group=_control_group(group, dev))
     token.record_stream(stream)
 
 

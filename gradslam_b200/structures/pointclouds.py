@@ -165,12 +165,29 @@ class Pointclouds(object):
         self._list_cache = {}
         self._tail_dirty = self._uninit
 
-    def _host_counts(self) -> List[int]:
-        """Per-element sizes on the host; synchronises with the device only if kernels changed them."""
+    def _host_counts(self, stream=None) -> List[int]:
+        """Per-element sizes on the host; synchronises with the device only if kernels changed them.  stream: read them
+        (and the overflow flag) through this CUDA stream and wait for IT only - the caller has ordered it after the
+        kernels that produced this map - instead of the current stream, which may already hold later work."""
         if self._counts_host is None:
-            self._counts_host = [int(c) for c in self._counts_dev[self._cur].tolist()]
-            self._bound = max(self._counts_host)
-            self._check_overflow()
+            if stream is not None and self._counts_dev.is_cuda:
+                with torch.cuda.stream(stream):
+                    host = torch.empty(self._B + 1, dtype=torch.int32, pin_memory=True)
+                    host[: self._B].copy_(self._counts_dev[self._cur], non_blocking=True)
+                    if self._overflow is not None:
+                        host[self._B:].copy_(self._overflow, non_blocking=True)
+                    else:
+                        host[self._B] = 0
+                stream.synchronize()
+                vals = host.tolist()
+                self._counts_host = [int(c) for c in vals[: self._B]]
+                self._bound = max(self._counts_host)
+                if vals[self._B] != 0:
+                    raise RuntimeError("gradslam_b200: surfel map capacity exceeded; points were dropped")
+            else:
+                self._counts_host = [int(c) for c in self._counts_dev[self._cur].tolist()]
+                self._bound = max(self._counts_host)
+                self._check_overflow()
         return self._counts_host
 
     def _check_overflow(self):
@@ -576,10 +593,10 @@ class Pointclouds(object):
         """Asynchronous read-back of the populated rows into PINNED host memory: returns a CPU Pointclouds (same packed
         layout) whose buffers are filled by device-to-host copies enqueued on `stream` (default: the current stream) -
         synchronise that stream before touching the result.  Pass the previous result as `out` to re-use its pinned
-        buffers.  One host synchronisation (the map sizes) precedes the copies."""
+        buffers.  One host synchronisation (the map sizes, read through `stream`) precedes the copies."""
         if not self.has_points:
             return Pointclouds()
-        counts = self._host_counts()
+        counts = self._host_counts(stream)
         n = max(max(counts), 1)
         if out is None or out._geo is None or out._geo.shape[1] < n or out._B != self._B:
             cap = int(n * 1.05) + 1

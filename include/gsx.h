@@ -250,11 +250,13 @@ int gsx_records_from_table(const int64_t *table, int64_t rows, int64_t capacity,
  * empty target), d2_out squared distance (may be NULL).  scratch: gsx_knn1_scratch_bytes bytes.
  * Target clouds with nt_stride > 4096 are binned into a uniform grid and searched ring by ring with an exact
  * termination bound (full scan as the fallback); smaller ones are scanned from shared memory.  Both return
- * the same (distance, index): candidates are ordered by (squared distance, index). */
+ * the same (distance, index): candidates are ordered by (squared distance, index).
+ * build_grid: 1 = bin the target into `scratch` first; 0 = `scratch` still holds the grid that an earlier call built
+ * for the same target (the ICP loop queries one target 2 x numiters times). */
 int64_t gsx_knn1_scratch_bytes(int B, int ns_stride, int nt_stride);
 int gsx_knn1(const float *src_points, const int32_t *src_count, int ns_stride, const float *tgt_points,
              const int32_t *tgt_count, int nt_stride, int B, int64_t *idx_out, float *d2_out, void *scratch,
-             int64_t scratch_bytes, void *stream);
+             int64_t scratch_bytes, int build_grid, void *stream);
 
 /* K6 as a differentiable op: for a GIVEN association nn_idx (int64 (ns), -1 = row unused) reduce the point-to-plane
  * rows A_i = [n, s x n], r_i = n.(p - s) (gauss_newton_solve, icputils.py:210-230) to the 28 sums
