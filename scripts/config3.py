@@ -12,7 +12,7 @@ from gradslam_b200.synthetic import make_sequence
 
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 8
 dev = torch.device("cuda:0")
-rgb, depth, K, poses = make_sequence(B, 2, 480, 640, seed=0, yaw0=0.6)
+rgb, depth, K, poses = make_sequence(B, 2, 480, 640, seed=0, yaw0=0.6)  # (the timings below include the upload; see config3_breakdown.py)
 d = depth.to(dev).requires_grad_(True)
 p = poses.to(dev).requires_grad_(True)
 slam = gs.ICPSLAM(odom="gradicp", numiters=10, dsratio=4, device=dev)
