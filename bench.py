@@ -44,6 +44,7 @@ def parse():
     ap.add_argument("--no-extra-configs", action="store_true", help="skip the B=1 / L=32 (config 2) line")
     ap.add_argument("--no-icp", action="store_true", help="skip the secondary ICP-odometry measurement")
     ap.add_argument("--no-raw", action="store_true", help="skip the dataset-native (uint8/uint16) ingest measurement")
+    ap.add_argument("--no-e2e", action="store_true", help="diagnostic runs only: skip the end-to-end leg (e2e = null)")
     return ap.parse_args()
 
 
@@ -337,8 +338,11 @@ def main():
         sampler.start()
     ms_dev, all_dev, _ = timed_median(frames_dev, args.steps, False, repeats)
     clocks = sampler.stop() if rank == 0 else None
-    run_steps(frames_host, 3, d2h=True)
-    ms_e2e, all_e2e, res = timed_median(frames_host, args.steps, True, repeats)
+    if args.no_e2e:
+        ms_e2e, all_e2e = float("nan"), []
+    else:
+        run_steps(frames_host, 3, d2h=True)
+        ms_e2e, all_e2e, res = timed_median(frames_host, args.steps, True, repeats)
 
     # extra: the same job fed in dataset-native form (uint8 colour + uint16 depth, 5 B/pixel over PCIe instead of 16)
     raw_extra = None
@@ -501,7 +505,8 @@ def main():
             "warmup": max(args.warmup, 3), "ms_per_step": ms_dev / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": workload_config(args, world),
-            "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+            "e2e": None if args.no_e2e else {
+                    "value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": ms_e2e / args.steps,
                     "result": "poses + map sizes + the fused map of this rank (packed rows, exact sizes) into pinned "
                               "host memory, overlapped with the next step",

