@@ -189,8 +189,10 @@ def workload_config(args, world):
                         args.width, args.height, args.batch, args.seqlen),
         "global_batch": args.batch * world, "seq_len": args.seqlen, "height": args.height, "width": args.width,
         "frames_per_step": args.batch * world * args.seqlen, "parallelism": "batch-sharded x%d" % world,
-        "map_exchange": None if world == 1 else "%s (%s)" % (os.environ.get("GSX_MAP_EXCHANGE", "peer"),
-                                                               EXCHANGE_SCHEDULE),
+        "map_exchange": None if world == 1 else "%s (%s)" % (
+            {2: "peer pulls over CUDA IPC, job-wide store"}.get(world, "NCCL all-gather of the packed row arrays")
+            if os.environ.get("GSX_MAP_EXCHANGE", "auto") == "auto" else os.environ["GSX_MAP_EXCHANGE"],
+            EXCHANGE_SCHEDULE),
         "l2_policy": "inputs (%.0f MB depth+rgb per GPU per step) exceed the 126 MB L2" % (
             args.batch * args.seqlen * args.height * args.width * 16 / 1e6),
     }
@@ -270,7 +272,8 @@ def main():
     # and pulls the peers' rows into the other blocks (GSX_BENCH_STORE=fresh: a fresh local map and a fresh gathered
     # store per step, own rows copied - the round-1 behaviour, for comparison)
     stores = []
-    if world > 1 and os.environ.get("GSX_BENCH_STORE", "shared") == "shared":
+    exchange = parallel.exchange_mode(dev) if world > 1 else None
+    if world > 1 and os.environ.get("GSX_BENCH_STORE", "shared" if exchange == "peer" else "fresh") == "shared":
         stores = [parallel.GatheredMaps(B, L * H * W, dev) for _ in range(2)]
 
     def run_steps(frames, steps, d2h):

@@ -23,7 +23,7 @@ import torch.distributed as dist
 from .structures.pointclouds import Pointclouds
 
 __all__ = ["shard_batch", "gather_maps", "gather_maps_begin", "gather_maps_end", "comm_stream", "bind_host_to_gpu",
-           "GatheredMaps"]
+           "GatheredMaps", "exchange_mode"]
 
 
 def bind_host_to_gpu(device) -> Optional[str]:
@@ -182,7 +182,7 @@ def gather_maps_begin(pointclouds: Pointclouds, group=None, into: Optional[Gathe
         import contextlib
 
         ctx = contextlib.nullcontext()
-    h.mode = _exchange_mode(dev)
+    h.mode = _exchange_mode(dev, h.world)
     h.meta_len = 0
     meta = None
     if h.mode == "peer":
@@ -265,16 +265,26 @@ def gather_maps_end(h: "_GatherHandle", wait: bool = True) -> Pointclouds:
     return out
 
 
-def _exchange_mode(device=None):
-    """GSX_MAP_EXCHANGE = peer | all_gather | p2p.  On CUDA the default is `peer` (copy-engine pulls through IPC mappings);
-    CPU tensors (the gloo tests) always use all_gather.  Measured numbers: DESIGN.md section 7."""
-
+def _exchange_mode(device=None, world=None):
+    """GSX_MAP_EXCHANGE = auto | peer | all_gather | p2p.  CPU tensors (the gloo tests) always use all_gather.  `auto`
+    (default) follows the measurements of DESIGN.md section 7: copy-engine pulls between TWO GPUs (7.16 ms per step against
+    8.02 for the collective), NCCL all-gather beyond (4 GPUs: 7.73 ms against 8.26 for the pulls - NCCL's ring keeps one
+    sender per receiver and, on NVSwitch, can multicast; the serial pulls of one rank cost the concurrent fusion kernels
+    more than they cost NCCL's throttled copy kernels)."""
     if device is not None and torch.device(device).type != "cuda":
         return "all_gather"
-    mode = os.environ.get("GSX_MAP_EXCHANGE", "peer")
-    if mode not in ("peer", "all_gather", "p2p"):
-        raise ValueError("GSX_MAP_EXCHANGE must be peer, all_gather or p2p (got %r)" % mode)
+    mode = os.environ.get("GSX_MAP_EXCHANGE", "auto")
+    if mode not in ("auto", "peer", "all_gather", "p2p"):
+        raise ValueError("GSX_MAP_EXCHANGE must be auto, peer, all_gather or p2p (got %r)" % mode)
+    if mode == "auto":
+        world = dist.get_world_size() if world is None else world
+        mode = "peer" if world == 2 else "all_gather"
     return mode
+
+
+def exchange_mode(device, group=None) -> str:
+    """The transport gather_maps will use for maps on `device` in `group` (see _exchange_mode)."""
+    return _exchange_mode(device, dist.get_world_size(group))
 
 
 def _exchange_peer(pc, out, counts, meta, rank, world, B, group, stream, skip_own=False):
