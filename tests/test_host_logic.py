@@ -342,3 +342,81 @@ def test_downsample_pointclouds_known_answer():
     ds2 = downsample_pointclouds(Pointclouds(pts), table, 2)
     assert torch.equal(ds2.points_padded, torch.tensor([[5.0, 5, 5], [3, 3, 3]]).unsqueeze(0))
     assert ds2.normals_padded is None and ds2.colors_padded is None
+
+
+def test_batched_downsample_pointclouds_matches_per_element_indexing():
+    """downsample_pointclouds selects all elements at once; the result must equal the reference's per-element boolean
+    indexing (icputils.py:604-617), including an empty element, an unsorted table and zero padding."""
+    import torch
+
+    import gradslam_b200 as gs
+    from gradslam_b200.odometry.icputils import downsample_pointclouds
+
+    g = torch.Generator().manual_seed(5)
+    sizes = [40, 0, 65]
+    mk = lambda c: [torch.rand(n, c, generator=g) for n in sizes]
+    pc = gs.Pointclouds(mk(3), mk(3), mk(3))
+    rows = []
+    for b, n in enumerate(sizes):
+        for i in range(n):
+            if torch.rand((), generator=g) < 0.6:
+                rows.append([b, i, int(torch.randint(0, 12, (), generator=g)), int(torch.randint(0, 12, (), generator=g))])
+    table = torch.tensor(rows)
+    table = table[torch.randperm(table.shape[0], generator=g)]  # element blocks interleaved
+    ds = 3
+    out = downsample_pointclouds(pc, table, ds)
+    kept = table[(table[:, 2] % ds == 0) & (table[:, 3] % ds == 0)]
+    for b in range(len(sizes)):
+        sel = kept[kept[:, 0] == b][:, 1]
+        for name in ("points_list", "normals_list", "colors_list"):
+            assert torch.equal(getattr(out, name)[b], getattr(pc, name)[b][sel]), (name, b)
+        n = int(out.num_points_per_pointcloud[b])
+        assert n == sel.numel() and float(out.points_padded[b, n:].abs().sum()) == 0.0
+    # no row survives
+    empty = downsample_pointclouds(pc, table[:0], ds)
+    assert empty.num_points_per_pointcloud.tolist() == [0, 0, 0]
+
+
+def test_compact_rows_is_stable_and_differentiable():
+    import torch
+
+    from gradslam_b200.odometry.icputils import _compact_rows
+
+    g = torch.Generator().manual_seed(2)
+    mask = torch.rand(5, 37, generator=g) < 0.35
+    mask[3] = False
+    v = torch.rand(5, 37, 3, generator=g, requires_grad=True)
+    (out,), counts = _compact_rows(mask, [v])
+    assert counts == mask.sum(1).tolist() and out.shape == (5, max(counts), 3)
+    for b in range(5):
+        assert torch.equal(out[b, : counts[b]], v[b][mask[b]])
+        assert float(out[b, counts[b]:].abs().sum()) == 0.0
+    out.sum().backward()
+    assert torch.equal(v.grad, mask.unsqueeze(-1).expand(-1, -1, 3).float())
+
+
+def test_exchange_mode_selection(monkeypatch):
+    from gradslam_b200 import parallel
+
+    monkeypatch.delenv("GSX_MAP_EXCHANGE", raising=False)
+    assert parallel._exchange_mode("cpu", 2) == "all_gather"  # gloo tests
+    assert parallel._exchange_mode("cuda:0", 2) == "peer"
+    assert parallel._exchange_mode("cuda:0", 4) == "all_gather"
+    assert parallel._exchange_mode("cuda:0", 8) == "all_gather"
+    monkeypatch.setenv("GSX_MAP_EXCHANGE", "p2p")
+    assert parallel._exchange_mode("cuda:0", 8) == "p2p"
+    monkeypatch.setenv("GSX_MAP_EXCHANGE", "bogus")
+    import pytest
+
+    with pytest.raises(ValueError):
+        parallel._exchange_mode("cuda:0", 2)
+
+
+def test_bind_host_to_gpu_is_harmless_without_a_gpu():
+    import os
+
+    from gradslam_b200 import parallel
+
+    before = os.sched_getaffinity(0)
+    assert parallel.bind_host_to_gpu("cuda:0") is None or os.sched_getaffinity(0) <= before
+    os.sched_setaffinity(0, before)
