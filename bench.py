@@ -493,6 +493,82 @@ def main():
                        "us_per_frame": 1e3 * ms1 / L,
                        "vs_batched_per_frame": (ms1 / L) / ((ms_dev / args.steps) / (B * L))}
 
+    # The other BASELINE.json configurations, so that they appear in a driver-run line (each guarded: a failure is
+    # reported as {"error": ...} and never costs the headline).  configs[2]: ICPSLAM 640x480, 10 iterations, batch 8,
+    # forward + backward; configs[3]: PointFusion 64-frame sequences, 4 per GPU (this GPU's share of the 32-sequence job);
+    # configs[4]: PointFusion 1280x960, batch 8.
+    other_configs = None
+    if rank == 0 and world == 1 and not args.no_extra_configs:
+        other_configs = {}
+
+        def per_call_ms(fn, calls, warm=2):
+            for _ in range(warm):
+                fn()
+            torch.cuda.synchronize(dev)
+            a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(calls):
+                fn()
+            b_.record()
+            torch.cuda.synchronize(dev)
+            return a.elapsed_time(b_) / calls
+
+        try:
+            r3, d3, K3, p3 = make_sequence(B, 2, H, W, seed=0, yaw0=0.6)
+            r3, K3 = r3.to(dev), K3.to(dev)
+            d3g, p3g = d3.to(dev).requires_grad_(True), p3.to(dev).requires_grad_(True)
+            icpslam = gs.ICPSLAM(odom="gradicp", numiters=10, dsratio=4, device=dev)
+            fwd_ms = bwd_ms = 0.0
+            calls = 5
+            for it in range(2 + calls):
+                d3g.grad = p3g.grad = None
+                ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+                ev[0].record()
+                _, rec3 = icpslam(gs.RGBDImages(r3, d3g, K3, p3g))
+                ev[1].record()
+                rec3.sum().backward()
+                ev[2].record()
+                torch.cuda.synchronize(dev)
+                if it >= 2:
+                    fwd_ms += ev[0].elapsed_time(ev[1]) / calls
+                    bwd_ms += ev[1].elapsed_time(ev[2]) / calls
+            with torch.no_grad():
+                fr3 = gs.RGBDImages(r3, d3g.detach(), K3, p3g.detach())
+                fused_ms = per_call_ms(lambda: icpslam(fr3), calls)
+                _, rec3f = icpslam(fr3)
+            other_configs["config3_icpslam_fwd_bwd"] = {
+                "workload": "ICPSLAM(odom='gradicp', numiters=10, dsratio=4) %dx%d B=%d L=2, inputs resident, "
+                            "loss = poses.sum()" % (W, H, B),
+                "forward_ms": fwd_ms, "backward_ms": bwd_ms, "fused_no_grad_forward_ms": fused_ms,
+                "grads_finite": bool(torch.isfinite(d3g.grad).all() and torch.isfinite(p3g.grad).all()),
+                "max_abs_pose_diff_fused_vs_differentiable": float((rec3f - rec3.detach()).abs().max()),
+                "max_abs_pose_error_vs_gt": float((rec3.detach().cpu() - p3).abs().max())}
+            del r3, d3, K3, p3, d3g, p3g, fr3, rec3, rec3f
+        except Exception as exc:  # noqa: BLE001 - reported, not fatal
+            other_configs["config3_icpslam_fwd_bwd"] = {"error": repr(exc)[:300]}
+        for key, (Bc, Lc, Hc, Wc), what in (
+                ("config4_b4_l64_per_gpu", (4, 64, H, W), "configs[3]: 64-frame sequences, 4 per GPU; each is two of the "
+                 "bench's 32-frame trajectories through the same room back to back, i.e. the second half revisits"),
+                ("config5_1280x960_b8", (8, 4, 960, 1280), "configs[4]: 1280x960, batch 8 (L=4)")):
+            try:
+                if key.startswith("config4") and B >= 8 and L * 2 == Lc:
+                    half = B // 2
+                    rc_, dc_, pc_ = (torch.cat([t[:half], t[half: 2 * half]], dim=1).contiguous()[:Bc]
+                                     for t in (rgb_d, depth_d, poses_d))
+                    Kc_ = K_d[:Bc].contiguous()
+                else:
+                    rc_, dc_, Kc_, pc_ = (t.to(dev) for t in make_sequence(Bc, Lc, Hc, Wc, seed=7))
+                frc = gs.RGBDImages(rc_, dc_, Kc_, pc_)
+                msc = per_call_ms(lambda: slam(frc), 5)
+                other_configs[key] = {"workload": "PointFusion(odom='gt') %dx%d B=%d L=%d, 1 GPU, forward, inputs "
+                                                  "resident (%s)" % (Wc, Hc, Bc, Lc, what),
+                                      "frames_per_s": Bc * Lc / msc * 1e3, "ms_per_step": msc,
+                                      "us_per_frame_per_sequence": 1e3 * msc / Lc}
+                del rc_, dc_, Kc_, pc_, frc
+            except Exception as exc:  # noqa: BLE001
+                other_configs[key] = {"error": repr(exc)[:300]}
+        torch.cuda.empty_cache()
+
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         fps, dt, cores, _ = cpu_reference_run(1, args.cpu_sample_frames, H, W)
@@ -519,6 +595,7 @@ def main():
             "repeats": repeats, "timed_regions_ms": all_dev,
             "roofline": roofline, "cpu_baseline": cpu_baseline, "clocks": clocks, "kernels": kernels,
             "icp_odometry": icp_extra, "e2e_raw_ingest": raw_extra, "config2_b1_l32": small_extra,
+            "other_configs": other_configs,
             "final_map_points_per_sequence": (frames_info[-1]["map_points"] + frames_info[-1]["new"]) // B
             if frames_info else None,
         }
