@@ -5,7 +5,8 @@ contiguous blocks of B_total / world sequences per rank, one process per GPU, an
 while the L frames are fused.  The only exchange is at the end: an all-gather of the per-sequence sizes
 followed by a variable-length all-gather of the fused maps, after which every rank holds all B_total maps.  The maps
 travel as they are stored - packed geometry rows (8 floats) and colour rows (4 floats) - and are received in place in the
-output store, no zero fill on either side.  Three transports (see _exchange_mode):
+output store, no zero fill on either side.  Three transports; GSX_MAP_EXCHANGE=auto (default) takes `peer` between two
+GPUs and `all_gather` beyond, as measured (see _exchange_mode):
 
   peer        each rank PULLS its peers' rows out of their stores (CUDA IPC mappings) with one pitched copy per peer and
               row array, executed by the copy engines over NVLink: no communication kernel on any SM, no staging copy
