@@ -12,6 +12,9 @@ GPUs and `all_gather` beyond, as measured (see _exchange_mode, DESIGN.md section
               row array, executed by the copy engines over NVLink: no communication kernel on any SM, no staging copy
               (csrc/gsx_peer.cu).  The size all-gather before the pulls orders them after the owners' fusion; a one-word
               all-reduce after them releases the owners' stores.
+              Requires all ranks on ONE node and stores from cudaMalloc-backed allocations (PyTorch's default caching
+              allocator; not `expandable_segments`) - gsx_peer_export / gsx_peer_open raise otherwise; select
+              GSX_MAP_EXCHANGE=all_gather there.
   all_gather  one NCCL all-gather per row array on `[:, :nmax]` staging copies (also the CPU / gloo path of the tests).
   p2p         grouped exact-size NCCL send / recv straight out of the stores.
 """
