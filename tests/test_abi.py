@@ -44,3 +44,25 @@ def test_no_oracle_import_in_product_package():
             if f.endswith(".py"):
                 src = open(os.path.join(dirpath, f)).read()
                 assert "gsx_oracle" not in src and "import oracle" not in src, os.path.join(dirpath, f)
+
+
+def test_peer_entry_points_check_their_arguments_without_a_gpu():
+    """gsx_peer_*: argument validation happens before any CUDA call, so it is testable here."""
+    import ctypes
+
+    from gradslam_b200 import _C
+
+    lib = _C.lib()
+    buf = (ctypes.c_ubyte * 64)()
+    off = ctypes.c_int64(0)
+    assert lib.gsx_peer_export(None, buf, ctypes.byref(off), None) != 0
+    assert b"gsx_peer_export" in lib.gsx_last_error()
+    out = ctypes.c_void_p()
+    assert lib.gsx_peer_open(None, 0, ctypes.byref(out)) != 0
+    assert lib.gsx_peer_open(buf, -1, ctypes.byref(out)) != 0
+    # a block wider than a pitch would overlap the next block
+    assert lib.gsx_peer_copy_rows(ctypes.c_void_p(16), 32, ctypes.c_void_p(16), 64, 48, 2, None) != 0
+    assert b"gsx_peer_copy_rows" in lib.gsx_last_error()
+    # nothing to move is not an error (and touches no pointer)
+    assert lib.gsx_peer_copy_rows(None, 32, None, 32, 0, 4, None) == 0
+    assert lib.gsx_peer_close_all() == 0
